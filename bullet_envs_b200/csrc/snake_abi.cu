@@ -1,0 +1,302 @@
+// snake_abi.cu -- the extern "C" boundary declared in include/snake_b200.h (host side).
+//
+// Owns: the [N,64] fp32 state array, the fp32 model tables, four device counters and (for the
+// *_host entry points) pinned staging buffers plus their device twins.  Everything else belongs to
+// the caller.  No CPU fallback: every entry point either enqueues CUDA work or fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "snake_step.cuh"
+
+size_t snk_step_smem_bytes();
+cudaError_t snk_configure_kernels();
+cudaError_t snk_launch_step(const DevTables* T, const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
+                            int32_t* ticks, unsigned long long* counters, int64_t n, cudaStream_t st);
+cudaError_t snk_launch_tick(const DevTables* T, const KParams& P, float* state, const float* targets, unsigned long long* counters, int64_t n,
+                            int n_ticks, cudaStream_t st);
+cudaError_t snk_launch_reset(const KParams& P, float* state, const uint8_t* mask, float* obs, int64_t n, int mode, cudaStream_t st);
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* detail = "") {
+    snprintf(g_err, sizeof g_err, fmt, detail);
+    return code;
+}
+#define CU(call)                                                                  \
+    do {                                                                          \
+        cudaError_t e_ = (call);                                                  \
+        if (e_ != cudaSuccess) return fail(SNK_E_CUDA, #call ": %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+struct snk_handle {
+    int device;
+    int64_t n;
+    KParams P;
+    DevTables* T;                 // device
+    float* state;                 // device [n,64]
+    unsigned long long* counters; // device [4]
+    int64_t launches;
+    // staging for the *_host entry points (allocated on first use)
+    cudaStream_t hstream;
+    float *h_act, *h_obs, *h_rew; // pinned
+    uint8_t *h_done, *h_mask;
+    int32_t* h_ticks;
+    float *d_act, *d_obs, *d_rew; // device twins
+    uint8_t *d_done, *d_mask;
+    int32_t* d_ticks;
+    bool staged;
+};
+
+static void to_tables(const snk_model* M, DevTables* T) {
+    memset(T, 0, sizeof *T);
+    for (int i = 0; i < NJ; i++) {
+        for (int k = 0; k < 9; k++) T->jR0[i][k] = (float)M->joint_R0[i][k];
+        for (int k = 0; k < 3; k++) { T->jt[i][k] = (float)M->joint_t[i][k]; T->jax[i][k] = (float)M->joint_axis[i][k]; }
+        T->jdamp[i] = (float)M->joint_damping[i];
+    }
+    for (int b = 0; b < NB; b++) {
+        T->mass[b] = (float)M->body_mass[b];
+        for (int k = 0; k < 3; k++) { T->com[b][k] = (float)M->body_com[b][k]; T->hpt[b][k] = (float)M->height_pt[b][k]; }
+        for (int k = 0; k < 9; k++) T->Ic[b][k] = (float)M->body_inertia[b][k];
+        T->hbody[b] = M->height_body[b];
+    }
+    for (int c = 0; c < NC; c++) {
+        for (int k = 0; k < 3; k++) { T->ccen[c][k] = (float)M->cyl_center[c][k]; T->cax[c][k] = (float)M->cyl_axis[c][k]; }
+        for (int k = 0; k < 9; k++) T->cfr[c][k] = (float)M->cyl_fric_R[c][k];
+        T->crad[c] = (float)M->cyl_radius[c]; T->chl[c] = (float)M->cyl_halflen[c]; T->cend[c] = (float)M->cyl_end[c];
+        T->cmar[c] = (float)M->cyl_margin[c]; T->cbrk[c] = (float)M->cyl_break[c];
+        T->cbody[c] = M->cyl_body[c];
+    }
+    for (int k = 0; k < 3; k++) T->fzax[k] = (float)M->fz_axis[k];
+    T->rootm = (float)M->root_mass;
+}
+
+static void to_kparams(const snk_params* p, KParams* P) {
+    memset(P, 0, sizeof *P);
+    P->dt = (float)p->dt; P->inv_dt = (float)(1.0 / p->dt);
+    for (int k = 0; k < 3; k++) { P->g[k] = (float)p->gravity[k]; P->aniso[k] = (float)p->aniso[k]; }
+    P->kp = (float)p->motor_kp; P->kd = (float)p->motor_kd;
+    P->maximp = isinf(p->motor_max_force) ? INFINITY : (float)(p->motor_max_force * p->dt);
+    P->sf = (float)p->scaling_factor; P->alpha = (float)p->alpha; P->beta = (float)p->beta; P->gamma = (float)p->gamma;
+    P->edt = (float)p->energy_dt; P->mu = (float)p->friction; P->kl = (float)p->lin_damping; P->ka = (float)p->ang_damping;
+    P->erp2 = (float)p->erp2; P->slop = (float)p->linear_slop; P->resthr = (float)p->residual_threshold;
+    P->maxvel = (float)p->max_coord_vel; P->errthr = (float)p->err_threshold; P->hthr = (float)p->height_threshold;
+    P->tang = (float)p->term_angle; P->donepen = (float)p->done_penalty; P->colf = (float)p->collision_force;
+    P->colpen = (float)p->collision_penalty; P->iters = p->solver_iterations; P->maxticks = p->max_ticks;
+    P->gait = p->gait_selection; P->cone = p->cone_friction; P->tjoint = p->term_joint; P->stale = p->stale_obs_on_reset;
+    P->altmotor = p->alternate_motor_order;
+    P->actdim = (p->gait_selection == 0 || p->gait_selection == 1) ? NJ / 2 : NJ; // SnakeGymEnv.py:72-76
+}
+
+extern "C" {
+
+const char* snk_last_error(void) { return g_err; }
+
+const char* snk_build_info(void) {
+    return "snake_b200 sm_100a; warp-per-env fused env-step; built " __DATE__ " " __TIME__;
+}
+
+int snk_default_params(snk_params* p) {
+    if (!p) return fail(SNK_E_ARG, "snk_default_params: null pointer%s");
+    memset(p, 0, sizeof *p);
+    p->dt = 1.0 / 240.0; p->gravity[2] = -9.8;
+    p->motor_kp = 0.1; p->motor_kd = 1.0; p->motor_max_force = INFINITY;
+    p->scaling_factor = 3.14159265358979323846 / 6.0;
+    p->alpha = 1.0; p->beta = 0.01; p->gamma = 0.1; p->energy_dt = 0.01;
+    p->friction = 2.0; p->aniso[0] = 1.0; p->aniso[1] = 0.1; p->aniso[2] = 0.01;
+    p->lin_damping = 0.04; p->ang_damping = 0.04; p->erp2 = 0.08; p->linear_slop = 1e-5; p->residual_threshold = 1e-7;
+    p->max_coord_vel = 100.0; p->err_threshold = 0.05; p->height_threshold = 0.1; p->term_angle = 0.5;
+    p->done_penalty = -5.0; p->collision_force = 10.0; p->collision_penalty = -10.0;
+    p->solver_iterations = 50; p->max_ticks = 41; p->gait_selection = 1; p->cone_friction = 1; p->term_joint = 9;
+    p->stale_obs_on_reset = 1; p->alternate_motor_order = 1; p->reserved0 = 0;
+    return 0;
+}
+
+int snk_create(const snk_model* model, const snk_params* params, int64_t n_envs, int device, snk_handle** out) {
+    if (!model || !params || !out) return fail(SNK_E_ARG, "snk_create: null pointer%s");
+    if (n_envs <= 0) return fail(SNK_E_ARG, "snk_create: n_envs must be positive%s");
+    if (params->term_joint < 0 || params->term_joint >= SNK_OBS_DIM) return fail(SNK_E_ARG, "snk_create: term_joint out of range%s");
+    if (params->solver_iterations < 1 || params->max_ticks < 0) return fail(SNK_E_ARG, "snk_create: bad iteration/tick limits%s");
+    if (!(params->dt > 0)) return fail(SNK_E_ARG, "snk_create: dt must be positive%s");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(SNK_E_NODEV, "snk_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(SNK_E_ARG, "snk_create: device index out of range%s");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(SNK_E_NODEV, "snk_create: kernels are built for sm_100a only, found %s", prop.name);
+    CU(snk_configure_kernels());
+    snk_handle* h = new (std::nothrow) snk_handle();
+    if (!h) return fail(SNK_E_NOMEM, "snk_create: out of host memory%s");
+    memset(h, 0, sizeof *h);
+    h->device = device; h->n = n_envs;
+    to_kparams(params, &h->P);
+    DevTables host_tables;
+    to_tables(model, &host_tables);
+    cudaError_t err = cudaMalloc(&h->T, sizeof(DevTables));
+    if (err == cudaSuccess) err = cudaMalloc(&h->state, (size_t)n_envs * SNK_STATE_STRIDE * sizeof(float));
+    if (err == cudaSuccess) err = cudaMalloc(&h->counters, 4 * sizeof(unsigned long long));
+    if (err == cudaSuccess) err = cudaMemcpy(h->T, &host_tables, sizeof host_tables, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemset(h->counters, 0, 4 * sizeof(unsigned long long));
+    if (err == cudaSuccess) err = snk_launch_reset(h->P, h->state, nullptr, nullptr, h->n, 1, 0);
+    if (err == cudaSuccess) err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) {
+        cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters);
+        delete h;
+        return fail(SNK_E_CUDA, "snk_create: %s", cudaGetErrorString(err));
+    }
+    h->launches = 1;
+    *out = h;
+    return 0;
+}
+
+int snk_destroy(snk_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->staged) {
+        cudaStreamSynchronize(h->hstream);
+        cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_done); cudaFreeHost(h->h_ticks);
+        cudaFreeHost(h->h_mask);
+        cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_ticks); cudaFree(h->d_mask);
+        cudaStreamDestroy(h->hstream);
+    }
+    cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters);
+    delete h;
+    return 0;
+}
+
+int64_t snk_num_envs(const snk_handle* h) { return h ? h->n : 0; }
+int snk_action_dim(const snk_handle* h) { return h ? h->P.actdim : 0; }
+int snk_device(const snk_handle* h) { return h ? h->device : -1; }
+int64_t snk_launch_count(const snk_handle* h) { return h ? h->launches : 0; }
+
+int snk_reset(snk_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
+    if (!h) return fail(SNK_E_ARG, "snk_reset: null handle%s");
+    CU(cudaSetDevice(h->device));
+    CU(snk_launch_reset(h->P, h->state, mask_dev, obs_dev, h->n, 0, (cudaStream_t)stream));
+    h->launches++;
+    return 0;
+}
+
+int snk_observe(snk_handle* h, float* obs_dev, void* stream) {
+    if (!h || !obs_dev) return fail(SNK_E_ARG, "snk_observe: null pointer%s");
+    CU(cudaSetDevice(h->device));
+    CU(snk_launch_reset(h->P, h->state, nullptr, obs_dev, h->n, 2, (cudaStream_t)stream));
+    h->launches++;
+    return 0;
+}
+
+int snk_step(snk_handle* h, const float* actions_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, int32_t* ticks_dev, void* stream) {
+    if (!h || !actions_dev || !obs_dev || !rew_dev || !done_dev) return fail(SNK_E_ARG, "snk_step: null pointer%s");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(h->counters, 0, 4 * sizeof(unsigned long long), st));
+    CU(snk_launch_step(h->T, h->P, h->state, actions_dev, obs_dev, rew_dev, done_dev, ticks_dev, h->counters, h->n, st));
+    h->launches++;
+    return 0;
+}
+
+int snk_tick(snk_handle* h, const float* targets_dev, int32_t n_ticks, void* stream) {
+    if (!h || !targets_dev || n_ticks < 0) return fail(SNK_E_ARG, "snk_tick: bad argument%s");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(h->counters, 0, 4 * sizeof(unsigned long long), st));
+    CU(snk_launch_tick(h->T, h->P, h->state, targets_dev, h->counters, h->n, n_ticks, st));
+    h->launches++;
+    return 0;
+}
+
+static int ensure_staging(snk_handle* h) {
+    if (h->staged) return 0;
+    size_t n = (size_t)h->n;
+    CU(cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+    CU(cudaMallocHost(&h->h_act, n * NJ * sizeof(float)));
+    CU(cudaMallocHost(&h->h_obs, n * SNK_OBS_DIM * sizeof(float)));
+    CU(cudaMallocHost(&h->h_rew, n * sizeof(float)));
+    CU(cudaMallocHost(&h->h_done, n));
+    CU(cudaMallocHost(&h->h_mask, n));
+    CU(cudaMallocHost(&h->h_ticks, n * sizeof(int32_t)));
+    CU(cudaMalloc(&h->d_act, n * NJ * sizeof(float)));
+    CU(cudaMalloc(&h->d_obs, n * SNK_OBS_DIM * sizeof(float)));
+    CU(cudaMalloc(&h->d_rew, n * sizeof(float)));
+    CU(cudaMalloc(&h->d_done, n));
+    CU(cudaMalloc(&h->d_mask, n));
+    CU(cudaMalloc(&h->d_ticks, n * sizeof(int32_t)));
+    h->staged = true;
+    return 0;
+}
+
+int snk_step_host(snk_handle* h, const float* actions_host, float* obs_host, float* rew_host, uint8_t* done_host, int32_t* ticks_host) {
+    if (!h || !actions_host || !obs_host || !rew_host || !done_host) return fail(SNK_E_ARG, "snk_step_host: null pointer%s");
+    CU(cudaSetDevice(h->device));
+    int rc = ensure_staging(h);
+    if (rc) return rc;
+    size_t n = (size_t)h->n, na = n * h->P.actdim * sizeof(float);
+    cudaStream_t st = h->hstream;
+    memcpy(h->h_act, actions_host, na);
+    CU(cudaMemcpyAsync(h->d_act, h->h_act, na, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(h->counters, 0, 4 * sizeof(unsigned long long), st));
+    CU(snk_launch_step(h->T, h->P, h->state, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_ticks, h->counters, h->n, st));
+    h->launches++;
+    CU(cudaMemcpyAsync(h->h_obs, h->d_obs, n * SNK_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->h_rew, h->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
+    if (ticks_host) CU(cudaMemcpyAsync(h->h_ticks, h->d_ticks, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(obs_host, h->h_obs, n * SNK_OBS_DIM * sizeof(float));
+    memcpy(rew_host, h->h_rew, n * sizeof(float));
+    memcpy(done_host, h->h_done, n);
+    if (ticks_host) memcpy(ticks_host, h->h_ticks, n * sizeof(int32_t));
+    return 0;
+}
+
+int snk_reset_host(snk_handle* h, const uint8_t* mask_host, float* obs_host) {
+    if (!h) return fail(SNK_E_ARG, "snk_reset_host: null handle%s");
+    CU(cudaSetDevice(h->device));
+    int rc = ensure_staging(h);
+    if (rc) return rc;
+    size_t n = (size_t)h->n;
+    cudaStream_t st = h->hstream;
+    if (mask_host) {
+        memcpy(h->h_mask, mask_host, n);
+        CU(cudaMemcpyAsync(h->d_mask, h->h_mask, n, cudaMemcpyHostToDevice, st));
+    }
+    CU(snk_launch_reset(h->P, h->state, mask_host ? h->d_mask : nullptr, obs_host ? h->d_obs : nullptr, h->n, 0, st));
+    h->launches++;
+    if (obs_host) CU(cudaMemcpyAsync(h->h_obs, h->d_obs, n * SNK_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (obs_host) memcpy(obs_host, h->h_obs, n * SNK_OBS_DIM * sizeof(float));
+    return 0;
+}
+
+int snk_get_state(snk_handle* h, float* state_dev, void* stream) {
+    if (!h || !state_dev) return fail(SNK_E_ARG, "snk_get_state: null pointer%s");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(state_dev, h->state, (size_t)h->n * SNK_STATE_STRIDE * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+int snk_set_state(snk_handle* h, const float* state_dev, void* stream) {
+    if (!h || !state_dev) return fail(SNK_E_ARG, "snk_set_state: null pointer%s");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(h->state, state_dev, (size_t)h->n * SNK_STATE_STRIDE * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+int snk_last_counters(snk_handle* h, int64_t out[4]) {
+    if (!h || !out) return fail(SNK_E_ARG, "snk_last_counters: null pointer%s");
+    CU(cudaSetDevice(h->device));
+    unsigned long long tmp[4];
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(tmp, h->counters, sizeof tmp, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 4; k++) out[k] = (int64_t)tmp[k];
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,826 @@
+// snake_step.cu -- fused SnakeGymEnv.step() for N environments, one warp per environment (sm_100a).
+//
+// One launch = one SubprocVecEnv.step(): clip + createAction, the data-dependent 0..41-tick loop of
+// {PD motor rows, articulated-body forward dynamics, cylinder-vs-plane contacts, projected
+// Gauss-Seidel}, observation, reward, termination and auto-reset, written straight into the
+// caller's (torch) buffers.  All intermediate state of an environment lives in its warp's slice of
+// shared memory and in registers for the whole env-step; HBM sees 256 B of state in, 256 B out, the
+// action row in, and obs/reward/done out.
+//
+// Lane roles change by phase:
+//   kinematic / velocity / acceleration chains : every lane walks the 16-joint chain redundantly in
+//       registers (no shared-memory round trip per joint); lane b keeps body b's result
+//   bias forces                                 : lane = body
+//   articulated inertias (backward pass)        : lane = element of the 6x6 matrices, 4 stages/joint
+//   constraint rows (J, M^-1 J^T, rhs)          : lane = collision cylinder (32 cylinders = 32 lanes);
+//       lanes 0..15 additionally own one motor row; each lane runs the O(n) impulse response of its rows
+//   projected Gauss-Seidel                      : lane = generalized-velocity DoF (22 of 32 lanes);
+//       J.dv by xor-shuffle butterfly, impulses kept in the owning lane's registers
+//
+// Reference call sites replaced: SnakeGymEnv.py:33-50,82-103; snake.py:209-306,336-341;
+// ppo/multiprocessing_env.py:11-16; physics per SURVEY.md Appendix A (see oracle/snake_oracle.c,
+// whose row order, clamping and residual rule this kernel reproduces).
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "snake_step.cuh"
+
+#define FULL 0xffffffffu
+#define WARPS_PER_CTA 4
+
+struct WarpMem {
+    float s[SNK_STATE_STRIDE];
+    float Rw[NB][9];
+    float pw[NB][3];
+    float Rj[NB][9];
+    float v[NB][6];
+    float cb[NB][6];
+    float pA[NB][6];
+    float IA[NB][36];
+    float U[NB][6];
+    float Dinv[NB];
+    float uu[NB];
+    float X[36];
+    float Ia[36];
+    float Tm[36];
+    float pa[6];
+    float IA0inv[36];
+    float nu[ND];
+    float nuF[ND];
+    float target[NJ];
+    float J[3 * NC][ND];
+    float B[NROW][ND];
+    float rhs[NROW];
+    float invD[NROW];
+    float Dg[NROW];
+};
+
+// ---------------------------------------------------------------------------------------------
+// small helpers (register vectors)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cross3(const float* a, const float* b, float* o) {
+    float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+__device__ __forceinline__ float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void m3v(const float* M, const float* v, float* o) {
+    float x = M[0] * v[0] + M[1] * v[1] + M[2] * v[2], y = M[3] * v[0] + M[4] * v[1] + M[5] * v[2],
+          z = M[6] * v[0] + M[7] * v[1] + M[8] * v[2];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+__device__ __forceinline__ void m3tv(const float* M, const float* v, float* o) {
+    float x = M[0] * v[0] + M[3] * v[1] + M[6] * v[2], y = M[1] * v[0] + M[4] * v[1] + M[7] * v[2],
+          z = M[2] * v[0] + M[5] * v[1] + M[8] * v[2];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+__device__ __forceinline__ void m3m3(const float* A, const float* B, float* o) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) o[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+// motion vector parent -> child through a joint with child->parent rotation R and offset r
+__device__ __forceinline__ void xmot(const float* R, const float* r, const float* vp, float* vc) {
+    float t[3], u[3];
+    cross3(vp, r, t);
+    u[0] = vp[3] + t[0]; u[1] = vp[4] + t[1]; u[2] = vp[5] + t[2];
+    m3tv(R, vp, vc);
+    m3tv(R, u, vc + 3);
+}
+// force vector child -> parent
+__device__ __forceinline__ void xfrc(const float* R, const float* r, const float* fc, float* fp) {
+    float t[3];
+    m3v(R, fc, fp);
+    m3v(R, fc + 3, fp + 3);
+    cross3(r, fp + 3, t);
+    fp[0] += t[0]; fp[1] += t[1]; fp[2] += t[2];
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward kinematics; returns the checkSnakeHeight mean (snake.py:237-245), identical in all lanes
+// ---------------------------------------------------------------------------------------------
+__device__ float fk(WarpMem& W, const DevTables* __restrict__ T, int lane) {
+    if (lane < NJ) { // joint rotations, lane = joint
+        float a[3] = {__ldg(&T->jax[lane][0]), __ldg(&T->jax[lane][1]), __ldg(&T->jax[lane][2])};
+        float th = W.s[SNK_S_Q + lane], s, c;
+        sincosf(th, &s, &c);
+        float C = 1.f - c, Rq[9], R0[9], R[9];
+        Rq[0] = c + a[0] * a[0] * C;        Rq[1] = a[0] * a[1] * C - a[2] * s; Rq[2] = a[0] * a[2] * C + a[1] * s;
+        Rq[3] = a[1] * a[0] * C + a[2] * s; Rq[4] = c + a[1] * a[1] * C;        Rq[5] = a[1] * a[2] * C - a[0] * s;
+        Rq[6] = a[2] * a[0] * C - a[1] * s; Rq[7] = a[2] * a[1] * C + a[0] * s; Rq[8] = c + a[2] * a[2] * C;
+#pragma unroll
+        for (int k = 0; k < 9; k++) R0[k] = __ldg(&T->jR0[lane][k]);
+        m3m3(R0, Rq, R);
+#pragma unroll
+        for (int k = 0; k < 9; k++) W.Rj[lane + 1][k] = R[k];
+    }
+    __syncwarp();
+    float R[9], p[3], Rm[9], pm[3];
+    {
+        float x = W.s[SNK_S_QUAT], y = W.s[SNK_S_QUAT + 1], z = W.s[SNK_S_QUAT + 2], w = W.s[SNK_S_QUAT + 3];
+        R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w);     R[2] = 2 * (x * z + y * w);
+        R[3] = 2 * (x * y + z * w);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+        R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
+        p[0] = W.s[SNK_S_POS]; p[1] = W.s[SNK_S_POS + 1]; p[2] = W.s[SNK_S_POS + 2];
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) Rm[k] = R[k];
+    pm[0] = p[0]; pm[1] = p[1]; pm[2] = p[2];
+#pragma unroll 1
+    for (int i = 1; i < NB; i++) { // every lane walks the chain; lane i keeps body i
+        float Rn[9], t[3], r[3] = {__ldg(&T->jt[i - 1][0]), __ldg(&T->jt[i - 1][1]), __ldg(&T->jt[i - 1][2])};
+        m3v(R, r, t);
+        m3m3(R, W.Rj[i], Rn);
+        p[0] += t[0]; p[1] += t[1]; p[2] += t[2];
+#pragma unroll
+        for (int k = 0; k < 9; k++) R[k] = Rn[k];
+        if (lane == i) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) Rm[k] = R[k];
+            pm[0] = p[0]; pm[1] = p[1]; pm[2] = p[2];
+        }
+    }
+    if (lane < NB) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) W.Rw[lane][k] = Rm[k];
+        W.pw[lane][0] = pm[0]; W.pw[lane][1] = pm[1]; W.pw[lane][2] = pm[2];
+    }
+    __syncwarp();
+    float z = 0.f;
+#pragma unroll 1
+    for (int h = 0; h < NB; h++) {
+        int b = __ldg(&T->hbody[h]);
+        z += W.pw[b][2] + W.Rw[b][6] * __ldg(&T->hpt[h][0]) + W.Rw[b][7] * __ldg(&T->hpt[h][1]) + W.Rw[b][8] * __ldg(&T->hpt[h][2]);
+    }
+    return z / NB;
+}
+
+// ---------------------------------------------------------------------------------------------
+// response of the generalized velocity to a unit impulse (oracle: impulse_response): spatial impulse
+// f6 on body b (b < 0: none) and/or unit torque impulse at joint jm (0: none).  Runs per lane; every
+// lane walks all 16 joints so the shared-memory reads are warp-uniform broadcasts.
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ void impulse_response(const WarpMem& W, const DevTables* __restrict__ T, int b, const float* f6, int jm,
+                                              float* out /* ND, shared or local */) {
+    float u[NB];
+    float p[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = NB - 1; i >= 1; i--) {
+        if (i == b) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) p[k] -= f6[k];
+        }
+        float ax[3] = {__ldg(&T->jax[i - 1][0]), __ldg(&T->jax[i - 1][1]), __ldg(&T->jax[i - 1][2])};
+        float r[3] = {__ldg(&T->jt[i - 1][0]), __ldg(&T->jt[i - 1][1]), __ldg(&T->jt[i - 1][2])};
+        u[i] = ((i == jm) ? 1.f : 0.f) - dot3(ax, p);
+        float s = u[i] * W.Dinv[i], pa[6], pp[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) pa[k] = p[k] + W.U[i][k] * s;
+        xfrc(W.Rj[i], r, pa, pp);
+#pragma unroll
+        for (int k = 0; k < 6; k++) p[k] = pp[k];
+    }
+    if (b == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) p[k] -= f6[k];
+    }
+    float a[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; k++) s -= W.IA0inv[6 * r + k] * p[k];
+        a[r] = s;
+        out[r] = s;
+    }
+#pragma unroll
+    for (int i = 1; i < NB; i++) {
+        float ax[3] = {__ldg(&T->jax[i - 1][0]), __ldg(&T->jax[i - 1][1]), __ldg(&T->jax[i - 1][2])};
+        float r[3] = {__ldg(&T->jt[i - 1][0]), __ldg(&T->jt[i - 1][1]), __ldg(&T->jt[i - 1][2])};
+        float ac[6];
+        xmot(W.Rj[i], r, a, ac);
+        float s = u[i];
+#pragma unroll
+        for (int k = 0; k < 6; k++) s -= W.U[i][k] * ac[k];
+        float qdd = s * W.Dinv[i];
+        out[6 + i - 1] = qdd;
+        a[0] = ac[0] + ax[0] * qdd; a[1] = ac[1] + ax[1] * qdd; a[2] = ac[2] + ax[2] * qdd;
+        a[3] = ac[3]; a[4] = ac[4]; a[5] = ac[5];
+    }
+}
+
+// 6x6 SPD inverse by Cholesky, all in registers (every lane computes the same thing)
+__device__ void sym6_inverse(const float* A /* shared */, float* Ainv /* registers, 36 */) {
+    float L[36];
+#pragma unroll
+    for (int k = 0; k < 36; k++) L[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        float d = A[6 * j + j];
+#pragma unroll
+        for (int k = 0; k < j; k++) d -= L[6 * j + k] * L[6 * j + k];
+        d = sqrtf(d);
+        L[6 * j + j] = d;
+        float id = 1.f / d;
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) {
+            float s = A[6 * i + j];
+#pragma unroll
+            for (int k = 0; k < j; k++) s -= L[6 * i + k] * L[6 * j + k];
+            L[6 * i + j] = s * id;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        float y[6], x[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            float s = (i == c) ? 1.f : 0.f;
+#pragma unroll
+            for (int k = 0; k < i; k++) s -= L[6 * i + k] * y[k];
+            y[i] = s / L[6 * i + i];
+        }
+#pragma unroll
+        for (int i = 5; i >= 0; i--) {
+            float s = y[i];
+#pragma unroll
+            for (int k = i + 1; k < 6; k++) s -= L[6 * k + i] * x[k];
+            x[i] = s / L[6 * i + i];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) Ainv[6 * i + c] = x[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// one physics tick (oracle: forward_dynamics + tick).  Returns the PGS iteration count.
+// ---------------------------------------------------------------------------------------------
+__device__ int tick(WarpMem& W, const DevTables* __restrict__ T, const KParams& P, int lane) {
+    const float dt = P.dt;
+    // ---- pass 1: velocity chain (every lane, registers), lane b keeps v_b ----
+    float vcur[6], vm[6];
+    {
+        float w[3] = {W.s[SNK_S_OMEGA], W.s[SNK_S_OMEGA + 1], W.s[SNK_S_OMEGA + 2]};
+        float vv[3] = {W.s[SNK_S_VEL], W.s[SNK_S_VEL + 1], W.s[SNK_S_VEL + 2]};
+        m3tv(W.Rw[0], w, vcur);
+        m3tv(W.Rw[0], vv, vcur + 3);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) vm[k] = vcur[k];
+#pragma unroll 1
+    for (int i = 1; i < NB; i++) {
+        float r[3] = {__ldg(&T->jt[i - 1][0]), __ldg(&T->jt[i - 1][1]), __ldg(&T->jt[i - 1][2])};
+        float vn[6];
+        xmot(W.Rj[i], r, vcur, vn);
+        float qd = W.s[SNK_S_QD + i - 1];
+        vn[0] += __ldg(&T->jax[i - 1][0]) * qd; vn[1] += __ldg(&T->jax[i - 1][1]) * qd; vn[2] += __ldg(&T->jax[i - 1][2]) * qd;
+#pragma unroll
+        for (int k = 0; k < 6; k++) vcur[k] = vn[k];
+        if (lane == i) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) vm[k] = vn[k];
+        }
+    }
+    // ---- bias forces, lane = body ----
+    if (lane < NB) {
+        const int b = lane;
+        float m = __ldg(&T->mass[b]);
+        float c[3] = {__ldg(&T->com[b][0]), __ldg(&T->com[b][1]), __ldg(&T->com[b][2])};
+        float Ic[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Ic[k] = __ldg(&T->Ic[b][k]);
+        float cbv[6] = {0, 0, 0, 0, 0, 0};
+        if (b > 0) {
+            float qd = W.s[SNK_S_QD + b - 1];
+            float sq[3] = {__ldg(&T->jax[b - 1][0]) * qd, __ldg(&T->jax[b - 1][1]) * qd, __ldg(&T->jax[b - 1][2]) * qd};
+            cross3(vm, sq, cbv);
+            cross3(vm + 3, sq, cbv + 3);
+        }
+        // h = I v (rigid inertia at the body origin): h_lin = m (v + w x c), h_ang = Ic w + c x h_lin
+        float wc[3], vc[3], hl[3], ha[3], t[3];
+        cross3(vm, c, wc);
+        vc[0] = vm[3] + wc[0]; vc[1] = vm[4] + wc[1]; vc[2] = vm[5] + wc[2];
+        hl[0] = m * vc[0]; hl[1] = m * vc[1]; hl[2] = m * vc[2];
+        float Iw[3];
+        m3v(Ic, vm, Iw);
+        cross3(c, hl, t);
+        ha[0] = Iw[0] + t[0]; ha[1] = Iw[1] + t[1]; ha[2] = Iw[2] + t[2];
+        float p[6], t1[3], t2[3];
+        cross3(vm, ha, t1); cross3(vm + 3, hl, t2);
+        p[0] = t1[0] + t2[0]; p[1] = t1[1] + t2[1]; p[2] = t1[2] + t2[2];
+        cross3(vm, hl, p + 3);
+        // gravity + velocity damping
+        float gb[3], fg[3], ng[3], Fd[3], Td[3], nd[3];
+        m3tv(W.Rw[b], P.g, gb);
+        fg[0] = m * gb[0]; fg[1] = m * gb[1]; fg[2] = m * gb[2];
+        cross3(c, fg, ng);
+        float nv = sqrtf(dot3(vc, vc)), nw = sqrtf(dot3(vm, vm));
+        float kl = P.kl + P.kl * nv, ka = P.ka + P.ka * nw;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { Fd[k] = -m * vc[k] * kl; Td[k] = -Iw[k] * ka; }
+        cross3(c, Fd, nd);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { p[k] -= ng[k] + Td[k] + nd[k]; p[3 + k] -= fg[k] + Fd[k]; }
+#pragma unroll
+        for (int k = 0; k < 6; k++) { W.v[b][k] = vm[k]; W.cb[b][k] = cbv[k]; W.pA[b][k] = p[k]; }
+    }
+    // rigid spatial inertias at the body origins -> IA, lane = element
+    for (int idx = lane; idx < NB * 36; idx += 32) {
+        int b = idx / 36, e = idx - b * 36, r = e / 6, cc = e - r * 6;
+        float m = __ldg(&T->mass[b]);
+        const float* c = T->com[b];
+        float val;
+        if (r < 3 && cc < 3) { // Ic - m [c]x[c]x = Ic + m (c.c 1 - c c^T)
+            float c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2);
+            float cr = (r == 0) ? c0 : (r == 1) ? c1 : c2, ccv = (cc == 0) ? c0 : (cc == 1) ? c1 : c2;
+            val = __ldg(&T->Ic[b][3 * r + cc]) + m * (((r == cc) ? (c0 * c0 + c1 * c1 + c2 * c2) : 0.f) - cr * ccv);
+        } else if (r >= 3 && cc >= 3) {
+            val = (r == cc) ? m : 0.f;
+        } else { // m [c]x (upper right), -m [c]x (lower left)
+            int a = (r < 3) ? r : r - 3, d = (cc < 3) ? cc : cc - 3;
+            float sgn = (r < 3) ? 1.f : -1.f;
+            float cx = 0.f;
+            if (a != d) {
+                int k3 = 3 - a - d; // the remaining index
+                float ck = __ldg(c + k3);
+                // [c]x[a][d] = -eps(a,d,k) c_k
+                bool even = ((a == 0 && d == 1) || (a == 1 && d == 2) || (a == 2 && d == 0));
+                cx = even ? -ck : ck;
+            }
+            val = sgn * m * cx;
+        }
+        (&W.IA[0][0])[idx] = val;
+    }
+    __syncwarp();
+    // ---- pass 2: articulated inertias, lane = matrix element ----
+#pragma unroll 1
+    for (int i = NB - 1; i >= 1; i--) {
+        const float ax0 = __ldg(&T->jax[i - 1][0]), ax1 = __ldg(&T->jax[i - 1][1]), ax2 = __ldg(&T->jax[i - 1][2]);
+        const float r0 = __ldg(&T->jt[i - 1][0]), r1 = __ldg(&T->jt[i - 1][1]), r2 = __ldg(&T->jt[i - 1][2]);
+        // stage A: U = IA ax (lanes 0..5); X (all lanes, 36 elements)
+        if (lane < 6) W.U[i][lane] = W.IA[i][6 * lane] * ax0 + W.IA[i][6 * lane + 1] * ax1 + W.IA[i][6 * lane + 2] * ax2;
+        for (int e = lane; e < 36; e += 32) {
+            int a = e / 6, c = e - 6 * a;
+            int a3 = (a < 3) ? a : a - 3, c3 = (c < 3) ? c : c - 3;
+            float val;
+            if (a < 3 && c >= 3) val = 0.f;
+            else if ((a < 3) == (c < 3)) val = W.Rj[i][3 * c3 + a3]; // E = Rj^T
+            else { // -(E rx)[a3][c3],  rx = [[0,-r2,r1],[r2,0,-r0],[-r1,r0,0]]
+                float e0 = W.Rj[i][a3], e1 = W.Rj[i][3 + a3], e2 = W.Rj[i][6 + a3]; // row a3 of E
+                float v0 = e1 * r2 - e2 * r1, v1 = -e0 * r2 + e2 * r0, v2 = e0 * r1 - e1 * r0;
+                val = -((c3 == 0) ? v0 : (c3 == 1) ? v1 : v2);
+            }
+            W.X[e] = val;
+        }
+        __syncwarp();
+        const float D = ax0 * W.U[i][0] + ax1 * W.U[i][1] + ax2 * W.U[i][2];
+        const float Dinv = 1.f / D;
+        const float tau = -__ldg(&T->jdamp[i - 1]) * W.s[SNK_S_QD + i - 1];
+        const float uu = tau - (ax0 * W.pA[i][0] + ax1 * W.pA[i][1] + ax2 * W.pA[i][2]);
+        if (lane == 0) { W.Dinv[i] = Dinv; W.uu[i] = uu; }
+        // stage B: Ia = IA - U U^T / D
+        for (int e = lane; e < 36; e += 32) {
+            int a = e / 6, c = e - 6 * a;
+            W.Ia[e] = W.IA[i][e] - W.U[i][a] * W.U[i][c] * Dinv;
+        }
+        __syncwarp();
+        // stage C: Tm = Ia X ; pa = pA + Ia cb + U uu / D (lanes 0..5)
+        for (int e = lane; e < 36; e += 32) {
+            int a = e / 6, c = e - 6 * a;
+            float z = 0.f;
+#pragma unroll
+            for (int k = 0; k < 6; k++) z += W.Ia[6 * a + k] * W.X[6 * k + c];
+            W.Tm[e] = z;
+        }
+        if (lane < 6) {
+            float z = W.pA[i][lane] + W.U[i][lane] * uu * Dinv;
+#pragma unroll
+            for (int k = 0; k < 6; k++) z += W.Ia[6 * lane + k] * W.cb[i][k];
+            W.pa[lane] = z;
+        }
+        __syncwarp();
+        // stage D: IA[i-1] += X^T Tm ; pA[i-1] += X* pa
+        for (int e = lane; e < 36; e += 32) {
+            int a = e / 6, c = e - 6 * a;
+            float z = 0.f;
+#pragma unroll
+            for (int k = 0; k < 6; k++) z += W.X[6 * k + a] * W.Tm[6 * k + c];
+            W.IA[i - 1][e] += z;
+        }
+        if (lane < 6) { // force transform = X^T applied to pa
+            float z = 0.f;
+#pragma unroll
+            for (int k = 0; k < 6; k++) z += W.X[6 * k + lane] * W.pa[k];
+            W.pA[i - 1][lane] += z;
+        }
+        __syncwarp();
+    }
+    // ---- base: IA0^-1 (registers, every lane), shared copy for the impulse responses ----
+    float Ainv[36];
+    sym6_inverse(W.IA[0], Ainv);
+    for (int e = lane; e < 36; e += 32) {
+        float val = 0.f;
+#pragma unroll
+        for (int k = 0; k < 36; k++) if (k == e) val = Ainv[k];
+        W.IA0inv[e] = val;
+    }
+    // ---- pass 3: acceleration chain (every lane), unconstrained velocity ----
+    {
+        float a[6];
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            float z = 0.f;
+#pragma unroll
+            for (int k = 0; k < 6; k++) z -= Ainv[6 * r + k] * W.pA[0][k];
+            a[r] = z;
+        }
+        float wxv[3];
+        cross3(W.v[0], W.v[0] + 3, wxv);
+        {
+            float al = 0.f;
+#pragma unroll
+            for (int r = 0; r < 6; r++) if (lane == r) al = a[r] + ((r >= 3) ? wxv[(r >= 3) ? r - 3 : 0] : 0.f);
+            if (lane < 6) W.nu[lane] = W.v[0][lane] + dt * al;
+        }
+        float myqdd = 0.f;
+#pragma unroll 1
+        for (int i = 1; i < NB; i++) {
+            float r[3] = {__ldg(&T->jt[i - 1][0]), __ldg(&T->jt[i - 1][1]), __ldg(&T->jt[i - 1][2])};
+            float ac[6];
+            xmot(W.Rj[i], r, a, ac);
+            float z = W.uu[i];
+#pragma unroll
+            for (int k = 0; k < 6; k++) { ac[k] += W.cb[i][k]; z -= W.U[i][k] * ac[k]; }
+            float qdd = z * W.Dinv[i];
+            a[0] = ac[0] + __ldg(&T->jax[i - 1][0]) * qdd; a[1] = ac[1] + __ldg(&T->jax[i - 1][1]) * qdd;
+            a[2] = ac[2] + __ldg(&T->jax[i - 1][2]) * qdd;
+            a[3] = ac[3]; a[4] = ac[4]; a[5] = ac[5];
+            if (lane == i - 1) myqdd = qdd;
+        }
+        if (lane < NJ) W.nu[6 + lane] = W.s[SNK_S_QD + lane] + dt * myqdd;
+    }
+    __syncwarp();
+
+    // ---- constraint rows ----
+    float lam_m = 0.f, lam_n = 0.f, lam_a = 0.f, lam_b = 0.f; // impulses owned by this lane
+    if (lane < NJ) { // motor row of joint lane+1 (A.4)
+        const int j = lane;
+        const float zero6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        impulse_response(W, T, -1, zero6, j + 1, W.B[j]);
+        float D = W.B[j][6 + j];
+        float q = W.s[SNK_S_Q + j], qd = W.nu[6 + j];
+        float vt = P.kp * (W.target[j] - q) * P.inv_dt + qd + P.kd * (0.f - qd);
+        W.Dg[j] = D; W.invD[j] = 1.f / D; W.rhs[j] = (vt - qd) / D;
+    }
+    bool active;
+    {
+        const int c = lane;
+        const int b = __ldg(&T->cbody[c]);
+        float cax[3] = {__ldg(&T->cax[c][0]), __ldg(&T->cax[c][1]), __ldg(&T->cax[c][2])};
+        float ccen[3] = {__ldg(&T->ccen[c][0]), __ldg(&T->ccen[c][1]), __ldg(&T->ccen[c][2])};
+        float axw[3], cw[3], p[3];
+        m3v(W.Rw[b], cax, axw);
+        m3v(W.Rw[b], ccen, cw);
+        float eh = __ldg(&T->cend[c]) * __ldg(&T->chl[c]);
+        float az = axw[2], nn = fmaxf(1.f - az * az, 1e-12f);
+        float inv = 1.f / sqrtf(nn), rad = __ldg(&T->crad[c]);
+        p[0] = W.pw[b][0] + cw[0] + eh * axw[0] + rad * (az * axw[0] * inv);
+        p[1] = W.pw[b][1] + cw[1] + eh * axw[1] + rad * (az * axw[1] * inv);
+        p[2] = W.pw[b][2] + cw[2] + eh * axw[2] + rad * ((az * axw[2] - 1.f) * inv);
+        float dist = p[2] - __ldg(&T->cmar[c]);
+        active = dist < __ldg(&T->cbrk[c]);
+        p[2] = dist;
+        float Rl[9], cfr[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) cfr[k] = __ldg(&T->cfr[c][k]);
+        m3m3(W.Rw[b], cfr, Rl);
+#pragma unroll 1
+        for (int f = 0; f < 3; f++) {
+            if (!active) break;
+            float d[3] = {0.f, 0.f, 1.f};
+            if (f > 0) {
+                float t[3] = {(f == 2) ? 1.f : 0.f, (f == 1) ? -1.f : 0.f, 0.f}, loc[3];
+                m3tv(Rl, t, loc);
+                loc[0] *= P.aniso[0]; loc[1] *= P.aniso[1]; loc[2] *= P.aniso[2];
+                m3v(Rl, loc, d);
+            }
+            const int r = (f == 0) ? c : NC + 2 * c + (f - 1); // index into J; B/rhs rows are NJ + r
+            float* Jr = W.J[r];
+            float* Br = W.B[NJ + r];
+            float rel[3] = {p[0] - W.pw[0][0], p[1] - W.pw[0][1], p[2] - W.pw[0][2]}, rxd[3], jb[6];
+            cross3(rel, d, rxd);
+            m3tv(W.Rw[0], rxd, jb);
+            m3tv(W.Rw[0], d, jb + 3);
+#pragma unroll
+            for (int k = 0; k < 6; k++) Jr[k] = jb[k];
+#pragma unroll 1
+            for (int j = 1; j < NB; j++) {
+                float val = 0.f;
+                if (j <= b) {
+                    float ax[3] = {__ldg(&T->jax[j - 1][0]), __ldg(&T->jax[j - 1][1]), __ldg(&T->jax[j - 1][2])}, aw[3];
+                    m3v(W.Rw[j], ax, aw);
+                    float ro[3] = {p[0] - W.pw[j][0], p[1] - W.pw[j][1], p[2] - W.pw[j][2]}, t[3];
+                    cross3(ro, d, t);
+                    val = dot3(aw, t);
+                }
+                Jr[6 + j - 1] = val;
+            }
+            float f6[6], db[3], pb[3], ro[3] = {p[0] - W.pw[b][0], p[1] - W.pw[b][1], p[2] - W.pw[b][2]};
+            m3tv(W.Rw[b], d, db);
+            m3tv(W.Rw[b], ro, pb);
+            cross3(pb, db, f6);
+            f6[3] = db[0]; f6[4] = db[1]; f6[5] = db[2];
+            impulse_response(W, T, b, f6, 0, Br);
+            float D = 0.f, vrel = 0.f;
+#pragma unroll 1
+            for (int k = 0; k < ND; k++) { D += Jr[k] * Br[k]; vrel += Jr[k] * W.nu[k]; }
+            float iD = 1.f / D, rh;
+            if (f == 0) {
+                float pen = dist + P.slop, verr = -vrel, perr = 0.f;
+                if (pen > 0.f) verr -= pen * P.inv_dt; else perr = -pen * P.erp2 * P.inv_dt;
+                rh = (verr + perr) * iD;
+            } else rh = -vrel * iD;
+            W.Dg[NJ + r] = D; W.invD[NJ + r] = iD; W.rhs[NJ + r] = rh;
+        }
+    }
+    const unsigned act = __ballot_sync(FULL, active);
+    __syncwarp();
+
+    // ---- projected Gauss-Seidel, lane = DoF ----
+    const bool dof = lane < ND;
+    const int ld = dof ? lane : 0;
+    float dv = 0.f;
+    int it = 0;
+#pragma unroll 1
+    for (;; it++) {
+        float res = 0.f;
+#pragma unroll 1
+        for (int jj = 0; jj < NJ; jj++) {
+            const int j = (P.altmotor && !(it & 1)) ? NJ - 1 - jj : jj;
+            float dvj = __shfl_sync(FULL, dv, 6 + j);
+            float lj = __shfl_sync(FULL, lam_m, j);
+            float d = W.rhs[j] - dvj * W.invD[j];
+            float sum = lj + d;
+            if (sum < -P.maximp) { d = -P.maximp - lj; sum = -P.maximp; }
+            else if (sum > P.maximp) { d = P.maximp - lj; sum = P.maximp; }
+            if (lane == j) lam_m = sum;
+            if (dof) dv += W.B[j][ld] * d;
+            float rr = d * W.Dg[j];
+            res = fmaxf(res, rr * rr);
+        }
+#pragma unroll 1
+        for (int c = 0; c < NC; c++) {
+            if (!((act >> c) & 1u)) continue;
+            const int r = NJ + c;
+            float jd = warp_sum(dof ? W.J[c][ld] * dv : 0.f);
+            float lc = __shfl_sync(FULL, lam_n, c);
+            float d = W.rhs[r] - jd * W.invD[r];
+            float sum = lc + d;
+            if (sum < 0.f) { d = -lc; sum = 0.f; }
+            if (lane == c) lam_n = sum;
+            if (dof) dv += W.B[r][ld] * d;
+            float rr = d * W.Dg[r];
+            res = fmaxf(res, rr * rr);
+        }
+#pragma unroll 1
+        for (int c = 0; c < NC; c++) {
+            if (!((act >> c) & 1u)) continue;
+            const int ja = NC + 2 * c, ra = NJ + ja, rb = ra + 1;
+            float xa = dof ? W.J[ja][ld] * dv : 0.f, xb = dof ? W.J[ja + 1][ld] * dv : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { xa += __shfl_xor_sync(FULL, xa, o); xb += __shfl_xor_sync(FULL, xb, o); }
+            float lim = P.mu * __shfl_sync(FULL, lam_n, c);
+            float la = __shfl_sync(FULL, lam_a, c), lb = __shfl_sync(FULL, lam_b, c);
+            float sa = la + (W.rhs[ra] - xa * W.invD[ra]), sb = lb + (W.rhs[rb] - xb * W.invD[rb]);
+            if (P.cone) {
+                float n2 = sa * sa + sb * sb;
+                if (n2 > lim * lim) { float sc = lim * (1.f / sqrtf(n2)); sa *= sc; sb *= sc; }
+            } else {
+                sa = fminf(fmaxf(sa, -lim), lim);
+                sb = fminf(fmaxf(sb, -lim), lim);
+            }
+            float da = sa - la, db = sb - lb;
+            if (lane == c) { lam_a = sa; lam_b = sb; }
+            if (dof) dv += W.B[ra][ld] * da + W.B[rb][ld] * db;
+            float rr = da * W.Dg[ra] + db * W.Dg[rb];
+            res = fmaxf(res, rr * rr);
+        }
+        if (res <= P.resthr || it >= P.iters - 1) break;
+    }
+
+    // ---- velocity update, joint feedback, semi-implicit Euler ----
+    if (dof) W.nuF[lane] = fminf(fmaxf(W.nu[lane] + dv, -P.maxvel), P.maxvel);
+    __syncwarp();
+    float wnew[3], vnew[3];
+    m3v(W.Rw[0], W.nuF, wnew);
+    m3v(W.Rw[0], W.nuF + 3, vnew);
+    float fz;
+    {
+        float vo[3] = {W.s[SNK_S_VEL], W.s[SNK_S_VEL + 1], W.s[SNK_S_VEL + 2]};
+        float nv = sqrtf(dot3(vo, vo)), f[3], zw[3], fzax[3] = {__ldg(&T->fzax[0]), __ldg(&T->fzax[1]), __ldg(&T->fzax[2])};
+        float rm = __ldg(&T->rootm);
+#pragma unroll
+        for (int k = 0; k < 3; k++) f[k] = rm * P.g[k] - rm * vo[k] * (P.kl + P.kl * nv) - rm * (vnew[k] - vo[k]) * P.inv_dt;
+        m3v(W.Rw[0], fzax, zw);
+        fz = dot3(zw, f);
+    }
+    float qn[4];
+    {
+        float ang = sqrtf(dot3(wnew, wnew)), sc;
+        if (ang < 0.001f) sc = 0.5f * dt - dt * dt * dt * 0.020833333333f * ang * ang;
+        else sc = sinf(0.5f * ang * dt) / ang;
+        float ax[3] = {wnew[0] * sc, wnew[1] * sc, wnew[2] * sc};
+        float cw = cosf(ang * dt * 0.5f);
+        const float* q = W.s + SNK_S_QUAT;
+        float x = cw * q[0] + ax[0] * q[3] + ax[1] * q[2] - ax[2] * q[1];
+        float y = cw * q[1] + ax[1] * q[3] + ax[2] * q[0] - ax[0] * q[2];
+        float z = cw * q[2] + ax[2] * q[3] + ax[0] * q[1] - ax[1] * q[0];
+        float w = cw * q[3] - ax[0] * q[0] - ax[1] * q[1] - ax[2] * q[2];
+        float in = 1.f / sqrtf(x * x + y * y + z * z + w * w);
+        qn[0] = x * in; qn[1] = y * in; qn[2] = z * in; qn[3] = w * in;
+    }
+    __syncwarp(); // all lanes have read the old state
+    if (lane < NJ) {
+        float qd = W.nuF[6 + lane];
+        W.s[SNK_S_TAU + lane] = lam_m * P.inv_dt;
+        W.s[SNK_S_QD + lane] = qd;
+        W.s[SNK_S_Q + lane] += qd * dt;
+    }
+    if (lane == 16) W.s[SNK_S_FZ] = fz;
+    if (lane >= 17 && lane < 20) {
+        int k = lane - 17;
+        W.s[SNK_S_VEL + k] = vnew[k]; W.s[SNK_S_OMEGA + k] = wnew[k]; W.s[SNK_S_POS + k] += vnew[k] * dt;
+    }
+    if (lane >= 20 && lane < 24) W.s[SNK_S_QUAT + lane - 20] = qn[lane - 20];
+    __syncwarp();
+    return it + 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float obs_of(const WarpMem& W, int k) { // snake.py:209-217
+    if (k < 16) return W.s[SNK_S_Q + k];
+    if (k < 32) return W.s[SNK_S_QD + k - 16];
+    if (k < 48) return W.s[SNK_S_TAU + k - 32];
+    if (k < 51) return W.s[SNK_S_POS + k - 48];
+    if (k < 55) return W.s[SNK_S_QUAT + k - 51];
+    return W.s[SNK_S_FZ];
+}
+
+__device__ __forceinline__ void soft_reset(WarpMem& W, const KParams& P, int lane) { // snake.py:119-127
+    for (int k = lane; k < SNK_STATE_STRIDE; k += 32) {
+        bool keep = (k >= SNK_S_TAU && k <= SNK_S_FZ) && P.stale;
+        if (!keep) W.s[k] = (k == SNK_S_QUAT + 3) ? 1.f : 0.f;
+    }
+}
+
+// RAW = false: one SubprocVecEnv.step.  RAW = true: n_ticks raw ticks with targets[N,16] (gait script).
+template <bool RAW>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2)
+snk_step_kernel(const DevTables* __restrict__ T, const KParams P, float* __restrict__ state, const float* __restrict__ in,
+                float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks,
+                unsigned long long* __restrict__ counters, int64_t n, int n_ticks) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t env = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
+    if (env >= n) return;
+    WarpMem& W = reinterpret_cast<WarpMem*>(smem_raw)[warp];
+    float* gs = state + env * SNK_STATE_STRIDE;
+    W.s[lane] = gs[lane];
+    W.s[lane + 32] = gs[lane + 32];
+    if (lane < NJ) {
+        float tgt;
+        if (RAW) tgt = in[env * NJ + lane];
+        else { // checkBound (SnakeGymEnv.py:82-88) + createAction (snake.py:247-269) + scaling (snake.py:223-225)
+            int k = -1;
+            if (P.gait == 0) { if (!(lane & 1)) k = lane >> 1; }
+            else if (P.gait == 1) { if (lane & 1) k = lane >> 1; }
+            else k = lane;
+            float a = (k >= 0) ? in[env * P.actdim + k] : 0.f;
+            a = fminf(fmaxf(a, -1.f), 1.f);
+            tgt = a * P.sf;
+        }
+        W.target[lane] = tgt;
+    }
+    __syncwarp();
+    const float xprev = W.s[SNK_S_POS];
+    float height = fk(W, T, lane);
+    int counter = 0, iters = 0;
+    bool end_height = false;
+    if (RAW) {
+        for (int t = 0; t < n_ticks; t++) {
+            iters += tick(W, T, P, lane);
+            counter++;
+            height = fk(W, T, lane);
+        }
+    } else {
+        for (;;) { // snake.py:284-304
+            float e2 = 0.f;
+#pragma unroll 1
+            for (int j = 0; j < NJ; j++) { float d = W.target[j] - W.s[SNK_S_Q + j]; e2 += d * d; }
+            if (!(sqrtf(e2) > P.errthr)) break;
+            iters += tick(W, T, P, lane);
+            counter++;
+            height = fk(W, T, lane);
+            if (height > P.hthr) { end_height = true; break; }
+            if (counter >= P.maxticks) break;
+        }
+    }
+    if (RAW) {
+        gs[lane] = W.s[lane];
+        gs[lane + 32] = W.s[lane + 32];
+        if (lane == 0 && counters) { atomicAdd(&counters[0], (unsigned long long)counter); atomicAdd(&counters[1], (unsigned long long)iters); }
+        return;
+    }
+    const bool bad = __any_sync(FULL, !isfinite(W.s[lane]) || !isfinite(W.s[lane + 32]));
+    // reward (SnakeGymEnv.py:90-97, snake.py:336-341) and termination (SnakeGymEnv.py:99-103), every lane
+    float energy = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < NJ; j++) energy += W.s[SNK_S_QD + j] * W.s[SNK_S_TAU + j] * P.edt;
+    float r = P.alpha * (W.s[SNK_S_POS] - xprev) + ((fabsf(W.s[SNK_S_FZ]) > P.colf) ? P.colpen : 0.f) - P.beta * fabsf(W.s[SNK_S_POS + 1] - 0.f) -
+              P.gamma * energy;
+    bool d = (fabsf(obs_of(W, P.tjoint)) > P.tang) || (height > P.hthr) || end_height;
+    if (bad) { d = true; r = P.donepen; }
+    else if (d) r += P.donepen;
+    __syncwarp();
+    if (bad) { W.s[lane] = 0.f; W.s[lane + 32] = 0.f; __syncwarp(); }
+    if (lane == 0) { W.s[SNK_S_RET] += r; W.s[SNK_S_LEN] += 1.f; }
+    __syncwarp();
+    if (d) { soft_reset(W, P, lane); __syncwarp(); } // in-step reset + worker reset: post-reset obs (multiprocessing_env.py:14-15)
+    float* go = obs + env * SNK_OBS_DIM;
+    go[lane] = obs_of(W, lane);
+    if (lane + 32 < SNK_OBS_DIM) go[lane + 32] = obs_of(W, lane + 32);
+    gs[lane] = W.s[lane];
+    gs[lane + 32] = W.s[lane + 32];
+    if (lane == 0) {
+        rew[env] = r;
+        done[env] = d ? 1 : 0;
+        if (ticks) ticks[env] = counter;
+        if (counters) {
+            atomicAdd(&counters[0], (unsigned long long)counter);
+            atomicAdd(&counters[1], (unsigned long long)iters);
+            if (d) atomicAdd(&counters[2], 1ull);
+            if (bad) atomicAdd(&counters[3], 1ull);
+        }
+    }
+}
+
+// reset / observe: one thread per (env, state slot).  mode 0 = masked soft reset (+ optional obs of
+// every env), 1 = initialise everything, 2 = observe only.
+__global__ void snk_reset_kernel(const KParams P, float* __restrict__ state, const uint8_t* __restrict__ mask, float* __restrict__ obs,
+                                 int64_t n, int mode) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t env = idx >> 6;
+    int k = (int)(idx & 63);
+    if (env >= n) return;
+    float* s = state + env * SNK_STATE_STRIDE;
+    float val = s[k];
+    const bool hit = (mode == 1) || (mode == 0 && (!mask || mask[env]));
+    if (hit) {
+        bool keep = (k >= SNK_S_TAU && k <= SNK_S_FZ) && P.stale && mode == 0;
+        if (!keep) { val = (k == SNK_S_QUAT + 3) ? 1.f : 0.f; s[k] = val; }
+    }
+    if (obs && k < SNK_S_RET) { // state slot -> observation index (snake.py:209-217)
+        int o = (k < SNK_S_QUAT) ? 48 + k : (k < SNK_S_VEL) ? 51 + (k - SNK_S_QUAT) : (k < SNK_S_Q) ? -1 : (k < SNK_S_QD) ? k - SNK_S_Q
+                : (k < SNK_S_TAU) ? 16 + (k - SNK_S_QD) : (k < SNK_S_FZ) ? 32 + (k - SNK_S_TAU) : 55;
+        if (o >= 0) obs[env * SNK_OBS_DIM + o] = val;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch wrappers used by the C-ABI host code (snake_abi.cu)
+// ---------------------------------------------------------------------------------------------
+size_t snk_step_smem_bytes() { return sizeof(WarpMem) * WARPS_PER_CTA; }
+
+cudaError_t snk_configure_kernels() {
+    cudaError_t e = cudaFuncSetAttribute(snk_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)snk_step_smem_bytes());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(snk_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)snk_step_smem_bytes());
+}
+
+cudaError_t snk_launch_step(const DevTables* T, const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
+                            int32_t* ticks, unsigned long long* counters, int64_t n, cudaStream_t st) {
+    dim3 grid((unsigned)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA)), block(WARPS_PER_CTA * 32);
+    snk_step_kernel<false><<<grid, block, snk_step_smem_bytes(), st>>>(T, P, state, actions, obs, rew, done, ticks, counters, n, 0);
+    return cudaGetLastError();
+}
+
+cudaError_t snk_launch_tick(const DevTables* T, const KParams& P, float* state, const float* targets, unsigned long long* counters, int64_t n,
+                            int n_ticks, cudaStream_t st) {
+    dim3 grid((unsigned)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA)), block(WARPS_PER_CTA * 32);
+    snk_step_kernel<true><<<grid, block, snk_step_smem_bytes(), st>>>(T, P, state, targets, nullptr, nullptr, nullptr, nullptr, counters, n, n_ticks);
+    return cudaGetLastError();
+}
+
+cudaError_t snk_launch_reset(const KParams& P, float* state, const uint8_t* mask, float* obs, int64_t n, int mode, cudaStream_t st) {
+    int64_t total = n * 64;
+    dim3 grid((unsigned)((total + 255) / 256)), block(256);
+    snk_reset_kernel<<<grid, block, 0, st>>>(P, state, mask, obs, n, mode);
+    return cudaGetLastError();
+}

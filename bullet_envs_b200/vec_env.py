@@ -1,0 +1,198 @@
+"""Device-resident drop-in for the reference's vector environment.
+
+:class:`SnakeVecEnv` keeps the interface of ``SubprocVecEnv`` (reference
+``ppo/multiprocessing_env.py:31-153``: ``reset``, ``step``, ``step_async``/``step_wait``, ``close``,
+``__len__``, ``num_envs``/``nenvs``, ``observation_space``, ``action_space``) but replaces the N
+worker processes, pipes and PyBullet clients by one batch of N environments resident in HBM and one
+CUDA kernel launch per ``step``.  Semantics are those of the worker loop (``:11-16``): on ``done``
+the returned observation is the post-reset one.
+
+* numpy actions in  -> numpy ``(obs[N,56], rews[N], dones[N] bool, infos)`` out, through the
+  C-ABI ``snk_step_host`` (pinned H2D / D2H inside the library) -- the strict drop-in for
+  ``ppo/train.py:122`` and ``ars/train.py:99``;
+* CUDA torch actions in -> CUDA torch tensors out, zero-copy on the current torch stream; pass
+  ``out=(obs, rew, done)`` to have the kernel write straight into rollout-buffer slices.
+
+PyTorch is used for device memory and streams only.  There is no CPU fallback: constructing the
+class without the CUDA extension or without a GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _abi
+from .spaces import Box
+from .urdf_model import OBS_DIM, STATE_STRIDE, NJ, build_model
+
+
+class SnakeVecEnv:
+    def __init__(self, env_fns=None, num_envs=None, args=None, device=None, urdf_path=None, params=None,
+                 model=None, obs_dtype=np.float64):
+        """``env_fns``: list of thunks as given to ``SubprocVecEnv`` (only its length is used -- the
+        thunks would build PyBullet-backed envs) *or* pass ``num_envs``.  ``args``: the reference's
+        argparse namespace (``ppo/params.py``) or None for the defaults.  ``device``: CUDA device
+        index / ``torch.device``."""
+        import torch
+
+        if env_fns is not None and num_envs is None:
+            num_envs = env_fns if isinstance(env_fns, int) else len(env_fns)
+        if not num_envs or num_envs <= 0:
+            raise ValueError("num_envs must be positive")
+        self._torch = torch
+        self._lib = _abi.load_library()
+        if device is None:
+            dev_index = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        else:
+            d = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
+            dev_index = d.index if d.index is not None else 0
+        self.device = torch.device("cuda", dev_index)
+        self.params = params if params is not None else _abi.default_params(args)
+        self.model = model if model is not None else build_model(urdf_path)
+        self._cmodel = self.model.to_ctypes()
+        self._h = ctypes.c_void_p()
+        _abi.check(self._lib.snk_create(ctypes.byref(self._cmodel), ctypes.byref(self.params), int(num_envs), dev_index,
+                                        ctypes.byref(self._h)), self._lib)
+        self.num_envs = self.nenvs = int(num_envs)
+        self.act_dim = int(self._lib.snk_action_dim(self._h))
+        self.obs_dtype = obs_dtype
+        self.waiting = False
+        self.closed = False
+        self._pending = None
+        self._infos = tuple({} for _ in range(self.num_envs))  # SnakeGymEnv.py:45-46 (train mode)
+        # spaces: snake.py:166-177, SnakeGymEnv.py:60-79
+        hi = np.zeros(OBS_DIM)
+        hi[0:NJ] = np.pi
+        hi[NJ:3 * NJ] = np.inf
+        hi[3 * NJ:] = 1.0
+        self.observation_space = Box(-hi, hi)
+        self.action_space = Box(-np.ones(self.act_dim), np.ones(self.act_dim))
+        self.last_ticks = None
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return ctypes.c_void_p(self._torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _ptr(t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def _check_open(self):
+        if self.closed or not self._h:
+            raise RuntimeError("SnakeVecEnv is closed")
+
+    # ------------------------------------------------------------------ SubprocVecEnv surface
+    def reset(self, mask=None, as_torch=False):
+        """Soft reset (``snake.py:119-127``) of all environments (or of ``mask``); returns obs [N,56]."""
+        self._check_open()
+        torch = self._torch
+        if as_torch or (mask is not None and torch.is_tensor(mask) and mask.is_cuda):
+            obs = torch.empty((self.num_envs, OBS_DIM), dtype=torch.float32, device=self.device)
+            m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            _abi.check(self._lib.snk_reset(self._h, None if m is None else self._ptr(m), self._ptr(obs), self._stream()), self._lib)
+            return obs
+        obs = np.empty((self.num_envs, OBS_DIM), np.float32)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        _abi.check(self._lib.snk_reset_host(self._h, None if m is None else ctypes.c_void_p(m.ctypes.data),
+                                            ctypes.c_void_p(obs.ctypes.data)), self._lib)
+        return obs.astype(self.obs_dtype, copy=False)
+
+    def step_async(self, actions, out=None):
+        self._check_open()
+        torch = self._torch
+        if torch.is_tensor(actions) and actions.is_cuda:
+            a = actions.to(dtype=torch.float32).contiguous().view(self.num_envs, self.act_dim)
+            if out is None:
+                obs = torch.empty((self.num_envs, OBS_DIM), dtype=torch.float32, device=self.device)
+                rew = torch.empty((self.num_envs,), dtype=torch.float32, device=self.device)
+                done = torch.empty((self.num_envs,), dtype=torch.uint8, device=self.device)
+            else:
+                obs, rew, done = out
+                for t, shape, dt in ((obs, (self.num_envs, OBS_DIM), torch.float32), (rew, (self.num_envs,), torch.float32),
+                                     (done, (self.num_envs,), torch.uint8)):
+                    if not (t.is_cuda and t.is_contiguous() and t.dtype == dt and tuple(t.shape) == shape):
+                        raise ValueError("out tensors must be contiguous CUDA tensors obs[N,56] f32, rew[N] f32, done[N] u8")
+            ticks = torch.empty((self.num_envs,), dtype=torch.int32, device=self.device)
+            _abi.check(self._lib.snk_step(self._h, self._ptr(a), self._ptr(obs), self._ptr(rew), self._ptr(done), self._ptr(ticks),
+                                          self._stream()), self._lib)
+            self._pending = ("torch", obs, rew, done, ticks)
+        else:
+            a = np.ascontiguousarray(np.asarray(actions), np.float32).reshape(self.num_envs, self.act_dim)
+            obs = np.empty((self.num_envs, OBS_DIM), np.float32)
+            rew = np.empty(self.num_envs, np.float32)
+            done = np.empty(self.num_envs, np.uint8)
+            ticks = np.empty(self.num_envs, np.int32)
+            p = lambda x: ctypes.c_void_p(x.ctypes.data)
+            _abi.check(self._lib.snk_step_host(self._h, p(a), p(obs), p(rew), p(done), p(ticks)), self._lib)
+            self._pending = ("numpy", obs, rew, done, ticks)
+        self.waiting = True
+
+    def step_wait(self):
+        if self._pending is None:
+            raise RuntimeError("step_wait() without step_async()")
+        kind, obs, rew, done, ticks = self._pending
+        self._pending = None
+        self.waiting = False
+        self.last_ticks = ticks
+        if kind == "torch":
+            return obs, rew, done.bool(), self._infos
+        return obs.astype(self.obs_dtype, copy=False), rew.astype(self.obs_dtype, copy=False), done.astype(bool), self._infos
+
+    def step(self, actions, out=None):
+        self.step_async(actions, out=out)
+        return self.step_wait()
+
+    def close(self):
+        if self.closed:
+            return
+        self.closed = True
+        if self._h:
+            self._lib.snk_destroy(self._h)
+            self._h = None
+
+    def __len__(self):
+        return self.nenvs
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ extras (parity harness, gait script)
+    def tick(self, targets, n_ticks=1):
+        """Raw physics ticks with joint targets [N,16] (``snake_gait_test.py:96-104``)."""
+        self._check_open()
+        torch = self._torch
+        t = torch.as_tensor(np.asarray(targets, np.float32) if not torch.is_tensor(targets) else targets, dtype=torch.float32,
+                            device=self.device).contiguous().view(self.num_envs, NJ)
+        _abi.check(self._lib.snk_tick(self._h, self._ptr(t), int(n_ticks), self._stream()), self._lib)
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def observe(self):
+        torch = self._torch
+        obs = torch.empty((self.num_envs, OBS_DIM), dtype=torch.float32, device=self.device)
+        _abi.check(self._lib.snk_observe(self._h, self._ptr(obs), self._stream()), self._lib)
+        return obs
+
+    def get_state(self):
+        torch = self._torch
+        s = torch.empty((self.num_envs, STATE_STRIDE), dtype=torch.float32, device=self.device)
+        _abi.check(self._lib.snk_get_state(self._h, self._ptr(s), self._stream()), self._lib)
+        return s
+
+    def set_state(self, state):
+        torch = self._torch
+        s = torch.as_tensor(state, dtype=torch.float32, device=self.device).contiguous().view(self.num_envs, STATE_STRIDE)
+        _abi.check(self._lib.snk_set_state(self._h, self._ptr(s), self._stream()), self._lib)
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def counters(self):
+        """Device counters of the last step launch: ticks, PGS iterations, dones, non-finite resets."""
+        out = (ctypes.c_int64 * 4)()
+        _abi.check(self._lib.snk_last_counters(self._h, out), self._lib)
+        return dict(ticks=out[0], pgs_iterations=out[1], dones=out[2], nonfinite=out[3])
+
+    def launch_count(self):
+        return int(self._lib.snk_launch_count(self._h))

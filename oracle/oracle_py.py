@@ -1,0 +1,133 @@
+"""ctypes front-end of the CPU oracle (oracle/snake_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs; nothing under bullet_envs_b200/ imports this module.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+from bullet_envs_b200._abi import CParams, default_params  # noqa: E402  (ABI structs only)
+from bullet_envs_b200.urdf_model import CModel, build_model, NJ, OBS_DIM, STATE_STRIDE  # noqa: E402
+
+LIB = os.path.join(_HERE, "_ref", "libsnake_oracle.so")
+
+
+def build(force=False):
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(os.path.join(_HERE, "snake_oracle.c")):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return LIB
+
+
+_libs = {}
+
+
+def _load():
+    if "lib" not in _libs:
+        if not os.path.exists(LIB):
+            build()
+        _libs["lib"] = ctypes.CDLL(LIB)
+    return _libs["lib"]
+
+
+class Oracle:
+    """N independent snake environments stepped on the CPU in fp64 (or fp32 with ``f32=True``)."""
+
+    def __init__(self, n_envs, params: CParams | None = None, model=None, f32=False):
+        lib = _load()
+        self.pfx = "snk_cpu32_" if f32 else "snk_cpu_"
+        self.dtype = np.float32 if f32 else np.float64
+        self.n = int(n_envs)
+        self.params = params or default_params()
+        self.model = model or build_model()
+        self._cm = self.model.to_ctypes()
+        self._h = ctypes.c_void_p()
+        f = self._fn("create")
+        f.argtypes = [ctypes.POINTER(CModel), ctypes.POINTER(CParams), ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p)]
+        rc = f(ctypes.byref(self._cm), ctypes.byref(self.params), self.n, ctypes.byref(self._h))
+        if rc != 0:
+            raise RuntimeError("oracle create failed: %d" % rc)
+        self.act_dim = self._fn("action_dim")(self._h)
+        for name in ("reset", "step", "step_range", "tick", "observe", "get_state", "set_state", "counters", "kinematics", "destroy"):
+            getattr(lib, self.pfx + name).restype = ctypes.c_int
+
+    def _fn(self, name):
+        return getattr(_load(), self.pfx + name)
+
+    @staticmethod
+    def _p(a):
+        return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+    def close(self):
+        if self._h:
+            self._fn("destroy")(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self, mask=None):
+        obs = np.empty((self.n, OBS_DIM), self.dtype)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        self._fn("reset")(self._h, self._p(m), self._p(obs))
+        return obs
+
+    def step(self, actions, threads=1):
+        a = np.ascontiguousarray(actions, self.dtype).reshape(self.n, self.act_dim)
+        obs = np.empty((self.n, OBS_DIM), self.dtype)
+        rew = np.empty(self.n, self.dtype)
+        done = np.empty(self.n, np.uint8)
+        ticks = np.empty(self.n, np.int32)
+        if threads <= 1:
+            self._fn("step")(self._h, self._p(a), self._p(obs), self._p(rew), self._p(done), self._p(ticks))
+        else:
+            f = self._fn("step_range")
+            bounds = np.linspace(0, self.n, threads + 1).astype(np.int64)
+            with ThreadPoolExecutor(threads) as ex:
+                list(ex.map(lambda i: f(self._h, ctypes.c_int64(int(bounds[i])), ctypes.c_int64(int(bounds[i + 1])),
+                                        self._p(a), self._p(obs), self._p(rew), self._p(done), self._p(ticks)),
+                            range(threads)))
+        return obs, rew, done.astype(bool), ticks
+
+    def tick(self, targets, n_ticks=1):
+        t = np.ascontiguousarray(targets, self.dtype).reshape(self.n, NJ)
+        iters = np.empty(self.n, np.int32)
+        self._fn("tick")(self._h, self._p(t), ctypes.c_int32(n_ticks), self._p(iters))
+        return iters
+
+    def observe(self):
+        obs = np.empty((self.n, OBS_DIM), self.dtype)
+        self._fn("observe")(self._h, self._p(obs))
+        return obs
+
+    def get_state(self):
+        s = np.empty((self.n, STATE_STRIDE), self.dtype)
+        self._fn("get_state")(self._h, self._p(s))
+        return s
+
+    def set_state(self, s):
+        s = np.ascontiguousarray(s, self.dtype).reshape(self.n, STATE_STRIDE)
+        self._fn("set_state")(self._h, self._p(s))
+
+    def counters(self, clear=False):
+        out = (ctypes.c_int64 * 4)()
+        self._fn("counters")(self._h, out, ctypes.c_int(int(clear)))
+        return dict(ticks=out[0], pgs_iterations=out[1], dones=out[2], nonfinite=out[3])
+
+    def kinematics(self, e=0):
+        Rw = np.empty((17, 3, 3), self.dtype)
+        pw = np.empty((17, 3), self.dtype)
+        h = np.empty(1, self.dtype)
+        self._fn("kinematics")(self._h, ctypes.c_int64(e), self._p(Rw), self._p(pw), self._p(h))
+        return Rw, pw, float(h[0])
