@@ -30,7 +30,7 @@ class CParams(ctypes.Structure):
         ("collision_force", ctypes.c_double), ("collision_penalty", ctypes.c_double),
         ("solver_iterations", ctypes.c_int32), ("max_ticks", ctypes.c_int32), ("gait_selection", ctypes.c_int32),
         ("cone_friction", ctypes.c_int32), ("term_joint", ctypes.c_int32), ("stale_obs_on_reset", ctypes.c_int32),
-        ("alternate_motor_order", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("alternate_motor_order", ctypes.c_int32), ("motor_solver", ctypes.c_int32),
     ]
 
 
@@ -57,6 +57,7 @@ def default_params(args=None, **overrides) -> CParams:
     p.done_penalty, p.collision_force, p.collision_penalty = -5.0, 10.0, -10.0
     p.solver_iterations, p.max_ticks, p.gait_selection = 50, 41, 1
     p.cone_friction, p.term_joint, p.stale_obs_on_reset, p.alternate_motor_order = 1, 9, 1, 1
+    p.motor_solver = 2  # auto: motor rows eliminated exactly when force = inf and kd = 1 (the reference's setting)
     if args is not None:
         p.alpha, p.beta, p.gamma = float(args.alpha), float(args.beta), float(args.gamma)
         p.gait_selection = int(args.gaitSelection)

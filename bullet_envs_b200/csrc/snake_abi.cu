@@ -10,15 +10,23 @@
 
 #include <new>
 
-#include "snake_step.cuh"
+#include "snake_host.h"
 
-size_t snk_step_smem_bytes();
-cudaError_t snk_configure_kernels();
-cudaError_t snk_launch_step(const DevTables* T, const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
-                            int32_t* ticks, unsigned long long* counters, int64_t n, cudaStream_t st);
-cudaError_t snk_launch_tick(const DevTables* T, const KParams& P, float* state, const float* targets, unsigned long long* counters, int64_t n,
-                            int n_ticks, cudaStream_t st);
-cudaError_t snk_launch_reset(const KParams& P, float* state, const uint8_t* mask, float* obs, int64_t n, int mode, cudaStream_t st);
+// warp-per-env kernel with Bullet-order motor rows (snake_pgs.cu)
+cudaError_t snk_pgs_configure();
+cudaError_t snk_pgs_launch_step(const DevTables* T, const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
+                                int32_t* ticks, unsigned long long* counters, int64_t n, cudaStream_t st);
+cudaError_t snk_pgs_launch_tick(const DevTables* T, const KParams& P, float* state, const float* targets, unsigned long long* counters, int64_t n,
+                                int n_ticks, cudaStream_t st);
+// thread-per-env kernel with the motor rows eliminated (snake_exact.cu)
+cudaError_t snk_exact_configure(const ExTables* host_tables);
+cudaError_t snk_exact_launch_step(const KParams& P, float* state, int64_t npad, const float* actions, float* obs, float* rew, uint8_t* done,
+                                  int32_t* ticks, unsigned long long* counters, int64_t n, cudaStream_t st);
+cudaError_t snk_exact_launch_tick(const KParams& P, float* state, int64_t npad, const float* targets, unsigned long long* counters, int64_t n,
+                                  int n_ticks, cudaStream_t st);
+// layout-aware reset / observe and state import / export (snake_pgs.cu)
+cudaError_t snk_launch_reset(const KParams& P, float* state, int64_t npad, const uint8_t* mask, float* obs, int64_t n, int mode, cudaStream_t st);
+cudaError_t snk_launch_transpose(const float* src, float* dst, int64_t n, int64_t npad, int to_soa, cudaStream_t st);
 
 static thread_local char g_err[512] = "";
 
@@ -35,9 +43,10 @@ static int fail(int code, const char* fmt, const char* detail = "") {
 struct snk_handle {
     int device;
     int64_t n;
+    int64_t npad;                 // 0: state is [n][64] (warp-per-env kernel); else [64][npad] (thread-per-env kernel)
     KParams P;
-    DevTables* T;                 // device
-    float* state;                 // device [n,64]
+    DevTables* T;                 // device (warp-per-env kernel only)
+    float* state;                 // device
     unsigned long long* counters; // device [4]
     int64_t launches;
     // staging for the *_host entry points (allocated on first use)
@@ -51,45 +60,9 @@ struct snk_handle {
     bool staged;
 };
 
-static void to_tables(const snk_model* M, DevTables* T) {
-    memset(T, 0, sizeof *T);
-    for (int i = 0; i < NJ; i++) {
-        for (int k = 0; k < 9; k++) T->jR0[i][k] = (float)M->joint_R0[i][k];
-        for (int k = 0; k < 3; k++) { T->jt[i][k] = (float)M->joint_t[i][k]; T->jax[i][k] = (float)M->joint_axis[i][k]; }
-        T->jdamp[i] = (float)M->joint_damping[i];
-    }
-    for (int b = 0; b < NB; b++) {
-        T->mass[b] = (float)M->body_mass[b];
-        for (int k = 0; k < 3; k++) { T->com[b][k] = (float)M->body_com[b][k]; T->hpt[b][k] = (float)M->height_pt[b][k]; }
-        for (int k = 0; k < 9; k++) T->Ic[b][k] = (float)M->body_inertia[b][k];
-        T->hbody[b] = M->height_body[b];
-    }
-    for (int c = 0; c < NC; c++) {
-        for (int k = 0; k < 3; k++) { T->ccen[c][k] = (float)M->cyl_center[c][k]; T->cax[c][k] = (float)M->cyl_axis[c][k]; }
-        for (int k = 0; k < 9; k++) T->cfr[c][k] = (float)M->cyl_fric_R[c][k];
-        T->crad[c] = (float)M->cyl_radius[c]; T->chl[c] = (float)M->cyl_halflen[c]; T->cend[c] = (float)M->cyl_end[c];
-        T->cmar[c] = (float)M->cyl_margin[c]; T->cbrk[c] = (float)M->cyl_break[c];
-        T->cbody[c] = M->cyl_body[c];
-    }
-    for (int k = 0; k < 3; k++) T->fzax[k] = (float)M->fz_axis[k];
-    T->rootm = (float)M->root_mass;
-}
-
-static void to_kparams(const snk_params* p, KParams* P) {
-    memset(P, 0, sizeof *P);
-    P->dt = (float)p->dt; P->inv_dt = (float)(1.0 / p->dt);
-    for (int k = 0; k < 3; k++) { P->g[k] = (float)p->gravity[k]; P->aniso[k] = (float)p->aniso[k]; }
-    P->kp = (float)p->motor_kp; P->kd = (float)p->motor_kd;
-    P->maximp = isinf(p->motor_max_force) ? INFINITY : (float)(p->motor_max_force * p->dt);
-    P->sf = (float)p->scaling_factor; P->alpha = (float)p->alpha; P->beta = (float)p->beta; P->gamma = (float)p->gamma;
-    P->edt = (float)p->energy_dt; P->mu = (float)p->friction; P->kl = (float)p->lin_damping; P->ka = (float)p->ang_damping;
-    P->erp2 = (float)p->erp2; P->slop = (float)p->linear_slop; P->resthr = (float)p->residual_threshold;
-    P->maxvel = (float)p->max_coord_vel; P->errthr = (float)p->err_threshold; P->hthr = (float)p->height_threshold;
-    P->tang = (float)p->term_angle; P->donepen = (float)p->done_penalty; P->colf = (float)p->collision_force;
-    P->colpen = (float)p->collision_penalty; P->iters = p->solver_iterations; P->maxticks = p->max_ticks;
-    P->gait = p->gait_selection; P->cone = p->cone_friction; P->tjoint = p->term_joint; P->stale = p->stale_obs_on_reset;
-    P->altmotor = p->alternate_motor_order;
-    P->actdim = (p->gait_selection == 0 || p->gait_selection == 1) ? NJ / 2 : NJ; // SnakeGymEnv.py:72-76
+static cudaError_t launch_step(snk_handle* h, const float* act, float* obs, float* rew, uint8_t* done, int32_t* ticks, cudaStream_t st) {
+    if (h->npad) return snk_exact_launch_step(h->P, h->state, h->npad, act, obs, rew, done, ticks, h->counters, h->n, st);
+    return snk_pgs_launch_step(h->T, h->P, h->state, act, obs, rew, done, ticks, h->counters, h->n, st);
 }
 
 extern "C" {
@@ -97,7 +70,7 @@ extern "C" {
 const char* snk_last_error(void) { return g_err; }
 
 const char* snk_build_info(void) {
-    return "snake_b200 sm_100a; warp-per-env fused env-step; built " __DATE__ " " __TIME__;
+    return "snake_b200 sm_100a; fused env-step kernels: thread-per-env (motor rows eliminated) and warp-per-env (Bullet-order PGS); built " __DATE__ " " __TIME__;
 }
 
 int snk_default_params(snk_params* p) {
@@ -112,7 +85,7 @@ int snk_default_params(snk_params* p) {
     p->max_coord_vel = 100.0; p->err_threshold = 0.05; p->height_threshold = 0.1; p->term_angle = 0.5;
     p->done_penalty = -5.0; p->collision_force = 10.0; p->collision_penalty = -10.0;
     p->solver_iterations = 50; p->max_ticks = 41; p->gait_selection = 1; p->cone_friction = 1; p->term_joint = 9;
-    p->stale_obs_on_reset = 1; p->alternate_motor_order = 1; p->reserved0 = 0;
+    p->stale_obs_on_reset = 1; p->alternate_motor_order = 1; p->motor_solver = 2;
     return 0;
 }
 
@@ -131,20 +104,30 @@ int snk_create(const snk_model* model, const snk_params* params, int64_t n_envs,
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(SNK_E_NODEV, "snk_create: kernels are built for sm_100a only, found %s", prop.name);
-    CU(snk_configure_kernels());
+    if (params->motor_solver < 0 || params->motor_solver > 2) return fail(SNK_E_ARG, "snk_create: motor_solver must be 0, 1 or 2%s");
     snk_handle* h = new (std::nothrow) snk_handle();
     if (!h) return fail(SNK_E_NOMEM, "snk_create: out of host memory%s");
     memset(h, 0, sizeof *h);
     h->device = device; h->n = n_envs;
-    to_kparams(params, &h->P);
-    DevTables host_tables;
-    to_tables(model, &host_tables);
-    cudaError_t err = cudaMalloc(&h->T, sizeof(DevTables));
-    if (err == cudaSuccess) err = cudaMalloc(&h->state, (size_t)n_envs * SNK_STATE_STRIDE * sizeof(float));
+    snk_to_kparams(params, &h->P);
+    cudaError_t err = cudaSuccess;
+    if (h->P.exact) { // thread-per-env kernel: tables in constant memory, state as [slot][env]
+        ExTables xt;
+        if (snk_to_extables(model, &xt)) { delete h; return fail(SNK_E_ARG, "snk_create: model layout not supported by the exact motor solver%s"); }
+        h->npad = (n_envs + EB - 1) / EB * EB;
+        err = snk_exact_configure(&xt);
+    } else {
+        DevTables host_tables;
+        snk_to_tables(model, &host_tables);
+        err = snk_pgs_configure();
+        if (err == cudaSuccess) err = cudaMalloc(&h->T, sizeof(DevTables));
+        if (err == cudaSuccess) err = cudaMemcpy(h->T, &host_tables, sizeof host_tables, cudaMemcpyHostToDevice);
+    }
+    const size_t cols = (size_t)(h->npad ? h->npad : n_envs);
+    if (err == cudaSuccess) err = cudaMalloc(&h->state, cols * SNK_STATE_STRIDE * sizeof(float));
     if (err == cudaSuccess) err = cudaMalloc(&h->counters, 4 * sizeof(unsigned long long));
-    if (err == cudaSuccess) err = cudaMemcpy(h->T, &host_tables, sizeof host_tables, cudaMemcpyHostToDevice);
     if (err == cudaSuccess) err = cudaMemset(h->counters, 0, 4 * sizeof(unsigned long long));
-    if (err == cudaSuccess) err = snk_launch_reset(h->P, h->state, nullptr, nullptr, h->n, 1, 0);
+    if (err == cudaSuccess) err = snk_launch_reset(h->P, h->state, h->npad, nullptr, nullptr, h->n, 1, 0);
     if (err == cudaSuccess) err = cudaDeviceSynchronize();
     if (err != cudaSuccess) {
         cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters);
@@ -179,7 +162,7 @@ int64_t snk_launch_count(const snk_handle* h) { return h ? h->launches : 0; }
 int snk_reset(snk_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
     if (!h) return fail(SNK_E_ARG, "snk_reset: null handle%s");
     CU(cudaSetDevice(h->device));
-    CU(snk_launch_reset(h->P, h->state, mask_dev, obs_dev, h->n, 0, (cudaStream_t)stream));
+    CU(snk_launch_reset(h->P, h->state, h->npad, mask_dev, obs_dev, h->n, 0, (cudaStream_t)stream));
     h->launches++;
     return 0;
 }
@@ -187,7 +170,7 @@ int snk_reset(snk_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stre
 int snk_observe(snk_handle* h, float* obs_dev, void* stream) {
     if (!h || !obs_dev) return fail(SNK_E_ARG, "snk_observe: null pointer%s");
     CU(cudaSetDevice(h->device));
-    CU(snk_launch_reset(h->P, h->state, nullptr, obs_dev, h->n, 2, (cudaStream_t)stream));
+    CU(snk_launch_reset(h->P, h->state, h->npad, nullptr, obs_dev, h->n, 2, (cudaStream_t)stream));
     h->launches++;
     return 0;
 }
@@ -197,7 +180,7 @@ int snk_step(snk_handle* h, const float* actions_dev, float* obs_dev, float* rew
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaMemsetAsync(h->counters, 0, 4 * sizeof(unsigned long long), st));
-    CU(snk_launch_step(h->T, h->P, h->state, actions_dev, obs_dev, rew_dev, done_dev, ticks_dev, h->counters, h->n, st));
+    CU(launch_step(h, actions_dev, obs_dev, rew_dev, done_dev, ticks_dev, st));
     h->launches++;
     return 0;
 }
@@ -207,7 +190,8 @@ int snk_tick(snk_handle* h, const float* targets_dev, int32_t n_ticks, void* str
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaMemsetAsync(h->counters, 0, 4 * sizeof(unsigned long long), st));
-    CU(snk_launch_tick(h->T, h->P, h->state, targets_dev, h->counters, h->n, n_ticks, st));
+    if (h->npad) CU(snk_exact_launch_tick(h->P, h->state, h->npad, targets_dev, h->counters, h->n, n_ticks, st));
+    else CU(snk_pgs_launch_tick(h->T, h->P, h->state, targets_dev, h->counters, h->n, n_ticks, st));
     h->launches++;
     return 0;
 }
@@ -242,7 +226,7 @@ int snk_step_host(snk_handle* h, const float* actions_host, float* obs_host, flo
     memcpy(h->h_act, actions_host, na);
     CU(cudaMemcpyAsync(h->d_act, h->h_act, na, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(h->counters, 0, 4 * sizeof(unsigned long long), st));
-    CU(snk_launch_step(h->T, h->P, h->state, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_ticks, h->counters, h->n, st));
+    CU(launch_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_ticks, st));
     h->launches++;
     CU(cudaMemcpyAsync(h->h_obs, h->d_obs, n * SNK_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h->h_rew, h->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -267,7 +251,7 @@ int snk_reset_host(snk_handle* h, const uint8_t* mask_host, float* obs_host) {
         memcpy(h->h_mask, mask_host, n);
         CU(cudaMemcpyAsync(h->d_mask, h->h_mask, n, cudaMemcpyHostToDevice, st));
     }
-    CU(snk_launch_reset(h->P, h->state, mask_host ? h->d_mask : nullptr, obs_host ? h->d_obs : nullptr, h->n, 0, st));
+    CU(snk_launch_reset(h->P, h->state, h->npad, mask_host ? h->d_mask : nullptr, obs_host ? h->d_obs : nullptr, h->n, 0, st));
     h->launches++;
     if (obs_host) CU(cudaMemcpyAsync(h->h_obs, h->d_obs, n * SNK_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -278,14 +262,16 @@ int snk_reset_host(snk_handle* h, const uint8_t* mask_host, float* obs_host) {
 int snk_get_state(snk_handle* h, float* state_dev, void* stream) {
     if (!h || !state_dev) return fail(SNK_E_ARG, "snk_get_state: null pointer%s");
     CU(cudaSetDevice(h->device));
-    CU(cudaMemcpyAsync(state_dev, h->state, (size_t)h->n * SNK_STATE_STRIDE * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    if (h->npad) { CU(snk_launch_transpose(h->state, state_dev, h->n, h->npad, 0, (cudaStream_t)stream)); h->launches++; }
+    else CU(cudaMemcpyAsync(state_dev, h->state, (size_t)h->n * SNK_STATE_STRIDE * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
 }
 
 int snk_set_state(snk_handle* h, const float* state_dev, void* stream) {
     if (!h || !state_dev) return fail(SNK_E_ARG, "snk_set_state: null pointer%s");
     CU(cudaSetDevice(h->device));
-    CU(cudaMemcpyAsync(h->state, state_dev, (size_t)h->n * SNK_STATE_STRIDE * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    if (h->npad) { CU(snk_launch_transpose(state_dev, h->state, h->n, h->npad, 1, (cudaStream_t)stream)); h->launches++; }
+    else CU(cudaMemcpyAsync(h->state, state_dev, (size_t)h->n * SNK_STATE_STRIDE * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
 }
 

@@ -1,0 +1,598 @@
+// snake_exact_core.cuh -- one environment per THREAD: the env-step with the motor rows eliminated.
+//
+// With the reference's motor settings (force = inf, snake.py:26-27; PyBullet default kd = 1) every
+// motor row of the solver is the equality qd_j+ = kp (q*_j - q_j)/dt, so the 16 joints move on a
+// prescribed trajectory and only the 6 rigid degrees of freedom of the whole chain remain unknown.
+// The tick is then (oracle: tick_exact in oracle/snake_oracle.c, same rows, order, clamps, residual):
+//   pass 1  tip-ward walk in world axes: kinematics, velocities, reference accelerations (base
+//           acceleration zero, joint accelerations prescribed), Newton-Euler wrench of every body,
+//           composite inertia of the frozen chain, cylinder-vs-plane contact geometry;
+//   solve   the free rigid acceleration about the chain's centre of mass C (there the 6x6 composite
+//           inertia is block diagonal: mass and a 3x3 rotational inertia);
+//   rows    per contact: lever arm about C, effective masses, right-hand sides;
+//   PGS     projected Gauss-Seidel on the rigid twist (6 numbers in registers): all normal rows, then
+//           all friction pairs (implicit cone), <= 50 sweeps, Bullet's residual early exit;
+//   pass 2  base-ward walk: inverse dynamics with the contact impulses -> applied motor torques
+//           (getJointState()[3]), joint integration;
+//   finish  base velocity/pose integration, joint-0 reaction force.
+//
+// Data placement: the 13 base-state floats and the chain cursor live in
+// registers; the 18 floats per contact x 32 contacts live in shared memory as [contact][thread]
+// columns (bank = thread, conflict free); joint angles/velocities/torques stay in the handle's
+// structure-of-arrays state in global memory ([slot][env], one coalesced 128 B line per warp access,
+// L2 resident for the whole env-step); model tables are read from constant memory at warp-uniform
+// addresses.
+//
+// Everything here is __host__ __device__ so that tests/hostemu can run the very same fp32 code on the
+// CPU (development check only; the product library contains the device instantiation only).
+#pragma once
+#include "snake_step.cuh"
+
+#ifdef __CUDACC__
+#define SNK_HD __host__ __device__ __forceinline__
+#else
+#define SNK_HD inline
+#endif
+
+#define EB 32 // environments (= threads) per CTA
+
+// Model tables for the exact kernel (fp32; constant memory on the device).
+struct ExTables {
+    float jR0[NJ][9];
+    float jt[NJ][3];
+    float jax[NJ][3];
+    float jdamp[NJ];
+    float mass[NB];
+    float com[NB][3];
+    float Ic[NB][6]; // xx xy xz yy yz zz about the COM, body axes
+    float ccen[NC][3];
+    float cax[NC][3];
+    float cfr[NC][9];
+    float crad[NC], ceh[NC] /* end * halflen */, cmar[NC], cbrk[NC];
+    float hpt[NB][3];
+    float fzax[3];
+    float rootm, mtot, inv_mtot;
+    int cstart[NB + 1]; // cylinders of body b are [cstart[b], cstart[b+1])
+};
+
+// Shared-memory record of one CTA: contact rows as [contact][thread] columns.
+struct ExSmem {
+    float4 A[NC][EB];  // rx, ry (lever arm about C), rhs_n, invD_n
+    float4 B[NC][EB];  // rz, d1x, d1y, d1z
+    float4 C[NC][EB];  // d2x, d2y, d2z, rhs_1
+    float2 E[NC][EB];  // invD_1, invD_2
+    float R2[NC][EB];  // rhs_2
+    float Ln[NC][EB];  // normal impulse
+    float2 Lf[NC][EB]; // friction impulses
+    float tgt[NJ][EB]; // joint targets of this env-step
+};
+
+// ---- small float3 helpers -------------------------------------------------------------------
+struct V3 { float x, y, z; };
+SNK_HD V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+SNK_HD V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+SNK_HD V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+SNK_HD V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+SNK_HD V3 cross(V3 a, V3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+SNK_HD float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+SNK_HD V3 ld3(const float* p) { return mk(p[0], p[1], p[2]); }
+struct M3 { float m[9]; }; // row-major
+SNK_HD V3 mul(const M3& R, V3 v) {
+    return mk(R.m[0] * v.x + R.m[1] * v.y + R.m[2] * v.z, R.m[3] * v.x + R.m[4] * v.y + R.m[5] * v.z, R.m[6] * v.x + R.m[7] * v.y + R.m[8] * v.z);
+}
+SNK_HD V3 mulT(const M3& R, V3 v) {
+    return mk(R.m[0] * v.x + R.m[3] * v.y + R.m[6] * v.z, R.m[1] * v.x + R.m[4] * v.y + R.m[7] * v.z, R.m[2] * v.x + R.m[5] * v.y + R.m[8] * v.z);
+}
+SNK_HD M3 mul(const M3& A, const M3& B) {
+    M3 o;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) o.m[3 * i + j] = A.m[3 * i] * B.m[j] + A.m[3 * i + 1] * B.m[3 + j] + A.m[3 * i + 2] * B.m[6 + j];
+    return o;
+}
+SNK_HD M3 mulBT(const M3& A, const M3& B) { // A B^T
+    M3 o;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) o.m[3 * i + j] = A.m[3 * i] * B.m[3 * j] + A.m[3 * i + 1] * B.m[3 * j + 1] + A.m[3 * i + 2] * B.m[3 * j + 2];
+    return o;
+}
+struct S3 { float xx, xy, xz, yy, yz, zz; }; // symmetric 3x3
+SNK_HD V3 mul(const S3& S, V3 v) {
+    return mk(S.xx * v.x + S.xy * v.y + S.xz * v.z, S.xy * v.x + S.yy * v.y + S.yz * v.z, S.xz * v.x + S.yz * v.y + S.zz * v.z);
+}
+SNK_HD float ex_rcp(float x) {
+#ifdef __CUDA_ARCH__
+    return __frcp_rn(x);
+#else
+    return 1.0f / x;
+#endif
+}
+SNK_HD float ex_rsqrt(float x) { return 1.0f / sqrtf(x); }
+SNK_HD void ex_sincos(float a, float* s, float* c) {
+#ifdef __CUDA_ARCH__
+    sincosf(a, s, c);
+#else
+    *s = sinf(a); *c = cosf(a);
+#endif
+}
+SNK_HD M3 quat_to_m3(const float* q) { // xyzw
+    float x = q[0], y = q[1], z = q[2], w = q[3];
+    M3 R;
+    R.m[0] = 1 - 2 * (y * y + z * z); R.m[1] = 2 * (x * y - z * w);     R.m[2] = 2 * (x * z + y * w);
+    R.m[3] = 2 * (x * y + z * w);     R.m[4] = 1 - 2 * (x * x + z * z); R.m[5] = 2 * (y * z - x * w);
+    R.m[6] = 2 * (x * z - y * w);     R.m[7] = 2 * (y * z + x * w);     R.m[8] = 1 - 2 * (x * x + y * y);
+    return R;
+}
+// child->parent rotation of joint j at angle q: jR0 * Rot(jax, q)
+SNK_HD M3 joint_rot(const ExTables& T, int j, float q) {
+    float s, c;
+    ex_sincos(q, &s, &c);
+    const float ax = T.jax[j][0], ay = T.jax[j][1], az = T.jax[j][2], C = 1.f - c;
+    M3 Rq, R0;
+    Rq.m[0] = c + ax * ax * C;      Rq.m[1] = ax * ay * C - az * s; Rq.m[2] = ax * az * C + ay * s;
+    Rq.m[3] = ay * ax * C + az * s; Rq.m[4] = c + ay * ay * C;      Rq.m[5] = ay * az * C - ax * s;
+    Rq.m[6] = az * ax * C - ay * s; Rq.m[7] = az * ay * C + ax * s; Rq.m[8] = c + az * az * C;
+#pragma unroll
+    for (int k = 0; k < 9; k++) R0.m[k] = T.jR0[j][k];
+    return mul(R0, Rq);
+}
+// world inertia R Ic R^T of body b
+SNK_HD S3 world_inertia(const ExTables& T, int b, const M3& R) {
+    const float* I = T.Ic[b];
+    M3 t; // R * Ic
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float r0 = R.m[3 * i], r1 = R.m[3 * i + 1], r2 = R.m[3 * i + 2];
+        t.m[3 * i] = r0 * I[0] + r1 * I[1] + r2 * I[2];
+        t.m[3 * i + 1] = r0 * I[1] + r1 * I[3] + r2 * I[4];
+        t.m[3 * i + 2] = r0 * I[2] + r1 * I[4] + r2 * I[5];
+    }
+    S3 S;
+    S.xx = t.m[0] * R.m[0] + t.m[1] * R.m[1] + t.m[2] * R.m[2];
+    S.xy = t.m[0] * R.m[3] + t.m[1] * R.m[4] + t.m[2] * R.m[5];
+    S.xz = t.m[0] * R.m[6] + t.m[1] * R.m[7] + t.m[2] * R.m[8];
+    S.yy = t.m[3] * R.m[3] + t.m[4] * R.m[4] + t.m[5] * R.m[5];
+    S.yz = t.m[3] * R.m[6] + t.m[4] * R.m[7] + t.m[5] * R.m[8];
+    S.zz = t.m[6] * R.m[6] + t.m[7] * R.m[7] + t.m[8] * R.m[8];
+    return S;
+}
+
+// Per-thread view of the environment: registers (base state) + where its columns live.
+struct ExEnv {
+    float pos[3], quat[4], vel[3], omg[3]; // base state (SNK_S_POS..SNK_S_OMEGA), registers
+    float* st;                             // &state[0 * npad + env]; slot k at st[k * npad]
+    int64_t npad;
+    int tid;                               // column in the CTA's shared arrays
+};
+SNK_HD float& slot(const ExEnv& e, int k) { return e.st[(int64_t)k * e.npad]; }
+
+// Newton-Euler wrench of body b (force F, moment N about the COM) for COM acceleration ac, angular
+// velocity w / acceleration al; gravity and Bullet's velocity damping (per merged body, D2) are the
+// external forces.  vc = COM velocity.
+SNK_HD void body_wrench(const ExTables& T, const KParams& P, int b, const S3& Iw, V3 w, V3 al, V3 vc, V3 ac, V3* F, V3* N) {
+    const float m = T.mass[b];
+    const float nv = sqrtf(dot(vc, vc)), nw = sqrtf(dot(w, w));
+    const float kl = P.kl + P.kl * nv, ka = P.ka + P.ka * nw;
+    V3 Iww = mul(Iw, w);
+    *F = mk(m * (ac.x - P.g[0] + vc.x * kl), m * (ac.y - P.g[1] + vc.y * kl), m * (ac.z - P.g[2] + vc.z * kl));
+    V3 t = cross(w, Iww), Ial = mul(Iw, al);
+    *N = mk(Ial.x + t.x + Iww.x * ka, Ial.y + t.y + Iww.y * ka, Ial.z + t.z + Iww.z * ka);
+}
+
+// chain cursor: frame of the current body (position relative to the base origin) and its motion
+struct ExCursor {
+    M3 R;
+    V3 p, w, v, al, acc; // al/acc: reference accelerations (zero base acceleration)
+};
+
+struct ExTickOut { int iterations; int contacts; float height; float err2_next; };
+
+// -----------------------------------------------------------------------------------------------
+// One physics tick.  Returns the mean checkSnakeHeight z of the state at the START of the tick in
+// out->height; when `probe_only` is set (or when that height already exceeds the threshold and
+// `abort_on_height`), nothing is modified and *aborted = true.
+// -----------------------------------------------------------------------------------------------
+SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bool abort_on_height, bool* aborted, ExTickOut* out) {
+    const int tid = e.tid;
+    const float dt = P.dt, inv_dt = P.inv_dt;
+    const float p0z = e.pos[2];
+    // ------------------------------------------------------------------ pass 1: tip-ward
+    ExCursor c;
+    c.R = quat_to_m3(e.quat);
+    c.p = mk(0.f, 0.f, 0.f);
+    c.w = ld3(e.omg); c.v = ld3(e.vel);
+    c.al = mk(0.f, 0.f, 0.f); c.acc = mk(0.f, 0.f, 0.f);
+    V3 wJ = mk(0.f, 0.f, 0.f), vJ = mk(0.f, 0.f, 0.f); // motion due to the NEW joint rates alone
+    V3 h = mk(0.f, 0.f, 0.f), F0 = h, N0 = h;
+    S3 J; J.xx = J.xy = J.xz = J.yy = J.yz = J.zz = 0.f;
+    float hsum = 0.f, err2n = 0.f;
+    unsigned act = 0u;
+    float qn = slot(e, SNK_S_Q), qdn = slot(e, SNK_S_QD); // prefetched joint 0
+#pragma unroll 1
+    for (int i = 0; i < NB; i++) {
+        if (i > 0) {
+            const int j = i - 1;
+            const float q = qn, qd = qdn, tg = S.tgt[j][tid];
+            if (i < NJ) { qn = slot(e, SNK_S_Q + i); qdn = slot(e, SNK_S_QD + i); }
+            float qds = P.kp * (tg - q) * inv_dt;
+            qds = fminf(fmaxf(qds, -P.maxvel), P.maxvel);
+            const float qdd = (qds - qd) * inv_dt;
+            const float en = tg - (q + dt * qds);
+            err2n += en * en;
+            V3 d = mul(c.R, ld3(T.jt[j]));
+            V3 wxd = cross(c.w, d);
+            c.acc = c.acc + cross(c.al, d) + cross(c.w, wxd);
+            c.v = c.v + wxd;
+            vJ = vJ + cross(wJ, d);
+            c.p = c.p + d;
+            c.R = mul(c.R, joint_rot(T, j, q));
+            V3 a = mul(c.R, ld3(T.jax[j]));
+            V3 wq = a * qd;
+            c.al = c.al + a * qdd + cross(c.w, wq);
+            c.w = c.w + wq;
+            wJ = wJ + a * qds;
+        }
+        // ---- body i
+        {
+            const float m = T.mass[i];
+            V3 rc = mul(c.R, ld3(T.com[i]));
+            V3 cc = c.p + rc;
+            S3 Iw = world_inertia(T, i, c.R);
+            V3 wxr = cross(c.w, rc);
+            V3 vc = c.v + wxr;
+            V3 ac = c.acc + cross(c.al, rc) + cross(c.w, wxr);
+            V3 F, N;
+            body_wrench(T, P, i, Iw, c.w, c.al, vc, ac, &F, &N);
+            F0 = F0 + F;
+            N0 = N0 + cross(cc, F) + N;
+            h = h + cc * m;
+            const float c2 = dot(cc, cc);
+            J.xx += Iw.xx + m * (c2 - cc.x * cc.x); J.yy += Iw.yy + m * (c2 - cc.y * cc.y); J.zz += Iw.zz + m * (c2 - cc.z * cc.z);
+            J.xy += Iw.xy - m * cc.x * cc.y; J.xz += Iw.xz - m * cc.x * cc.z; J.yz += Iw.yz - m * cc.y * cc.z;
+            hsum += p0z + c.p.z + c.R.m[6] * T.hpt[i][0] + c.R.m[7] * T.hpt[i][1] + c.R.m[8] * T.hpt[i][2];
+        }
+        // ---- contacts of body i (A.5 with deviation D1: lowest point of the extreme rim)
+#pragma unroll 1
+        for (int k = T.cstart[i]; k < T.cstart[i + 1]; k++) {
+            V3 axw = mul(c.R, ld3(T.cax[k]));
+            V3 ce = c.p + mul(c.R, ld3(T.ccen[k])) + axw * T.ceh[k];
+            const float az = axw.z;
+            const float inv = ex_rsqrt(fmaxf(1.f - az * az, 1e-12f));
+            V3 pc = ce + mk(az * axw.x * inv, az * axw.y * inv, (az * az - 1.f) * inv) * T.crad[k];
+            const float dist = pc.z + p0z - T.cmar[k];
+            if (!(dist < T.cbrk[k])) continue;
+            act |= 1u << k;
+            pc.z = dist - p0z; // contact point at height `dist` (world), relative to the base origin
+            M3 cf, Rl;
+#pragma unroll
+            for (int q9 = 0; q9 < 9; q9++) cf.m[q9] = T.cfr[k][q9];
+            Rl = mul(c.R, cf);
+            // anisotropic friction directions: Rl diag(aniso) Rl^T t, t1 = (0,-1,0), t2 = (1,0,0)
+            V3 l1 = mk(-Rl.m[3] * P.aniso[0], -Rl.m[4] * P.aniso[1], -Rl.m[5] * P.aniso[2]);
+            V3 l2 = mk(Rl.m[0] * P.aniso[0], Rl.m[1] * P.aniso[1], Rl.m[2] * P.aniso[2]);
+            V3 d1 = mul(Rl, l1), d2 = mul(Rl, l2);
+            V3 uJ = vJ + cross(wJ, pc - c.p);
+            S.A[k][tid] = make_float4(pc.x, pc.y, uJ.x, 0.f);
+            S.B[k][tid] = make_float4(pc.z, d1.x, d1.y, d1.z);
+            S.C[k][tid] = make_float4(d2.x, d2.y, d2.z, uJ.y);
+            S.R2[k][tid] = uJ.z;
+        }
+    }
+    out->height = hsum * (1.f / NB);
+    out->err2_next = err2n;
+    if (abort_on_height && out->height > P.hthr) { *aborted = true; out->iterations = 0; out->contacts = 0; return; }
+    *aborted = false;
+
+    // ------------------------------------------------------------------ free rigid motion about C
+    const float invM = T.inv_mtot, M = T.mtot;
+    const V3 hc = h * invM; // C - p0
+    {
+        const float h2 = dot(hc, hc);
+        J.xx -= M * (h2 - hc.x * hc.x); J.yy -= M * (h2 - hc.y * hc.y); J.zz -= M * (h2 - hc.z * hc.z);
+        J.xy += M * hc.x * hc.y; J.xz += M * hc.x * hc.z; J.yz += M * hc.y * hc.z;
+    }
+    S3 Ji; // J^-1 (adjugate)
+    {
+        const float c00 = J.yy * J.zz - J.yz * J.yz, c01 = J.xz * J.yz - J.xy * J.zz, c02 = J.xy * J.yz - J.xz * J.yy;
+        const float det = J.xx * c00 + J.xy * c01 + J.xz * c02;
+        const float id = 1.f / det;
+        Ji.xx = c00 * id; Ji.xy = c01 * id; Ji.xz = c02 * id;
+        Ji.yy = (J.xx * J.zz - J.xz * J.xz) * id; Ji.yz = (J.xy * J.xz - J.xx * J.yz) * id; Ji.zz = (J.xx * J.yy - J.xy * J.xy) * id;
+    }
+    const V3 NC0 = N0 - cross(hc, F0);
+    const V3 alf = mul(Ji, NC0) * -1.f; // free angular acceleration
+    const V3 aC = F0 * -invM;           // free acceleration of the point C
+    const V3 w0 = ld3(e.omg), v0 = ld3(e.vel);
+    V3 wf = w0 + alf * dt;                           // free angular velocity
+    const V3 VC = v0 + cross(w0, hc) + aC * dt;      // free velocity of C (rigid field of the base)
+    // (the base origin moves with this rigid field: v0' = VC - wf x hc, i.e. a0 = aC - alf x hc)
+
+    // ------------------------------------------------------------------ rows
+    int ncontacts = 0;
+#pragma unroll 1
+    for (int k = 0; k < NC; k++) {
+        if (!((act >> k) & 1u)) continue;
+        ncontacts++;
+        float4 a = S.A[k][tid], b = S.B[k][tid], cc = S.C[k][tid];
+        const float uJz = S.R2[k][tid];
+        const V3 uJ = mk(a.z, cc.w, uJz);
+        const float dist = b.x + p0z;
+        const V3 r = mk(a.x - hc.x, a.y - hc.y, b.x - hc.z);
+        const V3 d1 = mk(b.y, b.z, b.w), d2 = mk(cc.x, cc.y, cc.z);
+        // velocity of the contact point under the free rigid motion plus the new joint rates.  The rigid
+        // field is (wf, velocity VC0 at C) with VC0 chosen so that the base origin gets v0 + dt a0:
+        const V3 vp = VC + cross(wf, r) + uJ;
+        // normal row
+        const V3 rn = mk(r.y, -r.x, 0.f);
+        const float Dn = invM + dot(rn, mul(Ji, rn));
+        const float iDn = 1.f / Dn;
+        const float pen = dist + P.slop;
+        float verr = -vp.z, perr = 0.f;
+        if (pen > 0.f) verr -= pen * inv_dt; else perr = -pen * P.erp2 * inv_dt;
+        const float rhsn = (verr + perr) * iDn;
+        // friction rows
+        const V3 r1 = cross(r, d1), r2 = cross(r, d2);
+        const float D1 = dot(d1, d1) * invM + dot(r1, mul(Ji, r1)), D2 = dot(d2, d2) * invM + dot(r2, mul(Ji, r2));
+        const float iD1 = 1.f / D1, iD2 = 1.f / D2;
+        S.A[k][tid] = make_float4(r.x, r.y, rhsn, iDn);
+        S.B[k][tid] = make_float4(r.z, d1.x, d1.y, d1.z);
+        S.C[k][tid] = make_float4(d2.x, d2.y, d2.z, -dot(d1, vp) * iD1);
+        S.E[k][tid] = make_float2(iD1, iD2);
+        S.R2[k][tid] = -dot(d2, vp) * iD2;
+        S.Ln[k][tid] = 0.f;
+        S.Lf[k][tid] = make_float2(0.f, 0.f);
+    }
+
+    // ------------------------------------------------------------------ projected Gauss-Seidel
+    V3 dw = mk(0.f, 0.f, 0.f), dV = mk(0.f, 0.f, 0.f);
+    int it = 0;
+#pragma unroll 1
+    for (;; it++) {
+        float res = 0.f;
+#pragma unroll 1
+        for (int k = 0; k < NC; k++) {
+            if (!((act >> k) & 1u)) continue;
+            const float4 a = S.A[k][tid];
+            const float ln = S.Ln[k][tid];
+            const float jd = dV.z + dw.x * a.y - dw.y * a.x;
+            float d = a.z - jd * a.w;
+            float sum = ln + d;
+            if (sum < 0.f) { d = -ln; sum = 0.f; }
+            S.Ln[k][tid] = sum;
+            const V3 rn = mk(a.y * d, -a.x * d, 0.f);
+            dw = dw + mul(Ji, rn);
+            dV.z += d * invM;
+            const float rr = d * ex_rcp(a.w);
+            res = fmaxf(res, rr * rr);
+        }
+#pragma unroll 1
+        for (int k = 0; k < NC; k++) {
+            if (!((act >> k) & 1u)) continue;
+            const float4 a = S.A[k][tid], b = S.B[k][tid], cc = S.C[k][tid];
+            const float2 ee = S.E[k][tid], lf = S.Lf[k][tid];
+            const float rhs2 = S.R2[k][tid], lim = P.mu * S.Ln[k][tid];
+            const V3 r = mk(a.x, a.y, b.x), d1 = mk(b.y, b.z, b.w), d2 = mk(cc.x, cc.y, cc.z);
+            const V3 u = dV + cross(dw, r);
+            float sa = lf.x + (cc.w - dot(d1, u) * ee.x), sb = lf.y + (rhs2 - dot(d2, u) * ee.y);
+            if (P.cone) {
+                const float n2 = sa * sa + sb * sb;
+                if (n2 > lim * lim) { const float sc = lim * ex_rsqrt(n2); sa *= sc; sb *= sc; }
+            } else {
+                sa = fminf(fmaxf(sa, -lim), lim);
+                sb = fminf(fmaxf(sb, -lim), lim);
+            }
+            const float da = sa - lf.x, db = sb - lf.y;
+            S.Lf[k][tid] = make_float2(sa, sb);
+            const V3 f = d1 * da + d2 * db;
+            dV = dV + f * invM;
+            dw = dw + mul(Ji, cross(r, f));
+            const float rr = da * ex_rcp(ee.x) + db * ex_rcp(ee.y);
+            res = fmaxf(res, rr * rr);
+        }
+        if (res <= P.resthr || it >= P.iters - 1) break;
+    }
+    out->iterations = it + 1;
+    out->contacts = ncontacts;
+
+    // ------------------------------------------------------------------ new base velocity
+    // rigid field after the solve: angular wf + dw, velocity VC + dV at C; base origin = field at -hc
+    const V3 wN_u = wf + dw;
+    const V3 vN_u = (VC + dV) - cross(wN_u, hc);
+    // true base accelerations (before clamping, like the oracle): angular, and classical at the origin
+    const V3 al0 = (wN_u - w0) * inv_dt;
+    const V3 a0 = (vN_u - v0) * inv_dt;
+    // clamp in body-0 axes (maxCoordinateVelocity)
+    const M3 R0 = quat_to_m3(e.quat);
+    V3 wb = mulT(R0, wN_u), vb = mulT(R0, vN_u);
+    wb = mk(fminf(fmaxf(wb.x, -P.maxvel), P.maxvel), fminf(fmaxf(wb.y, -P.maxvel), P.maxvel), fminf(fmaxf(wb.z, -P.maxvel), P.maxvel));
+    vb = mk(fminf(fmaxf(vb.x, -P.maxvel), P.maxvel), fminf(fmaxf(vb.y, -P.maxvel), P.maxvel), fminf(fmaxf(vb.z, -P.maxvel), P.maxvel));
+    const V3 wN = mul(R0, wb), vN = mul(R0, vb);
+
+    // ------------------------------------------------------------------ pass 2: base-ward, torques
+    {
+        V3 SF = mk(0.f, 0.f, 0.f), SN = SF; // suffix wrench about the base origin
+#pragma unroll 1
+        for (int i = NB - 1; i >= 1; i--) {
+            const int j = i - 1;
+            const float q = slot(e, SNK_S_Q + j), qd = slot(e, SNK_S_QD + j), tg = S.tgt[j][tid];
+            float qds = P.kp * (tg - q) * inv_dt;
+            qds = fminf(fmaxf(qds, -P.maxvel), P.maxvel);
+            const float qdd = (qds - qd) * inv_dt;
+            // wrench of body i with the true accelerations
+            V3 rc = mul(c.R, ld3(T.com[i]));
+            V3 cc = c.p + rc;
+            S3 Iw = world_inertia(T, i, c.R);
+            V3 wxr = cross(c.w, rc);
+            V3 vc = c.v + wxr;
+            V3 ac = c.acc + cross(c.al, rc) + cross(c.w, wxr) + a0 + cross(al0, cc);
+            V3 F, N;
+            body_wrench(T, P, i, Iw, c.w, c.al + al0, vc, ac, &F, &N);
+            SF = SF + F;
+            SN = SN + cross(cc, F) + N;
+#pragma unroll 1
+            for (int k = T.cstart[i]; k < T.cstart[i + 1]; k++) {
+                if (!((act >> k) & 1u)) continue;
+                const float4 a = S.A[k][tid], b = S.B[k][tid], c4 = S.C[k][tid];
+                const float2 lf = S.Lf[k][tid];
+                const float ln = S.Ln[k][tid];
+                V3 f = mk(b.y * lf.x + c4.x * lf.y, b.z * lf.x + c4.y * lf.y, ln + b.w * lf.x + c4.z * lf.y) * inv_dt;
+                V3 r = mk(a.x + hc.x, a.y + hc.y, b.x + hc.z); // back to the base origin
+                SF = SF - f;
+                SN = SN - cross(r, f);
+            }
+            V3 a = mul(c.R, ld3(T.jax[j]));
+            const float tau = dot(a, SN - cross(c.p, SF)) + T.jdamp[j] * qd;
+            slot(e, SNK_S_TAU + j) = tau;
+            slot(e, SNK_S_QD + j) = qds;
+            slot(e, SNK_S_Q + j) = q + qds * dt;
+            // step to the parent frame
+            V3 wq = a * qd;
+            c.w = c.w - wq;
+            c.al = c.al - a * qdd - cross(c.w, wq);
+            c.R = mulBT(c.R, joint_rot(T, j, q));
+            V3 d = mul(c.R, ld3(T.jt[j]));
+            V3 wxd = cross(c.w, d);
+            c.p = c.p - d;
+            c.v = c.v - wxd;
+            c.acc = c.acc - cross(c.al, d) - cross(c.w, wxd);
+        }
+    }
+
+    // ------------------------------------------------------------------ finish: Fz, base integration
+    {   // reaction force of joint 0 (kdl_dummy_root -> base), z of link `base` (snake.py:202-206)
+        const float nv = sqrtf(dot(v0, v0));
+        const float rm = T.rootm, kl = P.kl + P.kl * nv;
+        V3 f = mk(rm * P.g[0] - rm * v0.x * kl - rm * (vN.x - v0.x) * inv_dt, rm * P.g[1] - rm * v0.y * kl - rm * (vN.y - v0.y) * inv_dt,
+                  rm * P.g[2] - rm * v0.z * kl - rm * (vN.z - v0.z) * inv_dt);
+        slot(e, SNK_S_FZ) = dot(mul(R0, ld3(T.fzax)), f);
+    }
+    e.vel[0] = vN.x; e.vel[1] = vN.y; e.vel[2] = vN.z;
+    e.omg[0] = wN.x; e.omg[1] = wN.y; e.omg[2] = wN.z;
+    e.pos[0] += vN.x * dt; e.pos[1] += vN.y * dt; e.pos[2] += vN.z * dt;
+    {   // quaternion exponential map, q <- exp(w dt / 2) * q, normalised
+        const float ang = sqrtf(dot(wN, wN));
+        float sc, sn, cw;
+        ex_sincos(0.5f * ang * dt, &sn, &cw);
+        if (ang < 0.001f) sc = 0.5f * dt - dt * dt * dt * 0.020833333333f * ang * ang;
+        else sc = sn / ang;
+        const float ax = wN.x * sc, ay = wN.y * sc, az = wN.z * sc;
+        const float* q = e.quat;
+        float x = cw * q[0] + ax * q[3] + ay * q[2] - az * q[1];
+        float y = cw * q[1] + ay * q[3] + az * q[0] - ax * q[2];
+        float z = cw * q[2] + az * q[3] + ax * q[1] - ay * q[0];
+        float w = cw * q[3] - ax * q[0] - ay * q[1] - az * q[2];
+        const float in = ex_rsqrt(x * x + y * y + z * z + w * w);
+        e.quat[0] = x * in; e.quat[1] = y * in; e.quat[2] = z * in; e.quat[3] = w * in;
+    }
+}
+
+// mean z of the checkSnakeHeight points (snake.py:237-245) of the current state: a z-only walk
+// (third row of every frame), used where no tick follows.
+SNK_HD float ex_height(const ExTables& T, const ExEnv& e) {
+    const M3 R0 = quat_to_m3(e.quat);
+    V3 r3 = mk(R0.m[6], R0.m[7], R0.m[8]); // third row of the current frame
+    float z = e.pos[2];
+    float hsum = z + r3.x * T.hpt[0][0] + r3.y * T.hpt[0][1] + r3.z * T.hpt[0][2];
+#pragma unroll 1
+    for (int i = 1; i < NB; i++) {
+        const int j = i - 1;
+        z += r3.x * T.jt[j][0] + r3.y * T.jt[j][1] + r3.z * T.jt[j][2];
+        const M3 Mj = joint_rot(T, j, slot(e, SNK_S_Q + j));
+        r3 = mulT(Mj, r3);
+        hsum += z + r3.x * T.hpt[i][0] + r3.y * T.hpt[i][1] + r3.z * T.hpt[i][2];
+    }
+    return hsum * (1.f / NB);
+}
+
+// -----------------------------------------------------------------------------------------------
+// task logic around the tick: one SubprocVecEnv.step of one environment (oracle: env_step).
+// S.tgt[.][tid] must hold the 16 joint targets (checkBound + createAction + scaling already applied).
+// On return the state slots and e.pos.. hold the post-step (post-reset when done) state.
+// -----------------------------------------------------------------------------------------------
+struct ExStepOut { float rew; int done, ticks, iters, bad; };
+
+SNK_HD float ex_obs_of(const ExEnv& e, int k) { // snake.py:209-217
+    if (k < 16) return slot(e, SNK_S_Q + k);
+    if (k < 32) return slot(e, SNK_S_QD + k - 16);
+    if (k < 48) return slot(e, SNK_S_TAU + k - 32);
+    if (k < 51) return e.pos[k - 48];
+    if (k < 55) return e.quat[k - 51];
+    return slot(e, SNK_S_FZ);
+}
+SNK_HD bool ex_finite(float x) { return fabsf(x) <= 3.402823466e38f; } // false for inf and nan
+
+SNK_HD void ex_load_base(ExEnv& e) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { e.pos[k] = slot(e, SNK_S_POS + k); e.vel[k] = slot(e, SNK_S_VEL + k); e.omg[k] = slot(e, SNK_S_OMEGA + k); }
+#pragma unroll
+    for (int k = 0; k < 4; k++) e.quat[k] = slot(e, SNK_S_QUAT + k);
+}
+SNK_HD void ex_store_base(const ExEnv& e) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { slot(e, SNK_S_POS + k) = e.pos[k]; slot(e, SNK_S_VEL + k) = e.vel[k]; slot(e, SNK_S_OMEGA + k) = e.omg[k]; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) slot(e, SNK_S_QUAT + k) = e.quat[k];
+}
+
+SNK_HD void ex_env_step(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, ExStepOut* o) {
+    const int tid = e.tid;
+    const float xprev = e.pos[0]; // self._observation[48], vec-wrapper semantics (Q8)
+    float e2 = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < NJ; j++) { const float d = S.tgt[j][tid] - slot(e, SNK_S_Q + j); e2 += d * d; }
+    int counter = 0, iters = 0;
+    bool end_height = false, have_height = false;
+    float height = 0.f;
+    while (sqrtf(e2) > P.errthr) { // snake.py:284-304
+        bool aborted;
+        ExTickOut to;
+        ex_tick(T, P, S, e, counter > 0, &aborted, &to);
+        if (aborted) { end_height = true; height = to.height; have_height = true; break; } // the previous tick lifted the snake
+        iters += to.iterations;
+        counter++;
+        e2 = to.err2_next;
+        if (counter >= P.maxticks) break; // `counter > 40`
+    }
+    if (!have_height) height = ex_height(T, e);
+    // non-finite guard, energy (snake.py:336-341)
+    bool bad = false;
+    float energy = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) bad |= !ex_finite(e.pos[k]) || !ex_finite(e.vel[k]) || !ex_finite(e.omg[k]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) bad |= !ex_finite(e.quat[k]);
+#pragma unroll 1
+    for (int j = 0; j < NJ; j++) {
+        const float q = slot(e, SNK_S_Q + j), qd = slot(e, SNK_S_QD + j), tau = slot(e, SNK_S_TAU + j);
+        bad |= !ex_finite(q) || !ex_finite(qd) || !ex_finite(tau);
+        energy += qd * tau * P.edt;
+    }
+    const float fz = slot(e, SNK_S_FZ);
+    float ret = slot(e, SNK_S_RET), len = slot(e, SNK_S_LEN);
+    bad |= !ex_finite(fz) || !ex_finite(ret) || !ex_finite(len);
+    // calculateReward (SnakeGymEnv.py:90-97), checkTermination (SnakeGymEnv.py:99-103)
+    float r = P.alpha * (e.pos[0] - xprev) + ((fabsf(fz) > P.colf) ? P.colpen : 0.f) - P.beta * fabsf(e.pos[1] - 0.f) - P.gamma * energy;
+    bool d = (fabsf(ex_obs_of(e, P.tjoint)) > P.tang) || (height > P.hthr) || end_height;
+    if (bad) {
+        d = true; r = P.donepen;
+#pragma unroll 1
+        for (int k = 0; k < SNK_STATE_STRIDE; k++) slot(e, k) = 0.f;
+        ret = 0.f; len = 0.f;
+    } else if (d) r += P.donepen;
+    ret += r; len += 1.f;
+    if (d) { // in-step reset + worker reset: the returned obs is the post-reset one (multiprocessing_env.py:14-15)
+#pragma unroll
+        for (int k = 0; k < 3; k++) { e.pos[k] = 0.f; e.vel[k] = 0.f; e.omg[k] = 0.f; e.quat[k] = 0.f; }
+        e.quat[3] = 1.f;
+#pragma unroll 1
+        for (int j = 0; j < NJ; j++) { slot(e, SNK_S_Q + j) = 0.f; slot(e, SNK_S_QD + j) = 0.f; if (!P.stale) slot(e, SNK_S_TAU + j) = 0.f; }
+        if (!P.stale) slot(e, SNK_S_FZ) = 0.f;
+        ret = 0.f; len = 0.f;
+    }
+    slot(e, SNK_S_RET) = ret; slot(e, SNK_S_LEN) = len;
+    ex_store_base(e);
+    o->rew = r; o->done = d ? 1 : 0; o->ticks = counter; o->iters = iters; o->bad = bad ? 1 : 0;
+}

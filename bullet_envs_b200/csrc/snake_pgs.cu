@@ -20,15 +20,10 @@
 // Reference call sites replaced: SnakeGymEnv.py:33-50,82-103; snake.py:209-306,336-341;
 // ppo/multiprocessing_env.py:11-16; physics per SURVEY.md Appendix A (see oracle/snake_oracle.c,
 // whose row order, clamping and residual rule this kernel reproduces).
-#include <cuda_runtime.h>
-#include <math.h>
-
-#include "snake_step.cuh"
-
-#define FULL 0xffffffffu
+#include "snake_dev.cuh"
 #define WARPS_PER_CTA 4
 
-struct WarpMem {
+struct WarpMemPgs {
     float s[SNK_STATE_STRIDE];
     float Rw[NB][9];
     float pw[NB][3];
@@ -56,116 +51,11 @@ struct WarpMem {
 };
 
 // ---------------------------------------------------------------------------------------------
-// small helpers (register vectors)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cross3(const float* a, const float* b, float* o) {
-    float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
-    o[0] = x; o[1] = y; o[2] = z;
-}
-__device__ __forceinline__ float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-__device__ __forceinline__ void m3v(const float* M, const float* v, float* o) {
-    float x = M[0] * v[0] + M[1] * v[1] + M[2] * v[2], y = M[3] * v[0] + M[4] * v[1] + M[5] * v[2],
-          z = M[6] * v[0] + M[7] * v[1] + M[8] * v[2];
-    o[0] = x; o[1] = y; o[2] = z;
-}
-__device__ __forceinline__ void m3tv(const float* M, const float* v, float* o) {
-    float x = M[0] * v[0] + M[3] * v[1] + M[6] * v[2], y = M[1] * v[0] + M[4] * v[1] + M[7] * v[2],
-          z = M[2] * v[0] + M[5] * v[1] + M[8] * v[2];
-    o[0] = x; o[1] = y; o[2] = z;
-}
-__device__ __forceinline__ void m3m3(const float* A, const float* B, float* o) {
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) o[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
-}
-__device__ __forceinline__ float warp_sum(float x) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
-    return x;
-}
-// motion vector parent -> child through a joint with child->parent rotation R and offset r
-__device__ __forceinline__ void xmot(const float* R, const float* r, const float* vp, float* vc) {
-    float t[3], u[3];
-    cross3(vp, r, t);
-    u[0] = vp[3] + t[0]; u[1] = vp[4] + t[1]; u[2] = vp[5] + t[2];
-    m3tv(R, vp, vc);
-    m3tv(R, u, vc + 3);
-}
-// force vector child -> parent
-__device__ __forceinline__ void xfrc(const float* R, const float* r, const float* fc, float* fp) {
-    float t[3];
-    m3v(R, fc, fp);
-    m3v(R, fc + 3, fp + 3);
-    cross3(r, fp + 3, t);
-    fp[0] += t[0]; fp[1] += t[1]; fp[2] += t[2];
-}
-
-// ---------------------------------------------------------------------------------------------
-// forward kinematics; returns the checkSnakeHeight mean (snake.py:237-245), identical in all lanes
-// ---------------------------------------------------------------------------------------------
-__device__ float fk(WarpMem& W, const DevTables* __restrict__ T, int lane) {
-    if (lane < NJ) { // joint rotations, lane = joint
-        float a[3] = {__ldg(&T->jax[lane][0]), __ldg(&T->jax[lane][1]), __ldg(&T->jax[lane][2])};
-        float th = W.s[SNK_S_Q + lane], s, c;
-        sincosf(th, &s, &c);
-        float C = 1.f - c, Rq[9], R0[9], R[9];
-        Rq[0] = c + a[0] * a[0] * C;        Rq[1] = a[0] * a[1] * C - a[2] * s; Rq[2] = a[0] * a[2] * C + a[1] * s;
-        Rq[3] = a[1] * a[0] * C + a[2] * s; Rq[4] = c + a[1] * a[1] * C;        Rq[5] = a[1] * a[2] * C - a[0] * s;
-        Rq[6] = a[2] * a[0] * C - a[1] * s; Rq[7] = a[2] * a[1] * C + a[0] * s; Rq[8] = c + a[2] * a[2] * C;
-#pragma unroll
-        for (int k = 0; k < 9; k++) R0[k] = __ldg(&T->jR0[lane][k]);
-        m3m3(R0, Rq, R);
-#pragma unroll
-        for (int k = 0; k < 9; k++) W.Rj[lane + 1][k] = R[k];
-    }
-    __syncwarp();
-    float R[9], p[3], Rm[9], pm[3];
-    {
-        float x = W.s[SNK_S_QUAT], y = W.s[SNK_S_QUAT + 1], z = W.s[SNK_S_QUAT + 2], w = W.s[SNK_S_QUAT + 3];
-        R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w);     R[2] = 2 * (x * z + y * w);
-        R[3] = 2 * (x * y + z * w);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
-        R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
-        p[0] = W.s[SNK_S_POS]; p[1] = W.s[SNK_S_POS + 1]; p[2] = W.s[SNK_S_POS + 2];
-    }
-#pragma unroll
-    for (int k = 0; k < 9; k++) Rm[k] = R[k];
-    pm[0] = p[0]; pm[1] = p[1]; pm[2] = p[2];
-#pragma unroll 1
-    for (int i = 1; i < NB; i++) { // every lane walks the chain; lane i keeps body i
-        float Rn[9], t[3], r[3] = {__ldg(&T->jt[i - 1][0]), __ldg(&T->jt[i - 1][1]), __ldg(&T->jt[i - 1][2])};
-        m3v(R, r, t);
-        m3m3(R, W.Rj[i], Rn);
-        p[0] += t[0]; p[1] += t[1]; p[2] += t[2];
-#pragma unroll
-        for (int k = 0; k < 9; k++) R[k] = Rn[k];
-        if (lane == i) {
-#pragma unroll
-            for (int k = 0; k < 9; k++) Rm[k] = R[k];
-            pm[0] = p[0]; pm[1] = p[1]; pm[2] = p[2];
-        }
-    }
-    if (lane < NB) {
-#pragma unroll
-        for (int k = 0; k < 9; k++) W.Rw[lane][k] = Rm[k];
-        W.pw[lane][0] = pm[0]; W.pw[lane][1] = pm[1]; W.pw[lane][2] = pm[2];
-    }
-    __syncwarp();
-    float z = 0.f;
-#pragma unroll 1
-    for (int h = 0; h < NB; h++) {
-        int b = __ldg(&T->hbody[h]);
-        z += W.pw[b][2] + W.Rw[b][6] * __ldg(&T->hpt[h][0]) + W.Rw[b][7] * __ldg(&T->hpt[h][1]) + W.Rw[b][8] * __ldg(&T->hpt[h][2]);
-    }
-    return z / NB;
-}
-
-// ---------------------------------------------------------------------------------------------
 // response of the generalized velocity to a unit impulse (oracle: impulse_response): spatial impulse
 // f6 on body b (b < 0: none) and/or unit torque impulse at joint jm (0: none).  Runs per lane; every
 // lane walks all 16 joints so the shared-memory reads are warp-uniform broadcasts.
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ void impulse_response(const WarpMem& W, const DevTables* __restrict__ T, int b, const float* f6, int jm,
+__device__ __noinline__ void impulse_response(const WarpMemPgs& W, const DevTables* __restrict__ T, int b, const float* f6, int jm,
                                               float* out /* ND, shared or local */) {
     float u[NB];
     float p[6] = {0, 0, 0, 0, 0, 0};
@@ -260,7 +150,7 @@ __device__ void sym6_inverse(const float* A /* shared */, float* Ainv /* registe
 // ---------------------------------------------------------------------------------------------
 // one physics tick (oracle: forward_dynamics + tick).  Returns the PGS iteration count.
 // ---------------------------------------------------------------------------------------------
-__device__ int tick(WarpMem& W, const DevTables* __restrict__ T, const KParams& P, int lane) {
+__device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParams& P, int lane) {
     const float dt = P.dt;
     // ---- pass 1: velocity chain (every lane, registers), lane b keeps v_b ----
     float vcur[6], vm[6];
@@ -662,165 +552,86 @@ __device__ int tick(WarpMem& W, const DevTables* __restrict__ T, const KParams& 
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernels
+// kernels: the env-step template instantiated for this solver variant
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float obs_of(const WarpMem& W, int k) { // snake.py:209-217
-    if (k < 16) return W.s[SNK_S_Q + k];
-    if (k < 32) return W.s[SNK_S_QD + k - 16];
-    if (k < 48) return W.s[SNK_S_TAU + k - 32];
-    if (k < 51) return W.s[SNK_S_POS + k - 48];
-    if (k < 55) return W.s[SNK_S_QUAT + k - 51];
-    return W.s[SNK_S_FZ];
-}
-
-__device__ __forceinline__ void soft_reset(WarpMem& W, const KParams& P, int lane) { // snake.py:119-127
-    for (int k = lane; k < SNK_STATE_STRIDE; k += 32) {
-        bool keep = (k >= SNK_S_TAU && k <= SNK_S_FZ) && P.stale;
-        if (!keep) W.s[k] = (k == SNK_S_QUAT + 3) ? 1.f : 0.f;
-    }
-}
-
-// RAW = false: one SubprocVecEnv.step.  RAW = true: n_ticks raw ticks with targets[N,16] (gait script).
-template <bool RAW>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2)
-snk_step_kernel(const DevTables* __restrict__ T, const KParams P, float* __restrict__ state, const float* __restrict__ in,
-                float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks,
-                unsigned long long* __restrict__ counters, int64_t n, int n_ticks) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t env = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
-    if (env >= n) return;
-    WarpMem& W = reinterpret_cast<WarpMem*>(smem_raw)[warp];
-    float* gs = state + env * SNK_STATE_STRIDE;
-    W.s[lane] = gs[lane];
-    W.s[lane + 32] = gs[lane + 32];
-    if (lane < NJ) {
-        float tgt;
-        if (RAW) tgt = in[env * NJ + lane];
-        else { // checkBound (SnakeGymEnv.py:82-88) + createAction (snake.py:247-269) + scaling (snake.py:223-225)
-            int k = -1;
-            if (P.gait == 0) { if (!(lane & 1)) k = lane >> 1; }
-            else if (P.gait == 1) { if (lane & 1) k = lane >> 1; }
-            else k = lane;
-            float a = (k >= 0) ? in[env * P.actdim + k] : 0.f;
-            a = fminf(fmaxf(a, -1.f), 1.f);
-            tgt = a * P.sf;
-        }
-        W.target[lane] = tgt;
-    }
-    __syncwarp();
-    const float xprev = W.s[SNK_S_POS];
-    float height = fk(W, T, lane);
-    int counter = 0, iters = 0;
-    bool end_height = false;
-    if (RAW) {
-        for (int t = 0; t < n_ticks; t++) {
-            iters += tick(W, T, P, lane);
-            counter++;
-            height = fk(W, T, lane);
-        }
-    } else {
-        for (;;) { // snake.py:284-304
-            float e2 = 0.f;
-#pragma unroll 1
-            for (int j = 0; j < NJ; j++) { float d = W.target[j] - W.s[SNK_S_Q + j]; e2 += d * d; }
-            if (!(sqrtf(e2) > P.errthr)) break;
-            iters += tick(W, T, P, lane);
-            counter++;
-            height = fk(W, T, lane);
-            if (height > P.hthr) { end_height = true; break; }
-            if (counter >= P.maxticks) break;
-        }
-    }
-    if (RAW) {
-        gs[lane] = W.s[lane];
-        gs[lane + 32] = W.s[lane + 32];
-        if (lane == 0 && counters) { atomicAdd(&counters[0], (unsigned long long)counter); atomicAdd(&counters[1], (unsigned long long)iters); }
-        return;
-    }
-    const bool bad = __any_sync(FULL, !isfinite(W.s[lane]) || !isfinite(W.s[lane + 32]));
-    // reward (SnakeGymEnv.py:90-97, snake.py:336-341) and termination (SnakeGymEnv.py:99-103), every lane
-    float energy = 0.f;
-#pragma unroll 1
-    for (int j = 0; j < NJ; j++) energy += W.s[SNK_S_QD + j] * W.s[SNK_S_TAU + j] * P.edt;
-    float r = P.alpha * (W.s[SNK_S_POS] - xprev) + ((fabsf(W.s[SNK_S_FZ]) > P.colf) ? P.colpen : 0.f) - P.beta * fabsf(W.s[SNK_S_POS + 1] - 0.f) -
-              P.gamma * energy;
-    bool d = (fabsf(obs_of(W, P.tjoint)) > P.tang) || (height > P.hthr) || end_height;
-    if (bad) { d = true; r = P.donepen; }
-    else if (d) r += P.donepen;
-    __syncwarp();
-    if (bad) { W.s[lane] = 0.f; W.s[lane + 32] = 0.f; __syncwarp(); }
-    if (lane == 0) { W.s[SNK_S_RET] += r; W.s[SNK_S_LEN] += 1.f; }
-    __syncwarp();
-    if (d) { soft_reset(W, P, lane); __syncwarp(); } // in-step reset + worker reset: post-reset obs (multiprocessing_env.py:14-15)
-    float* go = obs + env * SNK_OBS_DIM;
-    go[lane] = obs_of(W, lane);
-    if (lane + 32 < SNK_OBS_DIM) go[lane + 32] = obs_of(W, lane + 32);
-    gs[lane] = W.s[lane];
-    gs[lane + 32] = W.s[lane + 32];
-    if (lane == 0) {
-        rew[env] = r;
-        done[env] = d ? 1 : 0;
-        if (ticks) ticks[env] = counter;
-        if (counters) {
-            atomicAdd(&counters[0], (unsigned long long)counter);
-            atomicAdd(&counters[1], (unsigned long long)iters);
-            if (d) atomicAdd(&counters[2], 1ull);
-            if (bad) atomicAdd(&counters[3], 1ull);
-        }
-    }
-}
+#include "snake_task.cuh"
 
 // reset / observe: one thread per (env, state slot).  mode 0 = masked soft reset (+ optional obs of
-// every env), 1 = initialise everything, 2 = observe only.
-__global__ void snk_reset_kernel(const KParams P, float* __restrict__ state, const uint8_t* __restrict__ mask, float* __restrict__ obs,
-                                 int64_t n, int mode) {
+// every env), 1 = initialise everything, 2 = observe only.  npad = 0: state is [env][64] (warp-per-env
+// kernel); npad > 0: state is [64][npad] (thread-per-env kernel), padding columns included in `n`.
+__global__ void snk_reset_kernel(const KParams P, float* __restrict__ state, int64_t npad, const uint8_t* __restrict__ mask,
+                                 float* __restrict__ obs, int64_t n, int mode) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t env = idx >> 6;
-    int k = (int)(idx & 63);
-    if (env >= n) return;
-    float* s = state + env * SNK_STATE_STRIDE;
-    float val = s[k];
-    const bool hit = (mode == 1) || (mode == 0 && (!mask || mask[env]));
+    int64_t env;
+    int k;
+    if (npad) { k = (int)(idx / npad); env = idx - (int64_t)k * npad; if (k >= SNK_STATE_STRIDE) return; }
+    else { env = idx >> 6; k = (int)(idx & 63); if (env >= n) return; }
+    float* s = npad ? state + (int64_t)k * npad + env : state + env * SNK_STATE_STRIDE + k;
+    float val = *s;
+    const bool pad = env >= n; // padding columns of the SoA layout stay in the reset pose
+    const bool hit = (mode == 1) || (mode == 0 && (pad || !mask || mask[env]));
     if (hit) {
         bool keep = (k >= SNK_S_TAU && k <= SNK_S_FZ) && P.stale && mode == 0;
-        if (!keep) { val = (k == SNK_S_QUAT + 3) ? 1.f : 0.f; s[k] = val; }
+        if (!keep) { val = (k == SNK_S_QUAT + 3) ? 1.f : 0.f; *s = val; }
     }
-    if (obs && k < SNK_S_RET) { // state slot -> observation index (snake.py:209-217)
+    if (obs && !pad && k < SNK_S_RET) { // state slot -> observation index (snake.py:209-217)
         int o = (k < SNK_S_QUAT) ? 48 + k : (k < SNK_S_VEL) ? 51 + (k - SNK_S_QUAT) : (k < SNK_S_Q) ? -1 : (k < SNK_S_QD) ? k - SNK_S_Q
                 : (k < SNK_S_TAU) ? 16 + (k - SNK_S_QD) : (k < SNK_S_FZ) ? 32 + (k - SNK_S_TAU) : 55;
         if (o >= 0) obs[env * SNK_OBS_DIM + o] = val;
     }
 }
 
+// state export / import between the caller's [N,64] array and the handle's [64][npad] layout:
+// 32 x 32 tiles through shared memory so both sides move full 128 B lines.
+__global__ void snk_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n, int64_t npad, int to_soa) {
+    __shared__ float tile[32][33];
+    const int64_t env0 = (int64_t)blockIdx.x * 32;
+    const int k0 = blockIdx.y * 32, tx = threadIdx.x, ty = threadIdx.y; // block (32, 8)
+    if (to_soa) {
+        for (int r = ty; r < 32; r += 8) { int64_t env = env0 + r; tile[r][tx] = (env < n) ? src[env * SNK_STATE_STRIDE + k0 + tx] : 0.f; }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) { int64_t env = env0 + tx; if (env < n) dst[(int64_t)(k0 + r) * npad + env] = tile[tx][r]; }
+    } else {
+        for (int r = ty; r < 32; r += 8) { int64_t env = env0 + tx; tile[r][tx] = (env < n) ? src[(int64_t)(k0 + r) * npad + env] : 0.f; }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) { int64_t env = env0 + r; if (env < n) dst[env * SNK_STATE_STRIDE + k0 + tx] = tile[tx][r]; }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // launch wrappers used by the C-ABI host code (snake_abi.cu)
 // ---------------------------------------------------------------------------------------------
-size_t snk_step_smem_bytes() { return sizeof(WarpMem) * WARPS_PER_CTA; }
+size_t snk_pgs_smem_bytes() { return sizeof(WarpMemPgs) * WARPS_PER_CTA; }
 
-cudaError_t snk_configure_kernels() {
-    cudaError_t e = cudaFuncSetAttribute(snk_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)snk_step_smem_bytes());
+cudaError_t snk_pgs_configure() {
+    cudaError_t e = cudaFuncSetAttribute(snk_env_kernel<WarpMemPgs, false, WARPS_PER_CTA, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)snk_pgs_smem_bytes());
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(snk_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)snk_step_smem_bytes());
+    return cudaFuncSetAttribute(snk_env_kernel<WarpMemPgs, true, WARPS_PER_CTA, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)snk_pgs_smem_bytes());
 }
 
-cudaError_t snk_launch_step(const DevTables* T, const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
+cudaError_t snk_pgs_launch_step(const DevTables* T, const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
                             int32_t* ticks, unsigned long long* counters, int64_t n, cudaStream_t st) {
     dim3 grid((unsigned)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA)), block(WARPS_PER_CTA * 32);
-    snk_step_kernel<false><<<grid, block, snk_step_smem_bytes(), st>>>(T, P, state, actions, obs, rew, done, ticks, counters, n, 0);
+    snk_env_kernel<WarpMemPgs, false, WARPS_PER_CTA, 2><<<grid, block, snk_pgs_smem_bytes(), st>>>(T, P, state, actions, obs, rew, done, ticks, counters, n, 0);
     return cudaGetLastError();
 }
 
-cudaError_t snk_launch_tick(const DevTables* T, const KParams& P, float* state, const float* targets, unsigned long long* counters, int64_t n,
+cudaError_t snk_pgs_launch_tick(const DevTables* T, const KParams& P, float* state, const float* targets, unsigned long long* counters, int64_t n,
                             int n_ticks, cudaStream_t st) {
     dim3 grid((unsigned)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA)), block(WARPS_PER_CTA * 32);
-    snk_step_kernel<true><<<grid, block, snk_step_smem_bytes(), st>>>(T, P, state, targets, nullptr, nullptr, nullptr, nullptr, counters, n, n_ticks);
+    snk_env_kernel<WarpMemPgs, true, WARPS_PER_CTA, 2><<<grid, block, snk_pgs_smem_bytes(), st>>>(T, P, state, targets, nullptr, nullptr, nullptr, nullptr, counters, n, n_ticks);
     return cudaGetLastError();
 }
 
-cudaError_t snk_launch_reset(const KParams& P, float* state, const uint8_t* mask, float* obs, int64_t n, int mode, cudaStream_t st) {
-    int64_t total = n * 64;
+cudaError_t snk_launch_reset(const KParams& P, float* state, int64_t npad, const uint8_t* mask, float* obs, int64_t n, int mode, cudaStream_t st) {
+    int64_t total = (npad ? npad : n) * 64;
     dim3 grid((unsigned)((total + 255) / 256)), block(256);
-    snk_reset_kernel<<<grid, block, 0, st>>>(P, state, mask, obs, n, mode);
+    snk_reset_kernel<<<grid, block, 0, st>>>(P, state, npad, mask, obs, n, mode);
+    return cudaGetLastError();
+}
+
+cudaError_t snk_launch_transpose(const float* src, float* dst, int64_t n, int64_t npad, int to_soa, cudaStream_t st) {
+    dim3 grid((unsigned)((n + 31) / 32), 2), block(32, 8);
+    snk_transpose_kernel<<<grid, block, 0, st>>>(src, dst, n, npad, to_soa);
     return cudaGetLastError();
 }

@@ -35,5 +35,5 @@ struct DevTables {
 struct KParams {
     float dt, inv_dt, g[3], kp, kd, maximp, sf, alpha, beta, gamma, edt, mu, aniso[3], kl, ka, erp2, slop, resthr,
         maxvel, errthr, hthr, tang, donepen, colf, colpen;
-    int iters, maxticks, gait, cone, tjoint, stale, altmotor, actdim;
+    int iters, maxticks, gait, cone, tjoint, stale, altmotor, actdim, exact;
 };

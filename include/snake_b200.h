@@ -124,7 +124,9 @@ typedef struct snk_params {
     int32_t term_joint;         /* 9    SnakeGymEnv.py:100                                      */
     int32_t stale_obs_on_reset; /* 1 = torque/Fz slots keep last tick's values after reset (Q9) */
     int32_t alternate_motor_order; /* 1 = Bullet's `iteration & 1 ? j : n-1-j` motor row order  */
-    int32_t reserved0;          /* keeps the struct 8-byte sized; must be 0                     */
+    int32_t motor_solver;       /* 0 = motor rows relaxed inside the PGS in Bullet's order (A.4);
+                                   1 = motor rows imposed exactly (needs force = inf, kd = 1);
+                                   2 = auto: 1 when admissible, else 0     */
 } snk_params;
 
 typedef struct snk_handle snk_handle;

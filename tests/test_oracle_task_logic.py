@@ -16,10 +16,12 @@ def test_golden_meta(golden, model):
     assert np.allclose(hi[:16], np.pi) and np.isinf(hi[16:48]).all() and np.allclose(hi[48:], 1.0)
 
 
+@pytest.mark.parametrize("solver", ["", "pgs/"])
 @pytest.mark.parametrize("name", SCENARIOS)
-def test_oracle_reproduces_reference_python(golden, model, name):
+def test_oracle_reproduces_reference_python(golden, model, name, solver):
+    name = solver + name
     acts = golden[name + "/actions"]
-    o = Oracle(1, default_params(), model)
+    o = Oracle(1, default_params(motor_solver=0 if solver else 2), model)
     obs = o.reset()
     assert np.array_equal(obs[0], golden[name + "/obs"][0])
     for t, a in enumerate(acts):

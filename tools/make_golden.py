@@ -149,8 +149,12 @@ def main():
     ref_snake.time.sleep = lambda s: None
 
     out = {}
-    for name, actions in scenario_actions().items():
-        client = FakeClient()
+    # both motor-row treatments of the oracle's tick: "" = the default (auto -> motor rows eliminated,
+    # the kernel the reference configuration runs on), "pgs/" = Bullet-order rows inside the PGS
+    for prefix, solver in (("", 2), ("pgs/", 0)):
+      for name, actions in scenario_actions().items():
+        name = prefix + name
+        client = FakeClient(default_params(motor_solver=solver))
         robot = ref_snake.Snake(client, "snake/snake.urdf")
         env = ref_env.SnakeGymEnv(robot)
         obs0 = env.reset()                       # worker 'reset' command
