@@ -52,7 +52,8 @@ snk_exact_kernel(const KParams P, float* __restrict__ state, int64_t npad, const
 #pragma unroll 1
             for (int k = 0; k < P.actdim; k++) {
                 float a = in[env * P.actdim + k];
-                a = fminf(fmaxf(a, -1.f), 1.f);
+                a = (a < -1.f) ? -1.f : a; // checkBound's comparisons: a NaN passes through (SnakeGymEnv.py:84-87)
+                a = (a > 1.f) ? 1.f : a;
                 const int j = (P.gait == 0) ? 2 * k : (P.gait == 1) ? 2 * k + 1 : k;
                 S.tgt[j][tid] = a * P.sf;
             }

@@ -48,7 +48,8 @@ snk_env_kernel(const DevTables* __restrict__ T, const KParams P, float* __restri
             else if (P.gait == 1) { if (lane & 1) k = lane >> 1; }
             else k = lane;
             float a = (k >= 0) ? in[env * P.actdim + k] : 0.f;
-            a = fminf(fmaxf(a, -1.f), 1.f);
+            a = (a < -1.f) ? -1.f : a; // checkBound's comparisons: a NaN passes through (SnakeGymEnv.py:84-87)
+            a = (a > 1.f) ? 1.f : a;
             tgt = a * P.sf;
         }
         W.target[lane] = tgt;

@@ -37,7 +37,8 @@ static void set_targets_from_actions(Emu* h, const float* a, int tid) {
     const KParams& P = h->P;
     for (int j = 0; j < NJ; j++) h->S.tgt[j][tid] = 0.f;
     for (int k = 0; k < P.actdim; k++) {
-        float v = fminf(fmaxf(a[k], -1.f), 1.f);
+        float v = a[k];
+        v = (v < -1.f) ? -1.f : v; v = (v > 1.f) ? 1.f : v;
         int j = (P.gait == 0) ? 2 * k : (P.gait == 1) ? 2 * k + 1 : k;
         h->S.tgt[j][tid] = v * P.sf;
     }

@@ -1,0 +1,220 @@
+"""CUDA path vs the CPU oracle, through the C ABI (ctypes -> libsnake_b200.so).  Needs a B200.
+
+Tolerances (fp32 kernel vs fp64 oracle):
+  * joint angles / rates follow the motor law and must agree to fp32 round-off (north_star: 1e-4
+    relative after one step) in EVERY environment;
+  * the base twist is the solution of a projected Gauss-Seidel over ~32 redundant contacts: the
+    typical environment agrees to round-off, the tail (a different sweep count at the residual
+    threshold, a contact flipping at the breaking distance) is bounded by percentiles;
+  * integer outputs (tick counts, done flags) are compared exactly, on the fraction stated.
+"""
+import numpy as np
+import pytest
+
+from bullet_envs_b200 import default_params, gait_params
+from oracle.oracle_py import Oracle
+from scenarios import err_table, rollout_states, serpenoid_actions
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (there is no CPU fallback)")
+    return torch
+
+
+def make_env(n, params=None, **kw):
+    from bullet_envs_b200 import SnakeVecEnv
+    return SnakeVecEnv(num_envs=n, device=0, params=params, **kw)
+
+
+def test_library_is_the_cuda_build(torch):
+    from bullet_envs_b200 import _abi
+    lib = _abi.load_library()
+    assert b"sm_100a" in lib.snk_build_info()
+
+
+@pytest.mark.parametrize("solver", [2, 0])
+def test_reset_observation(torch, solver):
+    p = default_params(motor_solver=solver)
+    env = make_env(100, p); o = Oracle(100, p)
+    assert np.array_equal(env.reset(as_torch=True).cpu().numpy().astype(np.float64), o.reset())
+    assert np.array_equal(env.reset(), o.reset())  # numpy path (snk_reset_host)
+    env.close()
+
+
+@pytest.mark.parametrize("solver,n", [(1, 512), (0, 128)])
+def test_one_tick_from_rollout_states(torch, solver, n):
+    p = default_params(motor_solver=solver)
+    o = Oracle(n, p)
+    s, tg = rollout_states(o)
+    env = make_env(n, p)
+    env.set_state(s); o.set_state(s)
+    assert np.array_equal(env.get_state().cpu().numpy(), s.astype(np.float32))  # import/export round trip
+    env.tick(tg, 1); o.tick(tg.astype(np.float64), 1)
+    g = env.get_state().cpu().numpy().astype(np.float64)
+    t = err_table(o.get_state(), g)
+    if solver == 1:  # prescribed joints: round-off
+        assert t["q"][3] <= 1e-6 and t["qd"][3] <= 1e-5 * max(1.0, t["qd"][0]), (t["q"], t["qd"])
+    else:            # motor rows relaxed by 50 sweeps: 1e-4 relative
+        assert t["q"][3] <= 1e-4 * max(1.0, t["q"][0]) and t["qd"][2] <= 1e-3 * max(1.0, t["qd"][0]), (t["q"], t["qd"])
+    for f in ("vel", "omega"):
+        assert t[f][1] < 1e-4 * t[f][0] and t[f][2] < 3e-2 * t[f][0], (f, t[f])
+    assert t["pos"][1] < 1e-6 and t["quat"][1] < 1e-5 and t["pos"][3] < 1e-3
+    assert t["tau"][1] < 1e-3 * t["tau"][0] and t["fz"][1] < 1e-3 * t["fz"][0]
+    c = env.counters()
+    assert c["ticks"] == n
+    env.close()
+
+
+@pytest.mark.parametrize("solver", [2, 0])
+def test_env_steps_vs_oracle(torch, solver):
+    """config 2 of BASELINE.json at an oracle-sized sample: seeded U[-1,1] actions generated on the CPU as
+    float32 and fed identically to both sides."""
+    n, steps = (256, 5) if solver else (64, 3)
+    p = default_params(motor_solver=solver)
+    g = torch.Generator().manual_seed(0)
+    acts = (torch.rand((steps, n, 8), generator=g) * 2 - 1).numpy()
+    env = make_env(n, p); o = Oracle(n, p)
+    env.reset(as_torch=True); o.reset()
+    for t in range(steps):
+        obs, rew, done, infos = env.step(torch.from_numpy(acts[t]).cuda())
+        tk = env.last_ticks.cpu().numpy()
+        oo, orr, od, ot = o.step(acts[t].astype(np.float64), threads=8)
+        og = obs.cpu().numpy().astype(np.float64); rg = rew.cpu().numpy().astype(np.float64); dg = done.cpu().numpy()
+        assert (tk == ot).mean() >= 0.97, (t, (tk == ot).mean())
+        assert (dg == od).mean() >= 0.97
+        same = (tk == ot) & (dg == od)
+        tol_q = 1e-5 if solver else 2e-3
+        assert np.abs(og - oo)[same][:, :16].max() < tol_q, (t, np.abs(og - oo)[same][:, :16].max())
+        assert np.median(np.abs(og - oo)[same][:, 48:51].max(1)) < 2e-3            # base position (contact sensitive)
+        assert np.median(np.abs(rg - orr)[same]) < 5e-3                            # reward
+        assert len(infos) == n and infos[0] == {}
+    env.close()
+
+
+def test_golden_scenarios_on_the_gpu(torch, golden):
+    """The reference-Python golden vectors (tests/golden, made by tools/make_golden.py): tick counts, done
+    flags and joint angles of every step; the contact-sensitive base pose over the first steps."""
+    for name in ("const_half", "random", "clipped", "serpenoid", "terminate_q9"):
+        acts = golden[name + "/actions"]
+        env = make_env(1)
+        obs0 = env.reset()
+        assert np.array_equal(obs0[0], golden[name + "/obs"][0])
+        agree = 0
+        for t, a in enumerate(acts):
+            ob, r, d, _ = env.step(a[None, :])                  # numpy in -> numpy out (snk_step_host)
+            tk = int(env.last_ticks[0])
+            if tk != int(golden[name + "/ticks"][t]) or bool(d[0]) != bool(golden[name + "/done"][t]):
+                break                                           # fp32 trajectories part ways after a discrete event
+            agree += 1
+            assert np.abs(ob[0, :16] - golden[name + "/obs"][t + 1][:16]).max() < 1e-5, (name, t)
+            if t < 3:
+                assert np.abs(ob[0, 48:51] - golden[name + "/obs"][t + 1][48:51]).max() < 2e-3, (name, t)
+                assert abs(r[0] - golden[name + "/rew"][t]) < 2e-2, (name, t)
+        assert agree >= min(len(acts), 8), (name, agree)
+        env.close()
+
+
+def test_gait_script_ticks_finite_motor_force(torch):
+    """config 1 of BASELINE.json: raw ticks at dt = 0.01, g = -9.81, 4 N.m motors (snake_gait_test.py:50-53,96-104),
+    serpenoid targets with t = tick * 0.01; the force limit makes the motor rows inequalities, so this runs
+    the warp-per-env kernel with Bullet-order rows."""
+    p = gait_params()
+    n = 8
+    env = make_env(n, p); o = Oracle(n, p)
+    env.reset(as_torch=True); o.reset()
+    nn = np.arange(16)
+    qerr = []
+    for tick in range(120):
+        tg = np.where(nn % 2 == 1, -(np.pi / 6) * np.sin(4 * nn + 2 * tick * 0.01), 0.0)[None, :].repeat(n, 0).astype(np.float32)
+        env.tick(tg, 1); o.tick(tg.astype(np.float64), 1)
+        qerr.append(np.abs(env.get_state().cpu().numpy()[:, 13:29] - o.get_state()[:, 13:29]).max())
+    assert max(qerr[:20]) < 1e-4 and max(qerr) < 5e-2, (max(qerr[:20]), max(qerr))
+    env.close()
+
+
+def test_hundred_step_gait_rollout_bounds(torch):
+    """north_star: 'within a stated bound over a 100-step gait rollout; episode rewards within 1%'.
+    Stated bounds for the serpenoid gait driven through env.step (free running, no re-synchronisation):
+    joint angles stay within 1e-4 rad of the oracle at every step where both sides ran the same number of
+    ticks; the batch-mean 100-step return agrees within 1%; per-environment returns within 5% median."""
+    n, steps = 64, 100
+    rng = np.random.default_rng(7)
+    acts = serpenoid_actions(steps, n, phase=rng.uniform(0, 2 * np.pi, n)).astype(np.float32)
+    p = default_params()
+    env = make_env(n, p); o = Oracle(n, p)
+    env.reset(as_torch=True); o.reset()
+    Rg = np.zeros(n); Ro = np.zeros(n); worst_q = 0.0; same_frac = []
+    for t in range(steps):
+        obs, rew, done, _ = env.step(torch.from_numpy(acts[t]).cuda())
+        oo, orr, od, ot = o.step(acts[t].astype(np.float64), threads=8)
+        tk = env.last_ticks.cpu().numpy()
+        same = (tk == ot) & (done.cpu().numpy() == od)
+        same_frac.append(same.mean())
+        if same.any():
+            worst_q = max(worst_q, float(np.abs(obs.cpu().numpy()[same][:, :16] - oo[same][:, :16]).max()))
+        Rg += rew.cpu().numpy(); Ro += orr
+    assert worst_q < 1e-4, worst_q
+    assert np.mean(same_frac) > 0.9
+    assert abs(Rg.mean() - Ro.mean()) <= 0.01 * abs(Ro.mean()) + 1e-3, (Rg.mean(), Ro.mean())
+    assert np.median(np.abs(Rg - Ro) / (np.abs(Ro) + 1e-9)) < 0.05
+    env.close()
+
+
+def test_numpy_path_equals_device_path(torch):
+    n = 97
+    rng = np.random.default_rng(2)
+    a = rng.uniform(-1, 1, (2, n, 8)).astype(np.float32)
+    e1 = make_env(n); e2 = make_env(n)
+    e1.reset(); e2.reset()
+    for t in range(2):
+        o1, r1, d1, _ = e1.step(a[t])
+        o2, r2, d2, _ = e2.step(torch.from_numpy(a[t]).cuda())
+        assert o1.dtype == np.float64 and d1.dtype == bool
+        assert np.array_equal(o1.astype(np.float32), o2.cpu().numpy()) and np.array_equal(r1.astype(np.float32), r2.cpu().numpy())
+        assert np.array_equal(d1, d2.cpu().numpy())
+    e1.close(); e2.close()
+
+
+def test_edge_cases(torch):
+    # ragged sizes: 1 env, a partial last CTA, out-of-range actions are clipped like np.clip
+    for n in (1, 31, 33):
+        env = make_env(n); o = Oracle(n)
+        env.reset(); o.reset()
+        a = np.linspace(-3, 3, n * 8, dtype=np.float32).reshape(n, 8)
+        ob, r, d, _ = env.step(a)
+        oo, orr, od, ot = o.step(a.astype(np.float64))
+        assert np.array_equal(np.asarray(env.last_ticks), ot)
+        assert np.abs(ob[:, :16] - oo[:, :16]).max() < 1e-5
+        env.close()
+    # zero-tick step (snake.py:283-284): repeat an action that is already reached
+    env = make_env(4); env.reset()
+    a = np.full((4, 8), 0.5, np.float32)
+    env.step(a); env.step(a)
+    ob, r, d, _ = env.step(a)
+    assert (np.asarray(env.last_ticks) == 0).all() and not d.any()
+    energy = np.sum(ob[:, 16:32] * ob[:, 32:48] * 0.01, axis=1)
+    assert np.allclose(r, -0.01 * np.abs(ob[:, 49]) - 0.1 * energy, atol=1e-6)
+    env.close()
+    # a NaN action is a no-op step, as in the reference (checkBound and checkFeedback compare false on NaN)
+    env = make_env(64); env.reset()
+    a = np.zeros((64, 8), np.float32); a[:, 1] = 0.8; a[5, 3] = np.nan
+    ob, r, d, _ = env.step(a)
+    tk = np.asarray(env.last_ticks)
+    assert tk[5] == 0 and (tk[np.arange(64) != 5] > 0).all() and np.isfinite(ob).all()
+    # a non-finite state poisons one environment only: it is force-reset, reported done and counted
+    s = env.get_state().cpu().numpy(); s[7, 8] = np.inf
+    env.set_state(s)
+    a[:, 1] = -0.8; a[5, 3] = 0.0
+    ob, r, d, _ = env.step(a)
+    c = env.counters()
+    assert np.isfinite(ob).all() and np.isfinite(r).all()
+    assert d[7] and r[7] == -5.0 and c["nonfinite"] == 1 and not d[np.arange(64) != 7].any()
+    env.close()
+    # closed handle
+    with pytest.raises(RuntimeError):
+        env.step(a)
