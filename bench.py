@@ -117,7 +117,7 @@ def run_reference(args):
         return 0
     import numpy as np  # noqa: F401
     threads = os.cpu_count() or 1
-    n = 64 * threads
+    n = 128 * threads
     # W warm-up + K timed steps, each a bounded sample of the workload (n environments)
     from bullet_envs_b200 import default_params
     from oracle.oracle_py import Oracle
@@ -264,7 +264,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            nb = 32 * threads
+            nb = 512 * threads  # ~10 s of CPU work per leg
             v0, tk0, dt0 = cpu_leg(0, nb, 2, threads)
             v2, tk2, dt2 = cpu_leg(2, 4 * nb, 2, threads)
             line["cpu_baseline"] = {"value": v0, "unit": "env-steps/s", "cores": threads, "kind": "port",

@@ -23,7 +23,7 @@ __constant__ ExTables cT;
 static_assert(sizeof(ExSmem) >= EB * (SNK_OBS_DIM + 1) * sizeof(float), "observation staging must fit in the row storage");
 
 // RAW = false: one SubprocVecEnv.step.  RAW = true: n_ticks raw ticks with targets[N,16] (gait script).
-template <bool RAW>
+template <bool RAW, bool CONE>
 __global__ void __launch_bounds__(EB, 3)
 snk_exact_kernel(const KParams P, float* __restrict__ state, int64_t npad, const float* __restrict__ in, float* __restrict__ obs,
                  float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks, unsigned long long* __restrict__ counters,
@@ -65,7 +65,7 @@ snk_exact_kernel(const KParams P, float* __restrict__ state, int64_t npad, const
         for (int t = 0; t < n_ticks; t++) {
             bool ab;
             ExTickOut to;
-            ex_tick(cT, P, S, e, false, &ab, &to);
+            ex_tick<CONE>(cT, P, S, e, false, &ab, &to);
             iters += to.iterations;
         }
         ex_store_base(e);
@@ -76,7 +76,7 @@ snk_exact_kernel(const KParams P, float* __restrict__ state, int64_t npad, const
         return;
     }
     ExStepOut o;
-    ex_env_step(cT, P, S, e, &o);
+    ex_env_step<CONE>(cT, P, S, e, &o);
     // ---- outputs: rew/done/ticks are one coalesced store per warp; obs goes through shared memory
     if (live) {
         rew[env] = o.rew;
@@ -119,22 +119,25 @@ size_t snk_exact_smem_bytes() { return sizeof(ExSmem); }
 
 cudaError_t snk_exact_configure(const ExTables* host_tables) {
     cudaError_t e = cudaMemcpyToSymbol(cT, host_tables, sizeof(ExTables));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(snk_exact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExSmem));
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(snk_exact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExSmem));
+    const void* kernels[4] = {(const void*)snk_exact_kernel<false, true>, (const void*)snk_exact_kernel<false, false>,
+                              (const void*)snk_exact_kernel<true, true>, (const void*)snk_exact_kernel<true, false>};
+    for (int i = 0; i < 4 && e == cudaSuccess; i++)
+        e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExSmem));
+    return e;
 }
 
 cudaError_t snk_exact_launch_step(const KParams& P, float* state, int64_t npad, const float* actions, float* obs, float* rew, uint8_t* done,
                                   int32_t* ticks, unsigned long long* counters, int64_t n, cudaStream_t st) {
     dim3 grid((unsigned)(npad / EB)), block(EB);
-    snk_exact_kernel<false><<<grid, block, sizeof(ExSmem), st>>>(P, state, npad, actions, obs, rew, done, ticks, counters, n, 0);
+    if (P.cone) snk_exact_kernel<false, true><<<grid, block, sizeof(ExSmem), st>>>(P, state, npad, actions, obs, rew, done, ticks, counters, n, 0);
+    else snk_exact_kernel<false, false><<<grid, block, sizeof(ExSmem), st>>>(P, state, npad, actions, obs, rew, done, ticks, counters, n, 0);
     return cudaGetLastError();
 }
 
 cudaError_t snk_exact_launch_tick(const KParams& P, float* state, int64_t npad, const float* targets, unsigned long long* counters, int64_t n,
                                   int n_ticks, cudaStream_t st) {
     dim3 grid((unsigned)(npad / EB)), block(EB);
-    snk_exact_kernel<true><<<grid, block, sizeof(ExSmem), st>>>(P, state, npad, targets, nullptr, nullptr, nullptr, nullptr, counters, n, n_ticks);
+    if (P.cone) snk_exact_kernel<true, true><<<grid, block, sizeof(ExSmem), st>>>(P, state, npad, targets, nullptr, nullptr, nullptr, nullptr, counters, n, n_ticks);
+    else snk_exact_kernel<true, false><<<grid, block, sizeof(ExSmem), st>>>(P, state, npad, targets, nullptr, nullptr, nullptr, nullptr, counters, n, n_ticks);
     return cudaGetLastError();
 }

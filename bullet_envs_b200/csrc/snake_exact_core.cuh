@@ -57,15 +57,15 @@ struct ExTables {
 
 // Shared-memory record of one CTA: contact rows as [contact][thread] columns.
 struct ExSmem {
-    float4 A[NC][EB];  // rx, ry (lever arm about C), rhs_n, invD_n
+    float4 A[NC][EB];  // rx, ry (lever arm about C), rhs_n * invD_n, invD_n
     float4 B[NC][EB];  // rz, d1x, d1y, d1z
-    float4 C[NC][EB];  // d2x, d2y, d2z, rhs_1
+    float4 C[NC][EB];  // d2x, d2y, d2z, rhs_1 * invD_1
+    float4 L[NC][EB];  // friction impulses (2), rhs_2 * invD_2, normal impulse
     float2 E[NC][EB];  // invD_1, invD_2
-    float R2[NC][EB];  // rhs_2
-    float Ln[NC][EB];  // normal impulse
-    float2 Lf[NC][EB]; // friction impulses
     float tgt[NJ][EB]; // joint targets of this env-step
 };
+// a contact farther than its breaking threshold keeps an all-zero record: every update it produces is
+// exactly zero, so the solver loops need no per-contact branch
 
 // ---- small float3 helpers -------------------------------------------------------------------
 struct V3 { float x, y, z; };
@@ -110,7 +110,22 @@ SNK_HD float ex_rcp(float x) {
     return 1.0f / x;
 #endif
 }
-SNK_HD float ex_rsqrt(float x) { return 1.0f / sqrtf(x); }
+// clamp to [-m, m] with the oracle's comparisons (a NaN passes through, unlike fminf/fmaxf)
+SNK_HD float ex_clamp(float x, float m) { x = (x > m) ? m : x; return (x < -m) ? -m : x; }
+SNK_HD int ex_popc(unsigned x) {
+#ifdef __CUDA_ARCH__
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+SNK_HD float ex_rsqrt(float x) {
+#ifdef __CUDA_ARCH__
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
 SNK_HD void ex_sincos(float a, float* s, float* c) {
 #ifdef __CUDA_ARCH__
     sincosf(a, s, c);
@@ -195,6 +210,7 @@ struct ExTickOut { int iterations; int contacts; float height; float err2_next; 
 // out->height; when `probe_only` is set (or when that height already exceeds the threshold and
 // `abort_on_height`), nothing is modified and *aborted = true.
 // -----------------------------------------------------------------------------------------------
+template <bool CONE>
 SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bool abort_on_height, bool* aborted, ExTickOut* out) {
     const int tid = e.tid;
     const float dt = P.dt, inv_dt = P.inv_dt;
@@ -218,7 +234,7 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bo
             const float q = qn, qd = qdn, tg = S.tgt[j][tid];
             if (i < NJ) { qn = slot(e, SNK_S_Q + i); qdn = slot(e, SNK_S_QD + i); }
             float qds = P.kp * (tg - q) * inv_dt;
-            qds = fminf(fmaxf(qds, -P.maxvel), P.maxvel);
+            qds = ex_clamp(qds, P.maxvel);
             const float qdd = (qds - qd) * inv_dt;
             const float en = tg - (q + dt * qds);
             err2n += en * en;
@@ -278,7 +294,7 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bo
             S.A[k][tid] = make_float4(pc.x, pc.y, uJ.x, 0.f);
             S.B[k][tid] = make_float4(pc.z, d1.x, d1.y, d1.z);
             S.C[k][tid] = make_float4(d2.x, d2.y, d2.z, uJ.y);
-            S.R2[k][tid] = uJ.z;
+            S.L[k][tid] = make_float4(0.f, 0.f, uJ.z, 0.f);
         }
     }
     out->height = hsum * (1.f / NB);
@@ -311,13 +327,15 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bo
     // (the base origin moves with this rigid field: v0' = VC - wf x hc, i.e. a0 = aC - alf x hc)
 
     // ------------------------------------------------------------------ rows
-    int ncontacts = 0;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
     for (int k = 0; k < NC; k++) {
-        if (!((act >> k) & 1u)) continue;
-        ncontacts++;
+        if (!((act >> k) & 1u)) {
+            S.A[k][tid] = zero4; S.B[k][tid] = zero4; S.C[k][tid] = zero4; S.L[k][tid] = zero4; S.E[k][tid] = make_float2(0.f, 0.f);
+            continue;
+        }
         float4 a = S.A[k][tid], b = S.B[k][tid], cc = S.C[k][tid];
-        const float uJz = S.R2[k][tid];
+        const float uJz = S.L[k][tid].z;
         const V3 uJ = mk(a.z, cc.w, uJz);
         const float dist = b.x + p0z;
         const V3 r = mk(a.x - hc.x, a.y - hc.y, b.x - hc.z);
@@ -340,62 +358,72 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bo
         S.A[k][tid] = make_float4(r.x, r.y, rhsn, iDn);
         S.B[k][tid] = make_float4(r.z, d1.x, d1.y, d1.z);
         S.C[k][tid] = make_float4(d2.x, d2.y, d2.z, -dot(d1, vp) * iD1);
+        S.L[k][tid] = make_float4(0.f, 0.f, -dot(d2, vp) * iD2, 0.f);
         S.E[k][tid] = make_float2(iD1, iD2);
-        S.R2[k][tid] = -dot(d2, vp) * iD2;
-        S.Ln[k][tid] = 0.f;
-        S.Lf[k][tid] = make_float2(0.f, 0.f);
     }
 
     // ------------------------------------------------------------------ projected Gauss-Seidel
+    // The only serial dependence is the 6-vector (dw, dV); everything else of a row (loads, impulse
+    // store, residual) is off that chain, and the loops are branch free so that the scheduler can
+    // overlap it with the chain of the neighbouring rows.  The residual rule max (d D)^2 <= thr is
+    // evaluated division free as  |d| <= sqrt(thr) invD  on every row.
     V3 dw = mk(0.f, 0.f, 0.f), dV = mk(0.f, 0.f, 0.f);
+    const float sthr = sqrtf(P.resthr), mu = P.mu;
     int it = 0;
 #pragma unroll 1
     for (;; it++) {
-        float res = 0.f;
-#pragma unroll 1
+        float viol = 0.f; // max over the rows of |d| - sqrt(thr) invD (in the row's scaled units)
+#pragma unroll 4
         for (int k = 0; k < NC; k++) {
-            if (!((act >> k) & 1u)) continue;
             const float4 a = S.A[k][tid];
-            const float ln = S.Ln[k][tid];
-            const float jd = dV.z + dw.x * a.y - dw.y * a.x;
-            float d = a.z - jd * a.w;
-            float sum = ln + d;
-            if (sum < 0.f) { d = -ln; sum = 0.f; }
-            S.Ln[k][tid] = sum;
-            const V3 rn = mk(a.y * d, -a.x * d, 0.f);
-            dw = dw + mul(Ji, rn);
-            dV.z += d * invM;
-            const float rr = d * ex_rcp(a.w);
-            res = fmaxf(res, rr * rr);
+            const float ln = S.L[k][tid].w;
+            const float p = ln + a.z;
+            float jd = fmaf(dw.x, a.y, dV.z);
+            jd = fmaf(-dw.y, a.x, jd);
+            const float sum = fmaxf(fmaf(-jd, a.w, p), 0.f);
+            const float dd = sum - ln;
+            S.L[k][tid].w = sum;
+            const float t1 = a.y * dd, t2 = -a.x * dd; // rn * dd
+            dw.x = fmaf(Ji.xx, t1, fmaf(Ji.xy, t2, dw.x));
+            dw.y = fmaf(Ji.xy, t1, fmaf(Ji.yy, t2, dw.y));
+            dw.z = fmaf(Ji.xz, t1, fmaf(Ji.yz, t2, dw.z));
+            dV.z = fmaf(dd, invM, dV.z);
+            viol = fmaxf(viol, fmaf(-sthr, a.w, fabsf(dd)));
         }
-#pragma unroll 1
+#pragma unroll 2
         for (int k = 0; k < NC; k++) {
-            if (!((act >> k) & 1u)) continue;
-            const float4 a = S.A[k][tid], b = S.B[k][tid], cc = S.C[k][tid];
-            const float2 ee = S.E[k][tid], lf = S.Lf[k][tid];
-            const float rhs2 = S.R2[k][tid], lim = P.mu * S.Ln[k][tid];
-            const V3 r = mk(a.x, a.y, b.x), d1 = mk(b.y, b.z, b.w), d2 = mk(cc.x, cc.y, cc.z);
-            const V3 u = dV + cross(dw, r);
-            float sa = lf.x + (cc.w - dot(d1, u) * ee.x), sb = lf.y + (rhs2 - dot(d2, u) * ee.y);
-            if (P.cone) {
-                const float n2 = sa * sa + sb * sb;
-                if (n2 > lim * lim) { const float sc = lim * ex_rsqrt(n2); sa *= sc; sb *= sc; }
+            const float4 a = S.A[k][tid], b = S.B[k][tid], cc = S.C[k][tid], l = S.L[k][tid];
+            const float2 ee = S.E[k][tid];
+            const float pa = l.x + cc.w, pb = l.y + l.z, lim = mu * l.w;
+            // u = dV + dw x r
+            const float ux = fmaf(-dw.z, a.y, fmaf(dw.y, b.x, dV.x));
+            const float uy = fmaf(-dw.x, b.x, fmaf(dw.z, a.x, dV.y));
+            const float uz = fmaf(-dw.y, a.x, fmaf(dw.x, a.y, dV.z));
+            const float g1 = fmaf(b.w, uz, fmaf(b.z, uy, b.y * ux)), g2 = fmaf(cc.z, uz, fmaf(cc.y, uy, cc.x * ux));
+            float sa = fmaf(-g1, ee.x, pa), sb = fmaf(-g2, ee.y, pb);
+            if (CONE) { // implicit cone: radial projection onto the disc of radius mu * lambda_n
+                const float n2 = fmaf(sa, sa, sb * sb);
+                const float sc = (n2 > lim * lim) ? lim * ex_rsqrt(n2) : 1.f;
+                sa *= sc; sb *= sc;
             } else {
                 sa = fminf(fmaxf(sa, -lim), lim);
                 sb = fminf(fmaxf(sb, -lim), lim);
             }
-            const float da = sa - lf.x, db = sb - lf.y;
-            S.Lf[k][tid] = make_float2(sa, sb);
-            const V3 f = d1 * da + d2 * db;
-            dV = dV + f * invM;
-            dw = dw + mul(Ji, cross(r, f));
-            const float rr = da * ex_rcp(ee.x) + db * ex_rcp(ee.y);
-            res = fmaxf(res, rr * rr);
+            const float da = sa - l.x, db = sb - l.y;
+            *reinterpret_cast<float2*>(&S.L[k][tid]) = make_float2(sa, sb);
+            const float fx = fmaf(cc.x, db, b.y * da), fy = fmaf(cc.y, db, b.z * da), fz = fmaf(cc.z, db, b.w * da);
+            dV.x = fmaf(fx, invM, dV.x); dV.y = fmaf(fy, invM, dV.y); dV.z = fmaf(fz, invM, dV.z);
+            const float tx = fmaf(a.y, fz, -b.x * fy), ty = fmaf(b.x, fx, -a.x * fz), tz = fmaf(a.x, fy, -a.y * fx); // r x f
+            dw.x = fmaf(Ji.xx, tx, fmaf(Ji.xy, ty, fmaf(Ji.xz, tz, dw.x)));
+            dw.y = fmaf(Ji.xy, tx, fmaf(Ji.yy, ty, fmaf(Ji.yz, tz, dw.y)));
+            dw.z = fmaf(Ji.xz, tx, fmaf(Ji.yz, ty, fmaf(Ji.zz, tz, dw.z)));
+            // (da D1 + db D2)^2 <= thr  <=>  |da invD2 + db invD1| <= sqrt(thr) invD1 invD2
+            viol = fmaxf(viol, fmaf(-sthr * ee.x, ee.y, fabsf(fmaf(da, ee.y, db * ee.x))));
         }
-        if (res <= P.resthr || it >= P.iters - 1) break;
+        if (viol <= 0.f || it >= P.iters - 1) break;
     }
     out->iterations = it + 1;
-    out->contacts = ncontacts;
+    out->contacts = ex_popc(act);
 
     // ------------------------------------------------------------------ new base velocity
     // rigid field after the solve: angular wf + dw, velocity VC + dV at C; base origin = field at -hc
@@ -407,8 +435,8 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bo
     // clamp in body-0 axes (maxCoordinateVelocity)
     const M3 R0 = quat_to_m3(e.quat);
     V3 wb = mulT(R0, wN_u), vb = mulT(R0, vN_u);
-    wb = mk(fminf(fmaxf(wb.x, -P.maxvel), P.maxvel), fminf(fmaxf(wb.y, -P.maxvel), P.maxvel), fminf(fmaxf(wb.z, -P.maxvel), P.maxvel));
-    vb = mk(fminf(fmaxf(vb.x, -P.maxvel), P.maxvel), fminf(fmaxf(vb.y, -P.maxvel), P.maxvel), fminf(fmaxf(vb.z, -P.maxvel), P.maxvel));
+    wb = mk(ex_clamp(wb.x, P.maxvel), ex_clamp(wb.y, P.maxvel), ex_clamp(wb.z, P.maxvel));
+    vb = mk(ex_clamp(vb.x, P.maxvel), ex_clamp(vb.y, P.maxvel), ex_clamp(vb.z, P.maxvel));
     const V3 wN = mul(R0, wb), vN = mul(R0, vb);
 
     // ------------------------------------------------------------------ pass 2: base-ward, torques
@@ -419,7 +447,7 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bo
             const int j = i - 1;
             const float q = slot(e, SNK_S_Q + j), qd = slot(e, SNK_S_QD + j), tg = S.tgt[j][tid];
             float qds = P.kp * (tg - q) * inv_dt;
-            qds = fminf(fmaxf(qds, -P.maxvel), P.maxvel);
+            qds = ex_clamp(qds, P.maxvel);
             const float qdd = (qds - qd) * inv_dt;
             // wrench of body i with the true accelerations
             V3 rc = mul(c.R, ld3(T.com[i]));
@@ -435,10 +463,8 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bo
 #pragma unroll 1
             for (int k = T.cstart[i]; k < T.cstart[i + 1]; k++) {
                 if (!((act >> k) & 1u)) continue;
-                const float4 a = S.A[k][tid], b = S.B[k][tid], c4 = S.C[k][tid];
-                const float2 lf = S.Lf[k][tid];
-                const float ln = S.Ln[k][tid];
-                V3 f = mk(b.y * lf.x + c4.x * lf.y, b.z * lf.x + c4.y * lf.y, ln + b.w * lf.x + c4.z * lf.y) * inv_dt;
+                const float4 a = S.A[k][tid], b = S.B[k][tid], c4 = S.C[k][tid], l = S.L[k][tid];
+                V3 f = mk(b.y * l.x + c4.x * l.y, b.z * l.x + c4.y * l.y, l.w + b.w * l.x + c4.z * l.y) * inv_dt;
                 V3 r = mk(a.x + hc.x, a.y + hc.y, b.x + hc.z); // back to the base origin
                 SF = SF - f;
                 SN = SN - cross(r, f);
@@ -537,6 +563,7 @@ SNK_HD void ex_store_base(const ExEnv& e) {
     for (int k = 0; k < 4; k++) slot(e, SNK_S_QUAT + k) = e.quat[k];
 }
 
+template <bool CONE>
 SNK_HD void ex_env_step(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, ExStepOut* o) {
     const int tid = e.tid;
     const float xprev = e.pos[0]; // self._observation[48], vec-wrapper semantics (Q8)
@@ -549,7 +576,7 @@ SNK_HD void ex_env_step(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e
     while (sqrtf(e2) > P.errthr) { // snake.py:284-304
         bool aborted;
         ExTickOut to;
-        ex_tick(T, P, S, e, counter > 0, &aborted, &to);
+        ex_tick<CONE>(T, P, S, e, counter > 0, &aborted, &to);
         if (aborted) { end_height = true; height = to.height; have_height = true; break; } // the previous tick lifted the snake
         iters += to.iterations;
         counter++;

@@ -504,7 +504,7 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
     }
 
     // ---- velocity update, joint feedback, semi-implicit Euler ----
-    if (dof) W.nuF[lane] = fminf(fmaxf(W.nu[lane] + dv, -P.maxvel), P.maxvel);
+    if (dof) { float x = W.nu[lane] + dv; x = (x > P.maxvel) ? P.maxvel : x; W.nuF[lane] = (x < -P.maxvel) ? -P.maxvel : x; } // NaN passes through
     __syncwarp();
     float wnew[3], vnew[3];
     m3v(W.Rw[0], W.nuF, wnew);
