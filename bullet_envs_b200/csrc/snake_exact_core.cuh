@@ -112,6 +112,16 @@ SNK_HD float ex_rcp(float x) {
 }
 // clamp to [-m, m] with the oracle's comparisons (a NaN passes through, unlike fminf/fmaxf)
 SNK_HD float ex_clamp(float x, float m) { x = (x > m) ? m : x; return (x < -m) ? -m : x; }
+// single MUFU.RSQ (flush-to-zero, no denormal fix-up): only used on the solver's serial chain
+SNK_HD float ex_rsqrt_fast(float x) {
+#ifdef __CUDA_ARCH__
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
 SNK_HD int ex_popc(unsigned x) {
 #ifdef __CUDA_ARCH__
     return __popc(x);
@@ -373,52 +383,64 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bo
 #pragma unroll 1
     for (;; it++) {
         float viol = 0.f; // max over the rows of |d| - sqrt(thr) invD (in the row's scaled units)
+        {   // ---- normal rows; the record of row k+1 is fetched while row k is on the chain
+            float4 a = S.A[0][tid];
+            float ln = S.L[0][tid].w;
 #pragma unroll 4
-        for (int k = 0; k < NC; k++) {
-            const float4 a = S.A[k][tid];
-            const float ln = S.L[k][tid].w;
-            const float p = ln + a.z;
-            float jd = fmaf(dw.x, a.y, dV.z);
-            jd = fmaf(-dw.y, a.x, jd);
-            const float sum = fmaxf(fmaf(-jd, a.w, p), 0.f);
-            const float dd = sum - ln;
-            S.L[k][tid].w = sum;
-            const float t1 = a.y * dd, t2 = -a.x * dd; // rn * dd
-            dw.x = fmaf(Ji.xx, t1, fmaf(Ji.xy, t2, dw.x));
-            dw.y = fmaf(Ji.xy, t1, fmaf(Ji.yy, t2, dw.y));
-            dw.z = fmaf(Ji.xz, t1, fmaf(Ji.yz, t2, dw.z));
-            dV.z = fmaf(dd, invM, dV.z);
-            viol = fmaxf(viol, fmaf(-sthr, a.w, fabsf(dd)));
-        }
-#pragma unroll 2
-        for (int k = 0; k < NC; k++) {
-            const float4 a = S.A[k][tid], b = S.B[k][tid], cc = S.C[k][tid], l = S.L[k][tid];
-            const float2 ee = S.E[k][tid];
-            const float pa = l.x + cc.w, pb = l.y + l.z, lim = mu * l.w;
-            // u = dV + dw x r
-            const float ux = fmaf(-dw.z, a.y, fmaf(dw.y, b.x, dV.x));
-            const float uy = fmaf(-dw.x, b.x, fmaf(dw.z, a.x, dV.y));
-            const float uz = fmaf(-dw.y, a.x, fmaf(dw.x, a.y, dV.z));
-            const float g1 = fmaf(b.w, uz, fmaf(b.z, uy, b.y * ux)), g2 = fmaf(cc.z, uz, fmaf(cc.y, uy, cc.x * ux));
-            float sa = fmaf(-g1, ee.x, pa), sb = fmaf(-g2, ee.y, pb);
-            if (CONE) { // implicit cone: radial projection onto the disc of radius mu * lambda_n
-                const float n2 = fmaf(sa, sa, sb * sb);
-                const float sc = (n2 > lim * lim) ? lim * ex_rsqrt(n2) : 1.f;
-                sa *= sc; sb *= sc;
-            } else {
-                sa = fminf(fmaxf(sa, -lim), lim);
-                sb = fminf(fmaxf(sb, -lim), lim);
+            for (int k = 0; k < NC; k++) {
+                const int kn = (k + 1) & (NC - 1);
+                const float4 an = S.A[kn][tid];
+                const float lnn = S.L[kn][tid].w;
+                const float p = ln + a.z;
+                float jd = fmaf(dw.x, a.y, dV.z);
+                jd = fmaf(-dw.y, a.x, jd);
+                const float sum = fmaxf(fmaf(-jd, a.w, p), 0.f);
+                const float dd = sum - ln;
+                S.L[k][tid].w = sum;
+                const float t1 = a.y * dd, t2 = -a.x * dd; // rn * dd
+                dw.x = fmaf(Ji.xx, t1, fmaf(Ji.xy, t2, dw.x));
+                dw.y = fmaf(Ji.xy, t1, fmaf(Ji.yy, t2, dw.y));
+                dw.z = fmaf(Ji.xz, t1, fmaf(Ji.yz, t2, dw.z));
+                dV.z = fmaf(dd, invM, dV.z);
+                viol = fmaxf(viol, fmaf(-sthr, a.w, fabsf(dd)));
+                a = an; ln = lnn;
             }
-            const float da = sa - l.x, db = sb - l.y;
-            *reinterpret_cast<float2*>(&S.L[k][tid]) = make_float2(sa, sb);
-            const float fx = fmaf(cc.x, db, b.y * da), fy = fmaf(cc.y, db, b.z * da), fz = fmaf(cc.z, db, b.w * da);
-            dV.x = fmaf(fx, invM, dV.x); dV.y = fmaf(fy, invM, dV.y); dV.z = fmaf(fz, invM, dV.z);
-            const float tx = fmaf(a.y, fz, -b.x * fy), ty = fmaf(b.x, fx, -a.x * fz), tz = fmaf(a.x, fy, -a.y * fx); // r x f
-            dw.x = fmaf(Ji.xx, tx, fmaf(Ji.xy, ty, fmaf(Ji.xz, tz, dw.x)));
-            dw.y = fmaf(Ji.xy, tx, fmaf(Ji.yy, ty, fmaf(Ji.yz, tz, dw.y)));
-            dw.z = fmaf(Ji.xz, tx, fmaf(Ji.yz, ty, fmaf(Ji.zz, tz, dw.z)));
-            // (da D1 + db D2)^2 <= thr  <=>  |da invD2 + db invD1| <= sqrt(thr) invD1 invD2
-            viol = fmaxf(viol, fmaf(-sthr * ee.x, ee.y, fabsf(fmaf(da, ee.y, db * ee.x))));
+        }
+        {   // ---- friction pairs
+            float4 a = S.A[0][tid], b = S.B[0][tid], cc = S.C[0][tid], l = S.L[0][tid];
+            float2 ee = S.E[0][tid];
+#pragma unroll 2
+            for (int k = 0; k < NC; k++) {
+                const int kn = (k + 1) & (NC - 1);
+                const float4 an = S.A[kn][tid], bn = S.B[kn][tid], cn = S.C[kn][tid], lnx = S.L[kn][tid];
+                const float2 en = S.E[kn][tid];
+                const float pa = l.x + cc.w, pb = l.y + l.z, lim = mu * l.w;
+                // u = dV + dw x r
+                const float ux = fmaf(-dw.z, a.y, fmaf(dw.y, b.x, dV.x));
+                const float uy = fmaf(-dw.x, b.x, fmaf(dw.z, a.x, dV.y));
+                const float uz = fmaf(-dw.y, a.x, fmaf(dw.x, a.y, dV.z));
+                const float g1 = fmaf(b.w, uz, fmaf(b.z, uy, b.y * ux)), g2 = fmaf(cc.z, uz, fmaf(cc.y, uy, cc.x * ux));
+                float sa = fmaf(-g1, ee.x, pa), sb = fmaf(-g2, ee.y, pb);
+                if (CONE) { // implicit cone: radial projection onto the disc of radius mu * lambda_n,
+                            // s <- s min(1, lim / |s|)  (0/0 and lim/0 resolve to 1 through fminf)
+                    const float sc = fminf(1.f, lim * ex_rsqrt_fast(fmaf(sa, sa, sb * sb)));
+                    sa *= sc; sb *= sc;
+                } else {
+                    sa = fminf(fmaxf(sa, -lim), lim);
+                    sb = fminf(fmaxf(sb, -lim), lim);
+                }
+                const float da = sa - l.x, db = sb - l.y;
+                *reinterpret_cast<float2*>(&S.L[k][tid]) = make_float2(sa, sb);
+                const float fx = fmaf(cc.x, db, b.y * da), fy = fmaf(cc.y, db, b.z * da), fz = fmaf(cc.z, db, b.w * da);
+                dV.x = fmaf(fx, invM, dV.x); dV.y = fmaf(fy, invM, dV.y); dV.z = fmaf(fz, invM, dV.z);
+                const float tx = fmaf(a.y, fz, -b.x * fy), ty = fmaf(b.x, fx, -a.x * fz), tz = fmaf(a.x, fy, -a.y * fx); // r x f
+                dw.x = fmaf(Ji.xx, tx, fmaf(Ji.xy, ty, fmaf(Ji.xz, tz, dw.x)));
+                dw.y = fmaf(Ji.xy, tx, fmaf(Ji.yy, ty, fmaf(Ji.yz, tz, dw.y)));
+                dw.z = fmaf(Ji.xz, tx, fmaf(Ji.yz, ty, fmaf(Ji.zz, tz, dw.z)));
+                // (da D1 + db D2)^2 <= thr  <=>  |da invD2 + db invD1| <= sqrt(thr) invD1 invD2
+                viol = fmaxf(viol, fmaf(-sthr * ee.x, ee.y, fabsf(fmaf(da, ee.y, db * ee.x))));
+                a = an; b = bn; cc = cn; l = lnx; ee = en;
+            }
         }
         if (viol <= 0.f || it >= P.iters - 1) break;
     }
