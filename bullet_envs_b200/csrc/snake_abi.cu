@@ -20,13 +20,14 @@ cudaError_t snk_pgs_launch_tick(const DevTables* T, const KParams& P, float* sta
                                 int n_ticks, cudaStream_t st);
 // thread-per-env kernel with the motor rows eliminated (snake_exact.cu)
 cudaError_t snk_exact_configure(const ExTables* host_tables);
-cudaError_t snk_exact_launch_step(const KParams& P, float* state, int64_t npad, const float* actions, float* obs, float* rew, uint8_t* done,
+cudaError_t snk_exact_launch_step(const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
                                   int32_t* ticks, unsigned long long* counters, int64_t n, cudaStream_t st);
-cudaError_t snk_exact_launch_tick(const KParams& P, float* state, int64_t npad, const float* targets, unsigned long long* counters, int64_t n,
+cudaError_t snk_exact_launch_tick(const KParams& P, float* state, const float* targets, unsigned long long* counters, int64_t n,
                                   int n_ticks, cudaStream_t st);
-// layout-aware reset / observe and state import / export (snake_pgs.cu)
-cudaError_t snk_launch_reset(const KParams& P, float* state, int64_t npad, const uint8_t* mask, float* obs, int64_t n, int mode, cudaStream_t st);
-cudaError_t snk_launch_transpose(const float* src, float* dst, int64_t n, int64_t npad, int to_soa, cudaStream_t st);
+// reset / observe (snake_pgs.cu)
+cudaError_t snk_launch_reset(const KParams& P, float* state, const uint8_t* mask, float* obs, int64_t n, int mode, cudaStream_t st);
+
+#define NCOUNTERS 8
 
 static thread_local char g_err[512] = "";
 
@@ -43,11 +44,11 @@ static int fail(int code, const char* fmt, const char* detail = "") {
 struct snk_handle {
     int device;
     int64_t n;
-    int64_t npad;                 // 0: state is [n][64] (warp-per-env kernel); else [64][npad] (thread-per-env kernel)
+    bool exact;                   // thread-per-env kernel with the motor rows eliminated (else warp-per-env, Bullet-order rows)
     KParams P;
     DevTables* T;                 // device (warp-per-env kernel only)
-    float* state;                 // device
-    unsigned long long* counters; // device [4]
+    float* state;                 // device [n][64]
+    unsigned long long* counters; // device [NCOUNTERS]: ticks, sweeps, dones, non-finite, work-queue head
     int64_t launches;
     // staging for the *_host entry points (allocated on first use)
     cudaStream_t hstream;
@@ -61,7 +62,7 @@ struct snk_handle {
 };
 
 static cudaError_t launch_step(snk_handle* h, const float* act, float* obs, float* rew, uint8_t* done, int32_t* ticks, cudaStream_t st) {
-    if (h->npad) return snk_exact_launch_step(h->P, h->state, h->npad, act, obs, rew, done, ticks, h->counters, h->n, st);
+    if (h->exact) return snk_exact_launch_step(h->P, h->state, act, obs, rew, done, ticks, h->counters, h->n, st);
     return snk_pgs_launch_step(h->T, h->P, h->state, act, obs, rew, done, ticks, h->counters, h->n, st);
 }
 
@@ -114,7 +115,7 @@ int snk_create(const snk_model* model, const snk_params* params, int64_t n_envs,
     if (h->P.exact) { // thread-per-env kernel: tables in constant memory, state as [slot][env]
         ExTables xt;
         if (snk_to_extables(model, &xt)) { delete h; return fail(SNK_E_ARG, "snk_create: model layout not supported by the exact motor solver%s"); }
-        h->npad = (n_envs + EB - 1) / EB * EB;
+        h->exact = true;
         err = snk_exact_configure(&xt);
     } else {
         DevTables host_tables;
@@ -123,11 +124,10 @@ int snk_create(const snk_model* model, const snk_params* params, int64_t n_envs,
         if (err == cudaSuccess) err = cudaMalloc(&h->T, sizeof(DevTables));
         if (err == cudaSuccess) err = cudaMemcpy(h->T, &host_tables, sizeof host_tables, cudaMemcpyHostToDevice);
     }
-    const size_t cols = (size_t)(h->npad ? h->npad : n_envs);
-    if (err == cudaSuccess) err = cudaMalloc(&h->state, cols * SNK_STATE_STRIDE * sizeof(float));
-    if (err == cudaSuccess) err = cudaMalloc(&h->counters, 4 * sizeof(unsigned long long));
-    if (err == cudaSuccess) err = cudaMemset(h->counters, 0, 4 * sizeof(unsigned long long));
-    if (err == cudaSuccess) err = snk_launch_reset(h->P, h->state, h->npad, nullptr, nullptr, h->n, 1, 0);
+    if (err == cudaSuccess) err = cudaMalloc(&h->state, (size_t)n_envs * SNK_STATE_STRIDE * sizeof(float));
+    if (err == cudaSuccess) err = cudaMalloc(&h->counters, NCOUNTERS * sizeof(unsigned long long));
+    if (err == cudaSuccess) err = cudaMemset(h->counters, 0, NCOUNTERS * sizeof(unsigned long long));
+    if (err == cudaSuccess) err = snk_launch_reset(h->P, h->state, nullptr, nullptr, h->n, 1, 0);
     if (err == cudaSuccess) err = cudaDeviceSynchronize();
     if (err != cudaSuccess) {
         cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters);
@@ -162,7 +162,7 @@ int64_t snk_launch_count(const snk_handle* h) { return h ? h->launches : 0; }
 int snk_reset(snk_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
     if (!h) return fail(SNK_E_ARG, "snk_reset: null handle%s");
     CU(cudaSetDevice(h->device));
-    CU(snk_launch_reset(h->P, h->state, h->npad, mask_dev, obs_dev, h->n, 0, (cudaStream_t)stream));
+    CU(snk_launch_reset(h->P, h->state, mask_dev, obs_dev, h->n, 0, (cudaStream_t)stream));
     h->launches++;
     return 0;
 }
@@ -170,7 +170,7 @@ int snk_reset(snk_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stre
 int snk_observe(snk_handle* h, float* obs_dev, void* stream) {
     if (!h || !obs_dev) return fail(SNK_E_ARG, "snk_observe: null pointer%s");
     CU(cudaSetDevice(h->device));
-    CU(snk_launch_reset(h->P, h->state, h->npad, nullptr, obs_dev, h->n, 2, (cudaStream_t)stream));
+    CU(snk_launch_reset(h->P, h->state, nullptr, obs_dev, h->n, 2, (cudaStream_t)stream));
     h->launches++;
     return 0;
 }
@@ -179,7 +179,7 @@ int snk_step(snk_handle* h, const float* actions_dev, float* obs_dev, float* rew
     if (!h || !actions_dev || !obs_dev || !rew_dev || !done_dev) return fail(SNK_E_ARG, "snk_step: null pointer%s");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaMemsetAsync(h->counters, 0, 4 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
     CU(launch_step(h, actions_dev, obs_dev, rew_dev, done_dev, ticks_dev, st));
     h->launches++;
     return 0;
@@ -189,8 +189,8 @@ int snk_tick(snk_handle* h, const float* targets_dev, int32_t n_ticks, void* str
     if (!h || !targets_dev || n_ticks < 0) return fail(SNK_E_ARG, "snk_tick: bad argument%s");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaMemsetAsync(h->counters, 0, 4 * sizeof(unsigned long long), st));
-    if (h->npad) CU(snk_exact_launch_tick(h->P, h->state, h->npad, targets_dev, h->counters, h->n, n_ticks, st));
+    CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
+    if (h->exact) CU(snk_exact_launch_tick(h->P, h->state, targets_dev, h->counters, h->n, n_ticks, st));
     else CU(snk_pgs_launch_tick(h->T, h->P, h->state, targets_dev, h->counters, h->n, n_ticks, st));
     h->launches++;
     return 0;
@@ -225,7 +225,7 @@ int snk_step_host(snk_handle* h, const float* actions_host, float* obs_host, flo
     cudaStream_t st = h->hstream;
     memcpy(h->h_act, actions_host, na);
     CU(cudaMemcpyAsync(h->d_act, h->h_act, na, cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(h->counters, 0, 4 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
     CU(launch_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_ticks, st));
     h->launches++;
     CU(cudaMemcpyAsync(h->h_obs, h->d_obs, n * SNK_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -251,7 +251,7 @@ int snk_reset_host(snk_handle* h, const uint8_t* mask_host, float* obs_host) {
         memcpy(h->h_mask, mask_host, n);
         CU(cudaMemcpyAsync(h->d_mask, h->h_mask, n, cudaMemcpyHostToDevice, st));
     }
-    CU(snk_launch_reset(h->P, h->state, h->npad, mask_host ? h->d_mask : nullptr, obs_host ? h->d_obs : nullptr, h->n, 0, st));
+    CU(snk_launch_reset(h->P, h->state, mask_host ? h->d_mask : nullptr, obs_host ? h->d_obs : nullptr, h->n, 0, st));
     h->launches++;
     if (obs_host) CU(cudaMemcpyAsync(h->h_obs, h->d_obs, n * SNK_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -262,16 +262,14 @@ int snk_reset_host(snk_handle* h, const uint8_t* mask_host, float* obs_host) {
 int snk_get_state(snk_handle* h, float* state_dev, void* stream) {
     if (!h || !state_dev) return fail(SNK_E_ARG, "snk_get_state: null pointer%s");
     CU(cudaSetDevice(h->device));
-    if (h->npad) { CU(snk_launch_transpose(h->state, state_dev, h->n, h->npad, 0, (cudaStream_t)stream)); h->launches++; }
-    else CU(cudaMemcpyAsync(state_dev, h->state, (size_t)h->n * SNK_STATE_STRIDE * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    CU(cudaMemcpyAsync(state_dev, h->state, (size_t)h->n * SNK_STATE_STRIDE * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
 }
 
 int snk_set_state(snk_handle* h, const float* state_dev, void* stream) {
     if (!h || !state_dev) return fail(SNK_E_ARG, "snk_set_state: null pointer%s");
     CU(cudaSetDevice(h->device));
-    if (h->npad) { CU(snk_launch_transpose(state_dev, h->state, h->n, h->npad, 1, (cudaStream_t)stream)); h->launches++; }
-    else CU(cudaMemcpyAsync(h->state, state_dev, (size_t)h->n * SNK_STATE_STRIDE * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    CU(cudaMemcpyAsync(h->state, state_dev, (size_t)h->n * SNK_STATE_STRIDE * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
 }
 

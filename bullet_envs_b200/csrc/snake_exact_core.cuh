@@ -188,11 +188,10 @@ SNK_HD S3 world_inertia(const ExTables& T, int b, const M3& R) {
 // Per-thread view of the environment: registers (base state) + where its columns live.
 struct ExEnv {
     float pos[3], quat[4], vel[3], omg[3]; // base state (SNK_S_POS..SNK_S_OMEGA), registers
-    float* st;                             // &state[0 * npad + env]; slot k at st[k * npad]
-    int64_t npad;
+    float* st;                             // &state[env][0]; slot k at st[k] (256 B record, L1 resident during the step)
     int tid;                               // column in the CTA's shared arrays
 };
-SNK_HD float& slot(const ExEnv& e, int k) { return e.st[(int64_t)k * e.npad]; }
+SNK_HD float& slot(const ExEnv& e, int k) { return e.st[k]; }
 
 // Newton-Euler wrench of body b (force F, moment N about the COM) for COM acceleration ac, angular
 // velocity w / acceleration al; gravity and Bullet's velocity damping (per merged body, D2) are the
@@ -585,27 +584,36 @@ SNK_HD void ex_store_base(const ExEnv& e) {
     for (int k = 0; k < 4; k++) slot(e, SNK_S_QUAT + k) = e.quat[k];
 }
 
-template <bool CONE>
-SNK_HD void ex_env_step(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, ExStepOut* o) {
-    const int tid = e.tid;
-    const float xprev = e.pos[0]; // self._observation[48], vec-wrapper semantics (Q8)
+// progress of one environment through its env-step (snake.py:274-306): kept in registers between ticks
+struct ExRun { float xprev, e2, height; int counter, iters; bool end_height, have_height; };
+
+SNK_HD void ex_step_begin(const KParams& P, const ExSmem& S, const ExEnv& e, ExRun* r) {
+    r->xprev = e.pos[0]; // self._observation[48], vec-wrapper semantics (Q8)
     float e2 = 0.f;
 #pragma unroll 1
-    for (int j = 0; j < NJ; j++) { const float d = S.tgt[j][tid] - slot(e, SNK_S_Q + j); e2 += d * d; }
-    int counter = 0, iters = 0;
-    bool end_height = false, have_height = false;
-    float height = 0.f;
-    while (sqrtf(e2) > P.errthr) { // snake.py:284-304
-        bool aborted;
-        ExTickOut to;
-        ex_tick<CONE>(T, P, S, e, counter > 0, &aborted, &to);
-        if (aborted) { end_height = true; height = to.height; have_height = true; break; } // the previous tick lifted the snake
-        iters += to.iterations;
-        counter++;
-        e2 = to.err2_next;
-        if (counter >= P.maxticks) break; // `counter > 40`
-    }
-    if (!have_height) height = ex_height(T, e);
+    for (int j = 0; j < NJ; j++) { const float d = S.tgt[j][e.tid] - slot(e, SNK_S_Q + j); e2 += d * d; }
+    r->e2 = e2; r->height = 0.f; r->counter = 0; r->iters = 0; r->end_height = false; r->have_height = false;
+}
+
+// at most one physics tick; returns true when the tick loop of snake.py:284-304 has ended
+template <bool CONE>
+SNK_HD bool ex_step_advance(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, ExRun* r) {
+    if (!(sqrtf(r->e2) > P.errthr)) return true; // checkFeedback (snake.py:228-235); also the zero-tick step (Q5)
+    bool aborted;
+    ExTickOut to;
+    ex_tick<CONE>(T, P, S, e, r->counter > 0, &aborted, &to);
+    if (aborted) { r->end_height = true; r->height = to.height; r->have_height = true; return true; } // the previous tick lifted the snake
+    r->iters += to.iterations;
+    r->counter++;
+    r->e2 = to.err2_next;
+    return r->counter >= P.maxticks || !(sqrtf(r->e2) > P.errthr); // `counter > 40`
+}
+
+SNK_HD void ex_step_end(const ExTables& T, const KParams& P, ExEnv& e, const ExRun& run, ExStepOut* o) {
+    const float xprev = run.xprev;
+    const int counter = run.counter, iters = run.iters;
+    const bool end_height = run.end_height;
+    const float height = run.have_height ? run.height : ex_height(T, e);
     // non-finite guard, energy (snake.py:336-341)
     bool bad = false;
     float energy = 0.f;
@@ -644,4 +652,12 @@ SNK_HD void ex_env_step(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e
     slot(e, SNK_S_RET) = ret; slot(e, SNK_S_LEN) = len;
     ex_store_base(e);
     o->rew = r; o->done = d ? 1 : 0; o->ticks = counter; o->iters = iters; o->bad = bad ? 1 : 0;
+}
+
+template <bool CONE>
+SNK_HD void ex_env_step(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, ExStepOut* o) {
+    ExRun run;
+    ex_step_begin(P, S, e, &run);
+    while (!ex_step_advance<CONE>(T, P, S, e, &run)) {}
+    ex_step_end(T, P, e, run, o);
 }

@@ -557,44 +557,24 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
 #include "snake_task.cuh"
 
 // reset / observe: one thread per (env, state slot).  mode 0 = masked soft reset (+ optional obs of
-// every env), 1 = initialise everything, 2 = observe only.  npad = 0: state is [env][64] (warp-per-env
-// kernel); npad > 0: state is [64][npad] (thread-per-env kernel), padding columns included in `n`.
-__global__ void snk_reset_kernel(const KParams P, float* __restrict__ state, int64_t npad, const uint8_t* __restrict__ mask,
-                                 float* __restrict__ obs, int64_t n, int mode) {
+// every env), 1 = initialise everything, 2 = observe only.
+__global__ void snk_reset_kernel(const KParams P, float* __restrict__ state, const uint8_t* __restrict__ mask, float* __restrict__ obs,
+                                 int64_t n, int mode) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t env;
-    int k;
-    if (npad) { k = (int)(idx / npad); env = idx - (int64_t)k * npad; if (k >= SNK_STATE_STRIDE) return; }
-    else { env = idx >> 6; k = (int)(idx & 63); if (env >= n) return; }
-    float* s = npad ? state + (int64_t)k * npad + env : state + env * SNK_STATE_STRIDE + k;
-    float val = *s;
-    const bool pad = env >= n; // padding columns of the SoA layout stay in the reset pose
-    const bool hit = (mode == 1) || (mode == 0 && (pad || !mask || mask[env]));
+    int64_t env = idx >> 6;
+    int k = (int)(idx & 63);
+    if (env >= n) return;
+    float* s = state + env * SNK_STATE_STRIDE;
+    float val = s[k];
+    const bool hit = (mode == 1) || (mode == 0 && (!mask || mask[env]));
     if (hit) {
         bool keep = (k >= SNK_S_TAU && k <= SNK_S_FZ) && P.stale && mode == 0;
-        if (!keep) { val = (k == SNK_S_QUAT + 3) ? 1.f : 0.f; *s = val; }
+        if (!keep) { val = (k == SNK_S_QUAT + 3) ? 1.f : 0.f; s[k] = val; }
     }
-    if (obs && !pad && k < SNK_S_RET) { // state slot -> observation index (snake.py:209-217)
+    if (obs && k < SNK_S_RET) { // state slot -> observation index (snake.py:209-217)
         int o = (k < SNK_S_QUAT) ? 48 + k : (k < SNK_S_VEL) ? 51 + (k - SNK_S_QUAT) : (k < SNK_S_Q) ? -1 : (k < SNK_S_QD) ? k - SNK_S_Q
                 : (k < SNK_S_TAU) ? 16 + (k - SNK_S_QD) : (k < SNK_S_FZ) ? 32 + (k - SNK_S_TAU) : 55;
         if (o >= 0) obs[env * SNK_OBS_DIM + o] = val;
-    }
-}
-
-// state export / import between the caller's [N,64] array and the handle's [64][npad] layout:
-// 32 x 32 tiles through shared memory so both sides move full 128 B lines.
-__global__ void snk_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n, int64_t npad, int to_soa) {
-    __shared__ float tile[32][33];
-    const int64_t env0 = (int64_t)blockIdx.x * 32;
-    const int k0 = blockIdx.y * 32, tx = threadIdx.x, ty = threadIdx.y; // block (32, 8)
-    if (to_soa) {
-        for (int r = ty; r < 32; r += 8) { int64_t env = env0 + r; tile[r][tx] = (env < n) ? src[env * SNK_STATE_STRIDE + k0 + tx] : 0.f; }
-        __syncthreads();
-        for (int r = ty; r < 32; r += 8) { int64_t env = env0 + tx; if (env < n) dst[(int64_t)(k0 + r) * npad + env] = tile[tx][r]; }
-    } else {
-        for (int r = ty; r < 32; r += 8) { int64_t env = env0 + tx; tile[r][tx] = (env < n) ? src[(int64_t)(k0 + r) * npad + env] : 0.f; }
-        __syncthreads();
-        for (int r = ty; r < 32; r += 8) { int64_t env = env0 + r; if (env < n) dst[env * SNK_STATE_STRIDE + k0 + tx] = tile[tx][r]; }
     }
 }
 
@@ -623,15 +603,9 @@ cudaError_t snk_pgs_launch_tick(const DevTables* T, const KParams& P, float* sta
     return cudaGetLastError();
 }
 
-cudaError_t snk_launch_reset(const KParams& P, float* state, int64_t npad, const uint8_t* mask, float* obs, int64_t n, int mode, cudaStream_t st) {
-    int64_t total = (npad ? npad : n) * 64;
+cudaError_t snk_launch_reset(const KParams& P, float* state, const uint8_t* mask, float* obs, int64_t n, int mode, cudaStream_t st) {
+    int64_t total = n * 64;
     dim3 grid((unsigned)((total + 255) / 256)), block(256);
-    snk_reset_kernel<<<grid, block, 0, st>>>(P, state, npad, mask, obs, n, mode);
-    return cudaGetLastError();
-}
-
-cudaError_t snk_launch_transpose(const float* src, float* dst, int64_t n, int64_t npad, int to_soa, cudaStream_t st) {
-    dim3 grid((unsigned)((n + 31) / 32), 2), block(32, 8);
-    snk_transpose_kernel<<<grid, block, 0, st>>>(src, dst, n, npad, to_soa);
+    snk_reset_kernel<<<grid, block, 0, st>>>(P, state, mask, obs, n, mode);
     return cudaGetLastError();
 }

@@ -28,8 +28,8 @@ static inline float4 make_float4(float x, float y, float z, float w) { float4 r 
 struct Emu {
     ExTables T;
     KParams P;
-    int64_t n, npad;
-    float* state; // [64][npad]
+    int64_t n;
+    float* state; // [n][64]
     ExSmem S;
     int64_t counters[4];
 };
@@ -51,24 +51,24 @@ int emu_create(const snk_model* M, const snk_params* p, int64_t n, Emu** out) {
     Emu* h = (Emu*)calloc(1, sizeof(Emu));
     if (snk_to_extables(M, &h->T)) { free(h); return -1; }
     snk_to_kparams(p, &h->P);
-    h->n = n; h->npad = (n + 31) / 32 * 32;
-    h->state = (float*)calloc((size_t)64 * h->npad, sizeof(float));
-    for (int64_t e = 0; e < h->npad; e++) h->state[(SNK_S_QUAT + 3) * h->npad + e] = 1.f;
+    h->n = n;
+    h->state = (float*)calloc((size_t)64 * n, sizeof(float));
+    for (int64_t e = 0; e < n; e++) h->state[e * 64 + SNK_S_QUAT + 3] = 1.f;
     *out = h;
     return 0;
 }
 int emu_destroy(Emu* h) { free(h->state); free(h); return 0; }
 int emu_set_state(Emu* h, const float* aos) {
-    for (int64_t e = 0; e < h->n; e++) for (int k = 0; k < 64; k++) h->state[k * h->npad + e] = aos[e * 64 + k];
+    memcpy(h->state, aos, (size_t)h->n * 64 * sizeof(float));
     return 0;
 }
 int emu_get_state(Emu* h, float* aos) {
-    for (int64_t e = 0; e < h->n; e++) for (int k = 0; k < 64; k++) aos[e * 64 + k] = h->state[k * h->npad + e];
+    memcpy(aos, h->state, (size_t)h->n * 64 * sizeof(float));
     return 0;
 }
 int emu_tick(Emu* h, const float* targets, int n_ticks, int32_t* iters_out, int32_t* contacts_out, float* height_out) {
     for (int64_t e = 0; e < h->n; e++) {
-        ExEnv env; env.st = h->state + e; env.npad = h->npad; env.tid = (int)(e & 31);
+        ExEnv env; env.st = h->state + e * 64; env.tid = (int)(e & 31);
         for (int j = 0; j < NJ; j++) h->S.tgt[j][env.tid] = targets[e * NJ + j];
         ex_load_base(env);
         ExTickOut to = {0, 0, 0.f, 0.f};
@@ -86,7 +86,7 @@ int emu_tick(Emu* h, const float* targets, int n_ticks, int32_t* iters_out, int3
 }
 int emu_step(Emu* h, const float* actions, float* obs, float* rew, uint8_t* done, int32_t* ticks) {
     for (int64_t e = 0; e < h->n; e++) {
-        ExEnv env; env.st = h->state + e; env.npad = h->npad; env.tid = (int)(e & 31);
+        ExEnv env; env.st = h->state + e * 64; env.tid = (int)(e & 31);
         set_targets_from_actions(h, actions + e * h->P.actdim, env.tid);
         ex_load_base(env);
         ExStepOut o;
