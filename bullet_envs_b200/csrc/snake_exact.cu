@@ -5,56 +5,74 @@
 // snake_exact_core.cuh for the algorithm and oracle/snake_oracle.c:tick_exact for its CPU twin).
 //
 // One launch = one SubprocVecEnv.step(): clip + createAction, the data-dependent 0..41-tick loop,
-// observation, reward, termination, auto-reset.  The grid is persistent: 3 one-warp CTAs per SM (the
-// shared-memory limit), each lane owning one environment at a time.  The lock-step unit of a warp is
-// ONE PHYSICS TICK, not one env-step: a lane whose environment has finished its tick loop writes its
-// outputs and takes the next environment from a global counter while the other lanes keep ticking, so
-// the 0..41 spread of tick counts costs no idle lanes (only the last partial wave of the launch does).
+// observation, reward, termination, auto-reset.  The grid is persistent, one CTA of 6 warps per SM,
+// each lane owning one environment at a time (192 environments in flight per SM).  The per-environment
+// working set is the contact-row table (32 contacts x 18 words, re-read by every solver sweep), and what
+// bounds the kernel is how many of those tables fit on chip.  Blackwell has two on-chip memories:
+//   warps 0-3  keep their rows in TENSOR MEMORY (tcgen05.ld/st 32x32b: TMEM lane = thread, the 512 columns
+//              of the warp's quadrant = 32 contacts x 16 words), plus 10 KB of shared memory each;
+//   warps 4-5  keep theirs in shared memory ([word][contact][lane] columns, conflict free), 74 KB each.
+// The lock-step unit of a warp is ONE PHYSICS TICK, not one env-step: a lane whose environment has
+// finished its tick loop writes its outputs and takes the next environment from a global counter while
+// the other lanes keep ticking, so the 0..41 spread of tick counts costs no idle lanes.
 //
-// Data placement: contact rows in shared memory as [contact][thread] columns (conflict free), base
-// state and loop progress in registers, joint state in the environment's 256 B record of the handle's
-// [N][64] state array (L1 resident while the lane owns the environment), model tables in constant
-// memory at warp-uniform addresses.
+// Other data: base state and loop progress in registers, joint state in the environment's 256 B record
+// of the handle's [N][64] state array (L1 resident while the lane owns the environment), model tables in
+// constant memory at warp-uniform addresses.
 //
 // Reference call sites replaced: SnakeGymEnv.py:33-50,82-103; snake.py:209-306,336-341;
 // ppo/multiprocessing_env.py:11-16; snake_gait_test.py:96-104 (raw ticks).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "snake_exact_core.cuh"
 
 __constant__ ExTables cT;
 
 #define FULL 0xffffffffu
+#define TWARPS 4 // warps with rows in tensor memory (one per TMEM lane quadrant)
+#define SWARPS 2 // warps with rows in shared memory
+
+struct StepSmem {
+    RowsTmemAux t[TWARPS];
+    RowsSmemStore s[SWARPS];
+    uint32_t tmem_base;
+};
 
 // joint targets of one environment: checkBound (SnakeGymEnv.py:82-88) + createAction (snake.py:247-269)
 // + scaling (snake.py:223-225)
-__device__ __forceinline__ void load_targets(const KParams& P, ExSmem& S, int tid, const float* __restrict__ act) {
+template <class Rows>
+__device__ __forceinline__ void load_targets(const KParams& P, const Rows& R, const float* __restrict__ act) {
 #pragma unroll
-    for (int j = 0; j < NJ; j++) S.tgt[j][tid] = 0.f;
+    for (int j = 0; j < NJ; j++) R.tgt(j) = 0.f;
 #pragma unroll 1
     for (int k = 0; k < P.actdim; k++) {
         float a = act[k];
         a = (a < -1.f) ? -1.f : a; // checkBound's comparisons: a NaN passes through (SnakeGymEnv.py:84-87)
         a = (a > 1.f) ? 1.f : a;
         const int j = (P.gait == 0) ? 2 * k : (P.gait == 1) ? 2 * k + 1 : k;
-        S.tgt[j][tid] = a * P.sf;
+        R.tgt(j) = a * P.sf;
     }
 }
 
-// counters: [0] ticks, [1] PGS sweeps, [2] dones, [3] non-finite resets, [4] next environment to hand out
-template <bool CONE>
-__global__ void __launch_bounds__(EB, 3)
-snk_exact_step_kernel(const KParams P, float* __restrict__ state, const float* __restrict__ actions, float* __restrict__ obs,
-                      float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks, unsigned long long* __restrict__ counters,
-                      int64_t n) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    ExSmem& S = *reinterpret_cast<ExSmem*>(smem_raw);
-    const int tid = threadIdx.x;
-    const unsigned lt_mask = (1u << tid) - 1u;
-    ExEnv e;
+// The persistent loop of one warp.  counters: [0] ticks, [1] PGS sweeps, [2] dones, [3] non-finite resets,
+// [4] next environment to hand out.
+template <bool CONE, class Rows>
+__device__ __forceinline__ void run_warp(const KParams& P, const Rows& R, float* __restrict__ state, const float* __restrict__ actions,
+                                         float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks,
+                                         unsigned long long* __restrict__ counters, int64_t n) {
+    const int lane = R.lane;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    ExEnv e; // a lane without an environment computes (masked) on record 0 in the rest pose
     e.st = state;
-    e.tid = tid;
+    e.tid = lane;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { e.pos[k] = 0.f; e.vel[k] = 0.f; e.omg[k] = 0.f; e.quat[k] = 0.f; }
+    e.quat[3] = 1.f;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) R.tgt(j) = 0.f;
     ExRun run;
+    run.xprev = 0.f; run.e2 = 0.f; run.height = 0.f; run.counter = 0; run.iters = 0; run.end_height = false; run.have_height = false;
     int64_t env = -1;
     bool have = false;
     unsigned long long c_ticks = 0, c_iters = 0;
@@ -65,69 +83,118 @@ snk_exact_step_kernel(const KParams P, float* __restrict__ state, const float* _
         const unsigned need = __ballot_sync(FULL, !have);
         if (need) {
             unsigned long long base = 0;
-            if (tid == 0) base = atomicAdd(&counters[4], (unsigned long long)__popc(need));
+            if (lane == 0) base = atomicAdd(&counters[4], (unsigned long long)__popc(need));
             base = __shfl_sync(FULL, base, 0);
             if (!have) {
                 const int64_t cand = (int64_t)base + __popc(need & lt_mask);
                 if (cand < n) {
                     env = cand; have = true;
                     e.st = state + env * SNK_STATE_STRIDE;
-                    load_targets(P, S, tid, actions + env * P.actdim);
+                    load_targets(P, R, actions + env * P.actdim);
                     ex_load_base(e);
-                    ex_step_begin(P, S, e, &run);
+                    ex_step_begin(P, R, e, &run);
                 }
             }
         }
         if (!__any_sync(FULL, have)) break;
-        if (have) {
-            if (ex_step_advance<CONE>(cT, P, S, e, &run)) {
-                ExStepOut o;
-                ex_step_end(cT, P, e, run, &o);
-                rew[env] = o.rew;
-                done[env] = (uint8_t)o.done;
-                if (ticks) ticks[env] = o.ticks;
-                float* go = obs + env * SNK_OBS_DIM; // 224 B row, 16 B aligned: 14 full-sector vector stores
+        __syncwarp();
+        if (ex_step_advance<CONE>(cT, P, R, e, have, &run)) { // every lane of the warp ticks together
+            ExStepOut o;
+            ex_step_end(cT, P, e, run, &o);
+            rew[env] = o.rew;
+            done[env] = (uint8_t)o.done;
+            if (ticks) ticks[env] = o.ticks;
+            float* go = obs + env * SNK_OBS_DIM; // 224 B row, 16 B aligned: 14 full-sector vector stores
 #pragma unroll 1
-                for (int k = 0; k < SNK_OBS_DIM; k += 4)
-                    *reinterpret_cast<float4*>(go + k) = make_float4(ex_obs_of(e, k), ex_obs_of(e, k + 1), ex_obs_of(e, k + 2), ex_obs_of(e, k + 3));
-                c_ticks += (unsigned long long)o.ticks; c_iters += (unsigned long long)o.iters; c_done += o.done; c_bad += o.bad;
-                have = false;
-            }
+            for (int k = 0; k < SNK_OBS_DIM; k += 4)
+                *reinterpret_cast<float4*>(go + k) = make_float4(ex_obs_of(e, k), ex_obs_of(e, k + 1), ex_obs_of(e, k + 2), ex_obs_of(e, k + 3));
+            c_ticks += (unsigned long long)o.ticks; c_iters += (unsigned long long)o.iters; c_done += o.done; c_bad += o.bad;
+            have = false;
         }
+        __syncwarp();
     }
-    if (counters) { // one atomic per warp and counter
+    // one atomic per warp and counter
 #pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) {
-            c_ticks += __shfl_xor_sync(FULL, c_ticks, sft); c_iters += __shfl_xor_sync(FULL, c_iters, sft);
-            c_done += __shfl_xor_sync(FULL, c_done, sft); c_bad += __shfl_xor_sync(FULL, c_bad, sft);
-        }
-        if (tid == 0) {
-            atomicAdd(&counters[0], c_ticks);
-            atomicAdd(&counters[1], c_iters);
-            if (c_done) atomicAdd(&counters[2], (unsigned long long)c_done);
-            if (c_bad) atomicAdd(&counters[3], (unsigned long long)c_bad);
-        }
+    for (int sft = 16; sft > 0; sft >>= 1) {
+        c_ticks += __shfl_xor_sync(FULL, c_ticks, sft); c_iters += __shfl_xor_sync(FULL, c_iters, sft);
+        c_done += __shfl_xor_sync(FULL, c_done, sft); c_bad += __shfl_xor_sync(FULL, c_bad, sft);
+    }
+    if (lane == 0) {
+        atomicAdd(&counters[0], c_ticks);
+        atomicAdd(&counters[1], c_iters);
+        if (c_done) atomicAdd(&counters[2], (unsigned long long)c_done);
+        if (c_bad) atomicAdd(&counters[3], (unsigned long long)c_bad);
     }
 }
 
+// 6 warps per CTA, one CTA per SM: rows of warps 0-3 in tensor memory, of warps 4-5 in shared memory
+template <bool CONE>
+__global__ void __launch_bounds__((TWARPS + SWARPS) * 32, 1)
+snk_exact_step_kernel(const KParams P, float* __restrict__ state, const float* __restrict__ actions, float* __restrict__ obs,
+                      float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks, unsigned long long* __restrict__ counters,
+                      int64_t n) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StepSmem& S = *reinterpret_cast<StepSmem*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) { // the whole tensor memory of the SM: 512 columns x 128 lanes
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S.tmem_base);
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tbase = S.tmem_base;
+    if (warp < TWARPS) {
+        RowsT R;
+        R.taddr = tbase + ((uint32_t)(32 * warp) << 16);
+        R.s = &S.t[warp];
+        R.lane = lane;
+        run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, n);
+    } else {
+        RowsS R;
+        R.s = &S.s[warp - TWARPS];
+        R.lane = lane;
+        run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, n);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
+}
+
+// the same loop with every warp's rows in shared memory: one warp per CTA, 3 CTAs per SM
+// (SNK_EXACT_ROWS=smem; kept for the ablation in DESIGN.md section 6)
+template <bool CONE>
+__global__ void __launch_bounds__(EB, 3)
+snk_exact_step_kernel_smem(const KParams P, float* __restrict__ state, const float* __restrict__ actions, float* __restrict__ obs,
+                           float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks,
+                           unsigned long long* __restrict__ counters, int64_t n) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RowsS R;
+    R.s = reinterpret_cast<RowsSmemStore*>(smem_raw);
+    R.lane = threadIdx.x;
+    run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, n);
+}
+
 // n_ticks raw ticks with explicit targets[N,16] (gait script): every environment runs the same number of
-// ticks, so the assignment is static (thread = environment)
+// ticks, so the assignment is static (thread = environment); rows in shared memory
 template <bool CONE>
 __global__ void __launch_bounds__(EB, 3)
 snk_exact_tick_kernel(const KParams P, float* __restrict__ state, const float* __restrict__ targets, unsigned long long* __restrict__ counters,
                       int64_t n, int n_ticks) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ExSmem& S = *reinterpret_cast<ExSmem*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int64_t env = (int64_t)blockIdx.x * EB + tid;
-    if (env >= n) return;
+    RowsS R;
+    R.s = reinterpret_cast<RowsSmemStore*>(smem_raw);
+    R.lane = threadIdx.x;
+    const int64_t env = (int64_t)blockIdx.x * EB + threadIdx.x;
+    const bool live = env < n;
     ExEnv e;
-    e.st = state + env * SNK_STATE_STRIDE;
-    e.tid = tid;
+    e.st = state + (live ? env : 0) * SNK_STATE_STRIDE;
+    e.tid = threadIdx.x;
 #pragma unroll
     for (int j = 0; j < NJ; j += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(targets + env * NJ + j);
-        S.tgt[j][tid] = t.x; S.tgt[j + 1][tid] = t.y; S.tgt[j + 2][tid] = t.z; S.tgt[j + 3][tid] = t.w;
+        const float4 t = live ? *reinterpret_cast<const float4*>(targets + env * NJ + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        R.tgt(j) = t.x; R.tgt(j + 1) = t.y; R.tgt(j + 2) = t.z; R.tgt(j + 3) = t.w;
     }
     ex_load_base(e);
     int iters = 0;
@@ -135,51 +202,69 @@ snk_exact_tick_kernel(const KParams P, float* __restrict__ state, const float* _
     for (int t = 0; t < n_ticks; t++) {
         bool ab;
         ExTickOut to;
-        ex_tick<CONE>(cT, P, S, e, false, &ab, &to);
+        ex_tick<CONE>(cT, P, R, e, live, false, &ab, &to);
         iters += to.iterations;
     }
-    ex_store_base(e);
-    if (counters) {
-        atomicAdd(&counters[0], (unsigned long long)n_ticks);
-        atomicAdd(&counters[1], (unsigned long long)iters);
+    if (live) {
+        ex_store_base(e);
+        if (counters) {
+            atomicAdd(&counters[0], (unsigned long long)n_ticks);
+            atomicAdd(&counters[1], (unsigned long long)iters);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // launch wrappers used by the C-ABI host code (snake_abi.cu)
 // ---------------------------------------------------------------------------------------------
-size_t snk_exact_smem_bytes() { return sizeof(ExSmem); }
+static int g_sms = 0, g_smem_ctas = 0;
+static bool g_rows_tmem = true; // SNK_EXACT_ROWS=smem selects the shared-memory-only variant
 
-static int g_step_ctas = 0; // persistent grid of the step kernel: CTAs per SM (occupancy) x SMs
+size_t snk_exact_smem_bytes() { return g_rows_tmem ? sizeof(StepSmem) : sizeof(RowsSmemStore); }
+
+const char* snk_exact_variant() { return g_rows_tmem ? "rows in TMEM (4 warps) + shared memory (2 warps), 192 envs/SM" : "rows in shared memory, 3 x 32 envs/SM"; }
 
 cudaError_t snk_exact_configure(const ExTables* host_tables) {
+    const char* v = getenv("SNK_EXACT_ROWS");
+    g_rows_tmem = !(v && v[0] == 's');
     cudaError_t e = cudaMemcpyToSymbol(cT, host_tables, sizeof(ExTables));
-    const void* kernels[4] = {(const void*)snk_exact_step_kernel<true>, (const void*)snk_exact_step_kernel<false>,
-                              (const void*)snk_exact_tick_kernel<true>, (const void*)snk_exact_tick_kernel<false>};
+    const void* k1[4] = {(const void*)snk_exact_step_kernel_smem<true>, (const void*)snk_exact_step_kernel_smem<false>,
+                         (const void*)snk_exact_tick_kernel<true>, (const void*)snk_exact_tick_kernel<false>};
     for (int i = 0; i < 4 && e == cudaSuccess; i++)
-        e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExSmem));
+        e = cudaFuncSetAttribute(k1[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowsSmemStore));
+    const void* k2[2] = {(const void*)snk_exact_step_kernel<true>, (const void*)snk_exact_step_kernel<false>};
+    for (int i = 0; i < 2 && e == cudaSuccess; i++)
+        e = cudaFuncSetAttribute(k2[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
     if (e != cudaSuccess) return e;
-    int dev = 0, sms = 0, per_sm = 0;
+    int dev = 0, per_sm = 0;
     e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, snk_exact_step_kernel<true>, EB, sizeof(ExSmem));
-    if (e == cudaSuccess) g_step_ctas = sms * (per_sm > 0 ? per_sm : 1);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, snk_exact_step_kernel_smem<true>, EB, sizeof(RowsSmemStore));
+    if (e == cudaSuccess) g_smem_ctas = g_sms * (per_sm > 0 ? per_sm : 1);
     return e;
 }
 
 cudaError_t snk_exact_launch_step(const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
                                   int32_t* ticks, unsigned long long* counters, int64_t n, cudaStream_t st) {
-    const int64_t warps = (n + EB - 1) / EB;
-    dim3 grid((unsigned)(warps < g_step_ctas ? warps : g_step_ctas)), block(EB);
-    if (P.cone) snk_exact_step_kernel<true><<<grid, block, sizeof(ExSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, n);
-    else snk_exact_step_kernel<false><<<grid, block, sizeof(ExSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, n);
+    if (g_rows_tmem) {
+        const int per_cta = (TWARPS + SWARPS) * 32;
+        const int64_t want = (n + per_cta - 1) / per_cta;
+        dim3 grid((unsigned)(want < g_sms ? want : g_sms)), block(per_cta);
+        if (P.cone) snk_exact_step_kernel<true><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, n);
+        else snk_exact_step_kernel<false><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, n);
+    } else {
+        const int64_t warps = (n + EB - 1) / EB;
+        dim3 grid((unsigned)(warps < g_smem_ctas ? warps : g_smem_ctas)), block(EB);
+        if (P.cone) snk_exact_step_kernel_smem<true><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, actions, obs, rew, done, ticks, counters, n);
+        else snk_exact_step_kernel_smem<false><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, actions, obs, rew, done, ticks, counters, n);
+    }
     return cudaGetLastError();
 }
 
 cudaError_t snk_exact_launch_tick(const KParams& P, float* state, const float* targets, unsigned long long* counters, int64_t n,
                                   int n_ticks, cudaStream_t st) {
     dim3 grid((unsigned)((n + EB - 1) / EB)), block(EB);
-    if (P.cone) snk_exact_tick_kernel<true><<<grid, block, sizeof(ExSmem), st>>>(P, state, targets, counters, n, n_ticks);
-    else snk_exact_tick_kernel<false><<<grid, block, sizeof(ExSmem), st>>>(P, state, targets, counters, n, n_ticks);
+    if (P.cone) snk_exact_tick_kernel<true><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, targets, counters, n, n_ticks);
+    else snk_exact_tick_kernel<false><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, targets, counters, n, n_ticks);
     return cudaGetLastError();
 }

@@ -55,17 +55,98 @@ struct ExTables {
     int cstart[NB + 1]; // cylinders of body b are [cstart[b], cstart[b+1])
 };
 
-// Shared-memory record of one CTA: contact rows as [contact][thread] columns.
-struct ExSmem {
-    float4 A[NC][EB];  // rx, ry (lever arm about C), rhs_n * invD_n, invD_n
-    float4 B[NC][EB];  // rz, d1x, d1y, d1z
-    float4 C[NC][EB];  // d2x, d2y, d2z, rhs_1 * invD_1
-    float4 L[NC][EB];  // friction impulses (2), rhs_2 * invD_2, normal impulse
-    float2 E[NC][EB];  // invD_1, invD_2
-    float tgt[NJ][EB]; // joint targets of this env-step
+// -----------------------------------------------------------------------------------------------
+// Contact-row storage.  One record of 18 words per contact and environment:
+//   word  0      normal impulse                      (solver state)
+//   words 1-3    lever arm r about the chain's centre of mass
+//   words 4-9    friction directions d1, d2 (anisotropic, not normalised)
+//   words 10-11  rhs_1 invD_1, rhs_2 invD_2
+//   words 12-13  invD_1, invD_2
+//   words 14-15  friction impulses                   (solver state)
+//   N2           rhs_n invD_n, invD_n                (only the normal sweep reads these)
+// Words 0-15 live either in shared memory as [word/4][contact][lane] float4 columns (bank = lane) or in
+// TENSOR MEMORY: TMEM lane = thread, column = 16 * contact + word, moved with tcgen05.ld/st 32x32b
+// (sm_100a; the 512 columns of a warp's TMEM quadrant hold exactly 32 contacts x 16 words).  N2 and
+// the joint targets are always in shared memory.
+// -----------------------------------------------------------------------------------------------
+struct RowsSmemStore {  // one warp, rows in shared memory: 75 776 B
+    float4 X[4][NC][EB];
+    float2 N2[NC][EB];
+    float tgt[NJ][EB];
 };
-// a contact farther than its breaking threshold keeps an all-zero record: every update it produces is
-// exactly zero, so the solver loops need no per-contact branch
+struct RowsTmemAux {    // one warp, rows in tensor memory: 10 240 B of shared memory
+    float2 N2[NC][EB];
+    float tgt[NJ][EB];
+};
+typedef RowsSmemStore ExSmem;
+
+struct RowsS {
+    RowsSmemStore* s;
+    int lane;
+    SNK_HD float& tgt(int j) const { return s->tgt[j][lane]; }
+    SNK_HD void st_n2(int k, float a, float b) const { s->N2[k][lane] = make_float2(a, b); }
+    SNK_HD void st16(int k, float4 x0, float4 x1, float4 x2, float4 x3) const {
+        s->X[0][k][lane] = x0; s->X[1][k][lane] = x1; s->X[2][k][lane] = x2; s->X[3][k][lane] = x3;
+    }
+    SNK_HD void st12(int k, float4 x0, float4 x1, float4 x2) const { s->X[0][k][lane] = x0; s->X[1][k][lane] = x1; s->X[2][k][lane] = x2; }
+    SNK_HD void ld_n(int k, float4& x0, float2& n2) const { x0 = s->X[0][k][lane]; n2 = s->N2[k][lane]; }
+    SNK_HD void ld16(int k, float4& x0, float4& x1, float4& x2, float4& x3) const {
+        x0 = s->X[0][k][lane]; x1 = s->X[1][k][lane]; x2 = s->X[2][k][lane]; x3 = s->X[3][k][lane];
+    }
+    SNK_HD void st_ln(int k, float v) const { s->X[0][k][lane].x = v; }
+    SNK_HD void st_lf(int k, float a, float b) const { *reinterpret_cast<float2*>(&s->X[3][k][lane].z) = make_float2(a, b); }
+    SNK_HD void fence4(float4&) const {}
+    SNK_HD void fence16(float4&, float4&, float4&, float4&) const {}
+    SNK_HD void fence_st() const {}
+};
+
+#ifdef __CUDACC__
+// Rows in tensor memory.  Every access is a warp-wide .sync.aligned instruction: the code using this policy
+// keeps the warp converged (inactive lanes compute on their stale record and are masked at the commits).
+// Loads are asynchronous: the destination registers may only be read after fence4/fence16, which wait for
+// the load AND tie the registers so that the compiler cannot move a use above the wait.
+struct RowsT {
+    uint32_t taddr;  // TMEM address of this warp's quadrant: base + (32 * (warp % 4) << 16)
+    RowsTmemAux* s;
+    int lane;
+    __device__ __forceinline__ float& tgt(int j) const { return s->tgt[j][lane]; }
+    __device__ __forceinline__ void st_n2(int k, float a, float b) const { s->N2[k][lane] = make_float2(a, b); }
+    __device__ __forceinline__ void st4(uint32_t col, float4 v) const {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr + col), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
+    __device__ __forceinline__ void st16(int k, float4 x0, float4 x1, float4 x2, float4 x3) const {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr + 16u * k),
+                     "f"(x0.x), "f"(x0.y), "f"(x0.z), "f"(x0.w), "f"(x1.x), "f"(x1.y), "f"(x1.z), "f"(x1.w), "f"(x2.x), "f"(x2.y), "f"(x2.z), "f"(x2.w),
+                     "f"(x3.x), "f"(x3.y), "f"(x3.z), "f"(x3.w) : "memory");
+    }
+    __device__ __forceinline__ void st12(int k, float4 x0, float4 x1, float4 x2) const { st4(16u * k, x0); st4(16u * k + 4u, x1); st4(16u * k + 8u, x2); }
+    __device__ __forceinline__ void ld_n(int k, float4& x0, float2& n2) const {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(x0.x), "=f"(x0.y), "=f"(x0.z), "=f"(x0.w) : "r"(taddr + 16u * k) : "memory");
+        n2 = s->N2[k][lane];
+    }
+    __device__ __forceinline__ void ld16(int k, float4& x0, float4& x1, float4& x2, float4& x3) const {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=f"(x0.x), "=f"(x0.y), "=f"(x0.z), "=f"(x0.w), "=f"(x1.x), "=f"(x1.y), "=f"(x1.z), "=f"(x1.w), "=f"(x2.x), "=f"(x2.y), "=f"(x2.z),
+                       "=f"(x2.w), "=f"(x3.x), "=f"(x3.y), "=f"(x3.z), "=f"(x3.w)
+                     : "r"(taddr + 16u * k) : "memory");
+    }
+    __device__ __forceinline__ void st_ln(int k, float v) const {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr + 16u * k), "f"(v) : "memory");
+    }
+    __device__ __forceinline__ void st_lf(int k, float a, float b) const {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr + 16u * k + 14u), "f"(a), "f"(b) : "memory");
+    }
+    __device__ __forceinline__ void fence4(float4& x0) const {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(x0.x), "+f"(x0.y), "+f"(x0.z), "+f"(x0.w)::"memory");
+    }
+    __device__ __forceinline__ void fence16(float4& x0, float4& x1, float4& x2, float4& x3) const {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+f"(x0.x), "+f"(x0.y), "+f"(x0.z), "+f"(x0.w), "+f"(x1.x), "+f"(x1.y), "+f"(x1.z), "+f"(x1.w), "+f"(x2.x), "+f"(x2.y), "+f"(x2.z),
+                       "+f"(x2.w), "+f"(x3.x), "+f"(x3.y), "+f"(x3.z), "+f"(x3.w)::"memory");
+    }
+    __device__ __forceinline__ void fence_st() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+};
+#endif
 
 // ---- small float3 helpers -------------------------------------------------------------------
 struct V3 { float x, y, z; };
@@ -120,6 +201,14 @@ SNK_HD float ex_rsqrt_fast(float x) {
     return y;
 #else
     return 1.0f / sqrtf(x);
+#endif
+}
+// true when the predicate holds in every lane of the warp (the host emulation runs one environment at a time)
+SNK_HD bool ex_all(bool p) {
+#ifdef __CUDA_ARCH__
+    return __all_sync(0xffffffffu, p);
+#else
+    return p;
 #endif
 }
 SNK_HD int ex_popc(unsigned x) {
@@ -216,12 +305,13 @@ struct ExTickOut { int iterations; int contacts; float height; float err2_next; 
 
 // -----------------------------------------------------------------------------------------------
 // One physics tick.  Returns the mean checkSnakeHeight z of the state at the START of the tick in
-// out->height; when `probe_only` is set (or when that height already exceeds the threshold and
-// `abort_on_height`), nothing is modified and *aborted = true.
+// out->height; when that height already exceeds the threshold and `abort_on_height` is set, nothing is
+// modified and *aborted = true.  The function is WARP CONVERGENT: every lane executes every row-storage
+// access; a lane with `active` false (no environment, or one that needs no tick) and an aborted lane run
+// the arithmetic on whatever their registers hold and are masked at every commit.
 // -----------------------------------------------------------------------------------------------
-template <bool CONE>
-SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bool abort_on_height, bool* aborted, ExTickOut* out) {
-    const int tid = e.tid;
+template <bool CONE, class Rows>
+SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e, bool active, bool abort_on_height, bool* aborted, ExTickOut* out) {
     const float dt = P.dt, inv_dt = P.inv_dt;
     const float p0z = e.pos[2];
     // ------------------------------------------------------------------ pass 1: tip-ward
@@ -240,7 +330,7 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bo
     for (int i = 0; i < NB; i++) {
         if (i > 0) {
             const int j = i - 1;
-            const float q = qn, qd = qdn, tg = S.tgt[j][tid];
+            const float q = qn, qd = qdn, tg = R.tgt(j);
             if (i < NJ) { qn = slot(e, SNK_S_Q + i); qdn = slot(e, SNK_S_QD + i); }
             float qds = P.kp * (tg - q) * inv_dt;
             qds = ex_clamp(qds, P.maxvel);
@@ -288,8 +378,7 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bo
             const float inv = ex_rsqrt(fmaxf(1.f - az * az, 1e-12f));
             V3 pc = ce + mk(az * axw.x * inv, az * axw.y * inv, (az * az - 1.f) * inv) * T.crad[k];
             const float dist = pc.z + p0z - T.cmar[k];
-            if (!(dist < T.cbrk[k])) continue;
-            act |= 1u << k;
+            act |= (dist < T.cbrk[k]) ? (1u << k) : 0u; // a separated contact gets an all-zero record below
             pc.z = dist - p0z; // contact point at height `dist` (world), relative to the base origin
             M3 cf, Rl;
 #pragma unroll
@@ -300,16 +389,15 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bo
             V3 l2 = mk(Rl.m[0] * P.aniso[0], Rl.m[1] * P.aniso[1], Rl.m[2] * P.aniso[2]);
             V3 d1 = mul(Rl, l1), d2 = mul(Rl, l2);
             V3 uJ = vJ + cross(wJ, pc - c.p);
-            S.A[k][tid] = make_float4(pc.x, pc.y, uJ.x, 0.f);
-            S.B[k][tid] = make_float4(pc.z, d1.x, d1.y, d1.z);
-            S.C[k][tid] = make_float4(d2.x, d2.y, d2.z, uJ.y);
-            S.L[k][tid] = make_float4(0.f, 0.f, uJ.z, 0.f);
+            // pass-1 temporaries in the record: (uJ.x | pc), (d1 | d2.x), (d2.y d2.z | uJ.y uJ.z)
+            R.st12(k, make_float4(uJ.x, pc.x, pc.y, pc.z), make_float4(d1.x, d1.y, d1.z, d2.x), make_float4(d2.y, d2.z, uJ.y, uJ.z));
         }
     }
+    R.fence_st();
     out->height = hsum * (1.f / NB);
     out->err2_next = err2n;
-    if (abort_on_height && out->height > P.hthr) { *aborted = true; out->iterations = 0; out->contacts = 0; return; }
-    *aborted = false;
+    *aborted = abort_on_height && out->height > P.hthr;
+    const bool commit = active && !*aborted;
 
     // ------------------------------------------------------------------ free rigid motion about C
     const float invM = T.inv_mtot, M = T.mtot;
@@ -336,19 +424,16 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bo
     // (the base origin moves with this rigid field: v0' = VC - wf x hc, i.e. a0 = aC - alf x hc)
 
     // ------------------------------------------------------------------ rows
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
     for (int k = 0; k < NC; k++) {
-        if (!((act >> k) & 1u)) {
-            S.A[k][tid] = zero4; S.B[k][tid] = zero4; S.C[k][tid] = zero4; S.L[k][tid] = zero4; S.E[k][tid] = make_float2(0.f, 0.f);
-            continue;
-        }
-        float4 a = S.A[k][tid], b = S.B[k][tid], cc = S.C[k][tid];
-        const float uJz = S.L[k][tid].z;
-        const V3 uJ = mk(a.z, cc.w, uJz);
-        const float dist = b.x + p0z;
-        const V3 r = mk(a.x - hc.x, a.y - hc.y, b.x - hc.z);
-        const V3 d1 = mk(b.y, b.z, b.w), d2 = mk(cc.x, cc.y, cc.z);
+        float4 t0, t1, t2, t3;
+        R.ld16(k, t0, t1, t2, t3);
+        R.fence16(t0, t1, t2, t3);
+        const bool on = (act >> k) & 1u;
+        const V3 uJ = mk(t0.x, t2.z, t2.w);
+        const float dist = t0.w + p0z;
+        const V3 r = mk(t0.y - hc.x, t0.z - hc.y, t0.w - hc.z);
+        const V3 d1 = mk(t1.x, t1.y, t1.z), d2 = mk(t1.w, t2.x, t2.y);
         // velocity of the contact point under the free rigid motion plus the new joint rates.  The rigid
         // field is (wf, velocity VC0 at C) with VC0 chosen so that the base origin gets v0 + dt a0:
         const V3 vp = VC + cross(wf, r) + uJ;
@@ -364,62 +449,71 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bo
         const V3 r1 = cross(r, d1), r2 = cross(r, d2);
         const float D1 = dot(d1, d1) * invM + dot(r1, mul(Ji, r1)), D2 = dot(d2, d2) * invM + dot(r2, mul(Ji, r2));
         const float iD1 = 1.f / D1, iD2 = 1.f / D2;
-        S.A[k][tid] = make_float4(r.x, r.y, rhsn, iDn);
-        S.B[k][tid] = make_float4(r.z, d1.x, d1.y, d1.z);
-        S.C[k][tid] = make_float4(d2.x, d2.y, d2.z, -dot(d1, vp) * iD1);
-        S.L[k][tid] = make_float4(0.f, 0.f, -dot(d2, vp) * iD2, 0.f);
-        S.E[k][tid] = make_float2(iD1, iD2);
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        R.st16(k, on ? make_float4(0.f, r.x, r.y, r.z) : z4, on ? make_float4(d1.x, d1.y, d1.z, d2.x) : z4,
+               on ? make_float4(d2.y, d2.z, -dot(d1, vp) * iD1, -dot(d2, vp) * iD2) : z4, on ? make_float4(iD1, iD2, 0.f, 0.f) : z4);
+        R.st_n2(k, on ? rhsn : 0.f, on ? iDn : 0.f);
     }
+    R.fence_st();
 
     // ------------------------------------------------------------------ projected Gauss-Seidel
     // The only serial dependence is the 6-vector (dw, dV); everything else of a row (loads, impulse
     // store, residual) is off that chain, and the loops are branch free so that the scheduler can
     // overlap it with the chain of the neighbouring rows.  The residual rule max (d D)^2 <= thr is
-    // evaluated division free as  |d| <= sqrt(thr) invD  on every row.
+    // evaluated division free as  |d| <= sqrt(thr) invD  on every row.  A lane whose sweeps have ended
+    // (converged, or masked from the start) is `frozen`: it keeps executing the warp's loop but commits
+    // nothing, so its result is the one of the sweep at which the oracle's loop exits.
     V3 dw = mk(0.f, 0.f, 0.f), dV = mk(0.f, 0.f, 0.f);
     const float sthr = sqrtf(P.resthr), mu = P.mu;
-    int it = 0;
+    bool frozen = !commit;
+    int sweeps = 0;
 #pragma unroll 1
-    for (;; it++) {
+    for (int it = 0; it < P.iters; it++) {
+        if (ex_all(frozen)) break;
         float viol = 0.f; // max over the rows of |d| - sqrt(thr) invD (in the row's scaled units)
         {   // ---- normal rows; the record of row k+1 is fetched while row k is on the chain
-            float4 a = S.A[0][tid];
-            float ln = S.L[0][tid].w;
+            float4 nx; float2 nn;
+            R.ld_n(0, nx, nn);
 #pragma unroll 4
             for (int k = 0; k < NC; k++) {
-                const int kn = (k + 1) & (NC - 1);
-                const float4 an = S.A[kn][tid];
-                const float lnn = S.L[kn][tid].w;
-                const float p = ln + a.z;
-                float jd = fmaf(dw.x, a.y, dV.z);
-                jd = fmaf(-dw.y, a.x, jd);
-                const float sum = fmaxf(fmaf(-jd, a.w, p), 0.f);
+                R.fence4(nx);
+                const float4 x0 = nx; const float2 n2 = nn;  // (ln, rx, ry, rz), (rhs_n invD_n, invD_n)
+                R.ld_n((k + 1) & (NC - 1), nx, nn);
+                const float ln = x0.x;
+                const float p = ln + n2.x;
+                float jd = fmaf(dw.x, x0.z, dV.z);
+                jd = fmaf(-dw.y, x0.y, jd);
+                const float sum = fmaxf(fmaf(-jd, n2.y, p), 0.f);
                 const float dd = sum - ln;
-                S.L[k][tid].w = sum;
-                const float t1 = a.y * dd, t2 = -a.x * dd; // rn * dd
-                dw.x = fmaf(Ji.xx, t1, fmaf(Ji.xy, t2, dw.x));
-                dw.y = fmaf(Ji.xy, t1, fmaf(Ji.yy, t2, dw.y));
-                dw.z = fmaf(Ji.xz, t1, fmaf(Ji.yz, t2, dw.z));
-                dV.z = fmaf(dd, invM, dV.z);
-                viol = fmaxf(viol, fmaf(-sthr, a.w, fabsf(dd)));
-                a = an; ln = lnn;
+                R.st_ln(k, frozen ? ln : sum);
+                const float t1 = x0.z * dd, t2 = -x0.y * dd; // rn * dd
+                if (!frozen) {
+                    dw.x = fmaf(Ji.xx, t1, fmaf(Ji.xy, t2, dw.x));
+                    dw.y = fmaf(Ji.xy, t1, fmaf(Ji.yy, t2, dw.y));
+                    dw.z = fmaf(Ji.xz, t1, fmaf(Ji.yz, t2, dw.z));
+                    dV.z = fmaf(dd, invM, dV.z);
+                }
+                viol = fmaxf(viol, fmaf(-sthr, n2.y, fabsf(dd)));
             }
+            R.fence4(nx);
+            R.fence_st();
         }
         {   // ---- friction pairs
-            float4 a = S.A[0][tid], b = S.B[0][tid], cc = S.C[0][tid], l = S.L[0][tid];
-            float2 ee = S.E[0][tid];
+            float4 n0, n1, n2_, n3;
+            R.ld16(0, n0, n1, n2_, n3);
 #pragma unroll 2
             for (int k = 0; k < NC; k++) {
-                const int kn = (k + 1) & (NC - 1);
-                const float4 an = S.A[kn][tid], bn = S.B[kn][tid], cn = S.C[kn][tid], lnx = S.L[kn][tid];
-                const float2 en = S.E[kn][tid];
-                const float pa = l.x + cc.w, pb = l.y + l.z, lim = mu * l.w;
+                R.fence16(n0, n1, n2_, n3);
+                const float4 x0 = n0, x1 = n1, x2 = n2_, x3 = n3;
+                R.ld16((k + 1) & (NC - 1), n0, n1, n2_, n3);
+                const float rx = x0.y, ry = x0.z, rz = x0.w;
+                const float pa = x3.z + x2.z, pb = x3.w + x2.w, lim = mu * x0.x;
                 // u = dV + dw x r
-                const float ux = fmaf(-dw.z, a.y, fmaf(dw.y, b.x, dV.x));
-                const float uy = fmaf(-dw.x, b.x, fmaf(dw.z, a.x, dV.y));
-                const float uz = fmaf(-dw.y, a.x, fmaf(dw.x, a.y, dV.z));
-                const float g1 = fmaf(b.w, uz, fmaf(b.z, uy, b.y * ux)), g2 = fmaf(cc.z, uz, fmaf(cc.y, uy, cc.x * ux));
-                float sa = fmaf(-g1, ee.x, pa), sb = fmaf(-g2, ee.y, pb);
+                const float ux = fmaf(-dw.z, ry, fmaf(dw.y, rz, dV.x));
+                const float uy = fmaf(-dw.x, rz, fmaf(dw.z, rx, dV.y));
+                const float uz = fmaf(-dw.y, rx, fmaf(dw.x, ry, dV.z));
+                const float g1 = fmaf(x1.z, uz, fmaf(x1.y, uy, x1.x * ux)), g2 = fmaf(x2.y, uz, fmaf(x2.x, uy, x1.w * ux));
+                float sa = fmaf(-g1, x3.x, pa), sb = fmaf(-g2, x3.y, pb);
                 if (CONE) { // implicit cone: radial projection onto the disc of radius mu * lambda_n,
                             // s <- s min(1, lim / |s|)  (0/0 and lim/0 resolve to 1 through fminf)
                     const float sc = fminf(1.f, lim * ex_rsqrt_fast(fmaf(sa, sa, sb * sb)));
@@ -428,22 +522,25 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bo
                     sa = fminf(fmaxf(sa, -lim), lim);
                     sb = fminf(fmaxf(sb, -lim), lim);
                 }
-                const float da = sa - l.x, db = sb - l.y;
-                *reinterpret_cast<float2*>(&S.L[k][tid]) = make_float2(sa, sb);
-                const float fx = fmaf(cc.x, db, b.y * da), fy = fmaf(cc.y, db, b.z * da), fz = fmaf(cc.z, db, b.w * da);
-                dV.x = fmaf(fx, invM, dV.x); dV.y = fmaf(fy, invM, dV.y); dV.z = fmaf(fz, invM, dV.z);
-                const float tx = fmaf(a.y, fz, -b.x * fy), ty = fmaf(b.x, fx, -a.x * fz), tz = fmaf(a.x, fy, -a.y * fx); // r x f
-                dw.x = fmaf(Ji.xx, tx, fmaf(Ji.xy, ty, fmaf(Ji.xz, tz, dw.x)));
-                dw.y = fmaf(Ji.xy, tx, fmaf(Ji.yy, ty, fmaf(Ji.yz, tz, dw.y)));
-                dw.z = fmaf(Ji.xz, tx, fmaf(Ji.yz, ty, fmaf(Ji.zz, tz, dw.z)));
+                const float da = sa - x3.z, db = sb - x3.w;
+                R.st_lf(k, frozen ? x3.z : sa, frozen ? x3.w : sb);
+                const float fx = fmaf(x1.w, db, x1.x * da), fy = fmaf(x2.x, db, x1.y * da), fz = fmaf(x2.y, db, x1.z * da);
+                const float tx = fmaf(ry, fz, -rz * fy), ty = fmaf(rz, fx, -rx * fz), tz = fmaf(rx, fy, -ry * fx); // r x f
+                if (!frozen) {
+                    dV.x = fmaf(fx, invM, dV.x); dV.y = fmaf(fy, invM, dV.y); dV.z = fmaf(fz, invM, dV.z);
+                    dw.x = fmaf(Ji.xx, tx, fmaf(Ji.xy, ty, fmaf(Ji.xz, tz, dw.x)));
+                    dw.y = fmaf(Ji.xy, tx, fmaf(Ji.yy, ty, fmaf(Ji.yz, tz, dw.y)));
+                    dw.z = fmaf(Ji.xz, tx, fmaf(Ji.yz, ty, fmaf(Ji.zz, tz, dw.z)));
+                }
                 // (da D1 + db D2)^2 <= thr  <=>  |da invD2 + db invD1| <= sqrt(thr) invD1 invD2
-                viol = fmaxf(viol, fmaf(-sthr * ee.x, ee.y, fabsf(fmaf(da, ee.y, db * ee.x))));
-                a = an; b = bn; cc = cn; l = lnx; ee = en;
+                viol = fmaxf(viol, fmaf(-sthr * x3.x, x3.y, fabsf(fmaf(da, x3.y, db * x3.x))));
             }
+            R.fence16(n0, n1, n2_, n3);
+            R.fence_st();
         }
-        if (viol <= 0.f || it >= P.iters - 1) break;
+        if (!frozen) { sweeps++; frozen = (viol <= 0.f); }
     }
-    out->iterations = it + 1;
+    out->iterations = sweeps;
     out->contacts = ex_popc(act);
 
     // ------------------------------------------------------------------ new base velocity
@@ -466,7 +563,7 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bo
 #pragma unroll 1
         for (int i = NB - 1; i >= 1; i--) {
             const int j = i - 1;
-            const float q = slot(e, SNK_S_Q + j), qd = slot(e, SNK_S_QD + j), tg = S.tgt[j][tid];
+            const float q = slot(e, SNK_S_Q + j), qd = slot(e, SNK_S_QD + j), tg = R.tgt(j);
             float qds = P.kp * (tg - q) * inv_dt;
             qds = ex_clamp(qds, P.maxvel);
             const float qdd = (qds - qd) * inv_dt;
@@ -482,19 +579,22 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bo
             SF = SF + F;
             SN = SN + cross(cc, F) + N;
 #pragma unroll 1
-            for (int k = T.cstart[i]; k < T.cstart[i + 1]; k++) {
-                if (!((act >> k) & 1u)) continue;
-                const float4 a = S.A[k][tid], b = S.B[k][tid], c4 = S.C[k][tid], l = S.L[k][tid];
-                V3 f = mk(b.y * l.x + c4.x * l.y, b.z * l.x + c4.y * l.y, l.w + b.w * l.x + c4.z * l.y) * inv_dt;
-                V3 r = mk(a.x + hc.x, a.y + hc.y, b.x + hc.z); // back to the base origin
+            for (int k = T.cstart[i]; k < T.cstart[i + 1]; k++) { // a separated contact has a zero record: zero force
+                float4 x0, x1, x2, x3;
+                R.ld16(k, x0, x1, x2, x3);
+                R.fence16(x0, x1, x2, x3);
+                V3 f = mk(x1.x * x3.z + x1.w * x3.w, x1.y * x3.z + x2.x * x3.w, x0.x + x1.z * x3.z + x2.y * x3.w) * inv_dt;
+                V3 r = mk(x0.y + hc.x, x0.z + hc.y, x0.w + hc.z); // back to the base origin
                 SF = SF - f;
                 SN = SN - cross(r, f);
             }
             V3 a = mul(c.R, ld3(T.jax[j]));
             const float tau = dot(a, SN - cross(c.p, SF)) + T.jdamp[j] * qd;
-            slot(e, SNK_S_TAU + j) = tau;
-            slot(e, SNK_S_QD + j) = qds;
-            slot(e, SNK_S_Q + j) = q + qds * dt;
+            if (commit) {
+                slot(e, SNK_S_TAU + j) = tau;
+                slot(e, SNK_S_QD + j) = qds;
+                slot(e, SNK_S_Q + j) = q + qds * dt;
+            }
             // step to the parent frame
             V3 wq = a * qd;
             c.w = c.w - wq;
@@ -514,8 +614,9 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bo
         const float rm = T.rootm, kl = P.kl + P.kl * nv;
         V3 f = mk(rm * P.g[0] - rm * v0.x * kl - rm * (vN.x - v0.x) * inv_dt, rm * P.g[1] - rm * v0.y * kl - rm * (vN.y - v0.y) * inv_dt,
                   rm * P.g[2] - rm * v0.z * kl - rm * (vN.z - v0.z) * inv_dt);
-        slot(e, SNK_S_FZ) = dot(mul(R0, ld3(T.fzax)), f);
+        if (commit) slot(e, SNK_S_FZ) = dot(mul(R0, ld3(T.fzax)), f);
     }
+    if (commit) {
     e.vel[0] = vN.x; e.vel[1] = vN.y; e.vel[2] = vN.z;
     e.omg[0] = wN.x; e.omg[1] = wN.y; e.omg[2] = wN.z;
     e.pos[0] += vN.x * dt; e.pos[1] += vN.y * dt; e.pos[2] += vN.z * dt;
@@ -533,6 +634,7 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, bo
         float w = cw * q[3] - ax * q[0] - ay * q[1] - az * q[2];
         const float in = ex_rsqrt(x * x + y * y + z * z + w * w);
         e.quat[0] = x * in; e.quat[1] = y * in; e.quat[2] = z * in; e.quat[3] = w * in;
+    }
     }
 }
 
@@ -587,21 +689,26 @@ SNK_HD void ex_store_base(const ExEnv& e) {
 // progress of one environment through its env-step (snake.py:274-306): kept in registers between ticks
 struct ExRun { float xprev, e2, height; int counter, iters; bool end_height, have_height; };
 
-SNK_HD void ex_step_begin(const KParams& P, const ExSmem& S, const ExEnv& e, ExRun* r) {
+template <class Rows>
+SNK_HD void ex_step_begin(const KParams& P, const Rows& R, const ExEnv& e, ExRun* r) {
     r->xprev = e.pos[0]; // self._observation[48], vec-wrapper semantics (Q8)
     float e2 = 0.f;
 #pragma unroll 1
-    for (int j = 0; j < NJ; j++) { const float d = S.tgt[j][e.tid] - slot(e, SNK_S_Q + j); e2 += d * d; }
+    for (int j = 0; j < NJ; j++) { const float d = R.tgt(j) - slot(e, SNK_S_Q + j); e2 += d * d; }
     r->e2 = e2; r->height = 0.f; r->counter = 0; r->iters = 0; r->end_height = false; r->have_height = false;
 }
 
-// at most one physics tick; returns true when the tick loop of snake.py:284-304 has ended
-template <bool CONE>
-SNK_HD bool ex_step_advance(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, ExRun* r) {
-    if (!(sqrtf(r->e2) > P.errthr)) return true; // checkFeedback (snake.py:228-235); also the zero-tick step (Q5)
+// At most one physics tick.  Warp convergent: every lane of the warp calls it; `have` says whether the lane
+// owns an environment.  Returns true (only for lanes with `have`) when the tick loop of snake.py:284-304 has
+// ended for the lane's environment.
+template <bool CONE, class Rows>
+SNK_HD bool ex_step_advance(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e, bool have, ExRun* r) {
+    const bool need = have && (sqrtf(r->e2) > P.errthr); // checkFeedback (snake.py:228-235); false: zero-tick step (Q5)
     bool aborted;
     ExTickOut to;
-    ex_tick<CONE>(T, P, S, e, r->counter > 0, &aborted, &to);
+    ex_tick<CONE>(T, P, R, e, need, r->counter > 0, &aborted, &to);
+    if (!have) return false;
+    if (!need) return true;
     if (aborted) { r->end_height = true; r->height = to.height; r->have_height = true; return true; } // the previous tick lifted the snake
     r->iters += to.iterations;
     r->counter++;
@@ -654,10 +761,10 @@ SNK_HD void ex_step_end(const ExTables& T, const KParams& P, ExEnv& e, const ExR
     o->rew = r; o->done = d ? 1 : 0; o->ticks = counter; o->iters = iters; o->bad = bad ? 1 : 0;
 }
 
-template <bool CONE>
-SNK_HD void ex_env_step(const ExTables& T, const KParams& P, ExSmem& S, ExEnv& e, ExStepOut* o) {
+template <bool CONE, class Rows>
+SNK_HD void ex_env_step(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e, ExStepOut* o) {
     ExRun run;
-    ex_step_begin(P, S, e, &run);
-    while (!ex_step_advance<CONE>(T, P, S, e, &run)) {}
+    ex_step_begin(P, R, e, &run);
+    while (!ex_step_advance<CONE>(T, P, R, e, true, &run)) {}
     ex_step_end(T, P, e, run, o);
 }

@@ -74,7 +74,8 @@ int emu_tick(Emu* h, const float* targets, int n_ticks, int32_t* iters_out, int3
         ExTickOut to = {0, 0, 0.f, 0.f};
         for (int t = 0; t < n_ticks; t++) {
             bool ab;
-            if (h->P.cone) ex_tick<true>(h->T, h->P, h->S, env, false, &ab, &to); else ex_tick<false>(h->T, h->P, h->S, env, false, &ab, &to);
+            RowsS R; R.s = &h->S; R.lane = env.tid;
+            if (h->P.cone) ex_tick<true>(h->T, h->P, R, env, true, false, &ab, &to); else ex_tick<false>(h->T, h->P, R, env, true, false, &ab, &to);
             h->counters[0]++; h->counters[1] += to.iterations;
         }
         ex_store_base(env);
@@ -90,7 +91,8 @@ int emu_step(Emu* h, const float* actions, float* obs, float* rew, uint8_t* done
         set_targets_from_actions(h, actions + e * h->P.actdim, env.tid);
         ex_load_base(env);
         ExStepOut o;
-        if (h->P.cone) ex_env_step<true>(h->T, h->P, h->S, env, &o); else ex_env_step<false>(h->T, h->P, h->S, env, &o);
+        RowsS R; R.s = &h->S; R.lane = env.tid;
+        if (h->P.cone) ex_env_step<true>(h->T, h->P, R, env, &o); else ex_env_step<false>(h->T, h->P, R, env, &o);
         for (int k = 0; k < SNK_OBS_DIM; k++) obs[e * SNK_OBS_DIM + k] = ex_obs_of(env, k);
         rew[e] = o.rew; done[e] = (uint8_t)o.done;
         if (ticks) ticks[e] = o.ticks;
