@@ -471,6 +471,11 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
     for (int it = 0; it < P.iters; it++) {
         if (ex_all(frozen)) break;
         float viol = 0.f; // max over the rows of |d| - sqrt(thr) invD (in the row's scaled units)
+        // a frozen lane applies its (discarded) impulse changes through a zero inverse inertia: dw and dV stay
+        // bit-exact without any per-row select or branch
+        const float gate = frozen ? 0.f : 1.f, iM = invM * gate;
+        S3 Jg;
+        Jg.xx = Ji.xx * gate; Jg.xy = Ji.xy * gate; Jg.xz = Ji.xz * gate; Jg.yy = Ji.yy * gate; Jg.yz = Ji.yz * gate; Jg.zz = Ji.zz * gate;
         {   // ---- normal rows; the record of row k+1 is fetched while row k is on the chain
             float4 nx; float2 nn;
             R.ld_n(0, nx, nn);
@@ -487,12 +492,10 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
                 const float dd = sum - ln;
                 R.st_ln(k, frozen ? ln : sum);
                 const float t1 = x0.z * dd, t2 = -x0.y * dd; // rn * dd
-                if (!frozen) {
-                    dw.x = fmaf(Ji.xx, t1, fmaf(Ji.xy, t2, dw.x));
-                    dw.y = fmaf(Ji.xy, t1, fmaf(Ji.yy, t2, dw.y));
-                    dw.z = fmaf(Ji.xz, t1, fmaf(Ji.yz, t2, dw.z));
-                    dV.z = fmaf(dd, invM, dV.z);
-                }
+                dw.x = fmaf(Jg.xx, t1, fmaf(Jg.xy, t2, dw.x));
+                dw.y = fmaf(Jg.xy, t1, fmaf(Jg.yy, t2, dw.y));
+                dw.z = fmaf(Jg.xz, t1, fmaf(Jg.yz, t2, dw.z));
+                dV.z = fmaf(dd, iM, dV.z);
                 viol = fmaxf(viol, fmaf(-sthr, n2.y, fabsf(dd)));
             }
             R.fence4(nx);
@@ -526,12 +529,10 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
                 R.st_lf(k, frozen ? x3.z : sa, frozen ? x3.w : sb);
                 const float fx = fmaf(x1.w, db, x1.x * da), fy = fmaf(x2.x, db, x1.y * da), fz = fmaf(x2.y, db, x1.z * da);
                 const float tx = fmaf(ry, fz, -rz * fy), ty = fmaf(rz, fx, -rx * fz), tz = fmaf(rx, fy, -ry * fx); // r x f
-                if (!frozen) {
-                    dV.x = fmaf(fx, invM, dV.x); dV.y = fmaf(fy, invM, dV.y); dV.z = fmaf(fz, invM, dV.z);
-                    dw.x = fmaf(Ji.xx, tx, fmaf(Ji.xy, ty, fmaf(Ji.xz, tz, dw.x)));
-                    dw.y = fmaf(Ji.xy, tx, fmaf(Ji.yy, ty, fmaf(Ji.yz, tz, dw.y)));
-                    dw.z = fmaf(Ji.xz, tx, fmaf(Ji.yz, ty, fmaf(Ji.zz, tz, dw.z)));
-                }
+                dV.x = fmaf(fx, iM, dV.x); dV.y = fmaf(fy, iM, dV.y); dV.z = fmaf(fz, iM, dV.z);
+                dw.x = fmaf(Jg.xx, tx, fmaf(Jg.xy, ty, fmaf(Jg.xz, tz, dw.x)));
+                dw.y = fmaf(Jg.xy, tx, fmaf(Jg.yy, ty, fmaf(Jg.yz, tz, dw.y)));
+                dw.z = fmaf(Jg.xz, tx, fmaf(Jg.yz, ty, fmaf(Jg.zz, tz, dw.z)));
                 // (da D1 + db D2)^2 <= thr  <=>  |da invD2 + db invD1| <= sqrt(thr) invD1 invD2
                 viol = fmaxf(viol, fmaf(-sthr * x3.x, x3.y, fabsf(fmaf(da, x3.y, db * x3.x))));
             }
