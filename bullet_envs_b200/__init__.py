@@ -12,6 +12,6 @@ def __getattr__(name):  # torch is imported lazily (the first import can take a 
         from . import gym_env
         return getattr(gym_env, name)
     if name == "dist":
-        from . import dist
-        return dist
+        import importlib
+        return importlib.import_module(__name__ + ".dist")
     raise AttributeError(name)

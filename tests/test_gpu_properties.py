@@ -1,0 +1,101 @@
+"""Size-independent properties of the CUDA path at BASELINE.json's sizes (no oracle needed): determinism,
+independence of an environment from its position in the batch / from the lane, warp and row storage
+(tensor memory vs shared memory) that happens to process it, shard invariance, invariants of the outputs."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (there is no CPU fallback)")
+    return torch
+
+
+def rollout(torch, n, steps, acts, perm=None):
+    from bullet_envs_b200 import SnakeVecEnv
+    env = SnakeVecEnv(num_envs=n, device=0)
+    env.reset(as_torch=True)
+    out = []
+    for t in range(steps):
+        a = acts[t] if perm is None else acts[t][perm]
+        obs, rew, done, _ = env.step(a)
+        out.append((obs.clone(), rew.clone(), done.clone(), env.last_ticks.clone()))
+    st = env.get_state().clone()
+    c = env.counters()
+    env.close()
+    return out, st, c
+
+
+def test_config2_full_size_determinism_and_invariants(torch):
+    """config 2: 4096 environments, 100 env-steps of seeded U[-1,1] actions.  Environments are handed to lanes
+    through an atomic counter, so two runs process a given environment on different lanes / warps / row
+    storage: bit-identical results show that none of that leaks into the arithmetic."""
+    n, steps = 4096, 100
+    g = torch.Generator().manual_seed(0)
+    acts = (torch.rand((steps, n, 8), generator=g) * 2 - 1).cuda()
+    r1, s1, c1 = rollout(torch, n, steps, acts)
+    r2, s2, c2 = rollout(torch, n, steps, acts)
+    for (o1, w1, d1, t1), (o2, w2, d2, t2) in zip(r1, r2):
+        assert torch.equal(o1, o2) and torch.equal(w1, w2) and torch.equal(d1, d2) and torch.equal(t1, t2)
+    assert torch.equal(s1, s2)
+    ticks = torch.stack([x[3] for x in r1]).float()
+    obs = torch.stack([x[0] for x in r1]); rew = torch.stack([x[1] for x in r1]); done = torch.stack([x[2] for x in r1])
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    assert int(ticks.max()) <= 41 and 25 < float(ticks[1:].mean()) < 33          # snake.py:303 cap; ~0.9^k error decay
+    assert (obs[..., 51:55].norm(dim=-1) - 1).abs().max() < 1e-5                    # unit base quaternion
+    assert (obs[..., :16].abs() <= np.pi / 6 + 0.06).all()                          # joints stay within target range + tolerance
+    assert (obs[..., 0:16:2].abs() < 1e-6).all()                                    # gaitSelection 1 never drives the even joints
+    post = obs[done]                                                                # done -> post-reset observation
+    assert post.shape[0] > 0 and (post[:, :32] == 0).all() and (post[:, 48:51] == 0).all() and (post[:, 54] == 1).all()
+    assert c1["nonfinite"] == 0
+
+
+def test_environment_results_do_not_depend_on_batch_position(torch):
+    n, steps = 2048, 6
+    g = torch.Generator().manual_seed(3)
+    acts = (torch.rand((steps, n, 8), generator=g) * 2 - 1).cuda()
+    perm = torch.randperm(n, generator=g).cuda()
+    r1, s1, _ = rollout(torch, n, steps, acts)
+    r2, s2, _ = rollout(torch, n, steps, acts, perm)
+    for (o1, w1, d1, t1), (o2, w2, d2, t2) in zip(r1, r2):
+        assert torch.equal(o1[perm], o2) and torch.equal(w1[perm], w2) and torch.equal(d1[perm], d2) and torch.equal(t1[perm], t2)
+
+
+def test_shards_equal_the_unsharded_batch(torch):
+    """one process per GPU shards by contiguous index range: a shard's results are those of the same
+    environments inside the full batch (W = 1 vs W = 2 bit-identical)."""
+    from bullet_envs_b200.dist import shard_range
+    n, steps = 1000, 5
+    g = torch.Generator().manual_seed(5)
+    acts = (torch.rand((steps, n, 8), generator=g) * 2 - 1).cuda()
+    full, _, _ = rollout(torch, n, steps, acts)
+    for rank in range(2):
+        lo, hi = shard_range(n, rank, 2)
+        part, _, _ = rollout(torch, hi - lo, steps, acts[:, lo:hi].contiguous())
+        for (o1, w1, d1, t1), (o2, w2, d2, t2) in zip(full, part):
+            assert torch.equal(o1[lo:hi], o2) and torch.equal(w1[lo:hi], w2) and torch.equal(d1[lo:hi], d2)
+
+
+def test_row_storage_variants_agree(torch):
+    """SNK_EXACT_ROWS=smem (every warp's rows in shared memory) must give the same bits as the default
+    (rows of 4 warps in tensor memory): run the variant in a subprocess and compare a checksum."""
+    import os, subprocess, sys
+    code = ("import torch, hashlib; from bullet_envs_b200 import SnakeVecEnv;"
+            "g=torch.Generator().manual_seed(9); a=(torch.rand((4,1536,8),generator=g)*2-1).cuda();"
+            "e=SnakeVecEnv(num_envs=1536,device=0); e.reset(as_torch=True);"
+            "h=hashlib.sha256();\n"
+            "for t in range(4):\n"
+            "    o,r,d,_=e.step(a[t]); h.update(o.cpu().numpy().tobytes()); h.update(r.cpu().numpy().tobytes())\n"
+            "print('SUM', h.hexdigest())")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sums = []
+    for rows in ("tmem", "smem"):
+        env = dict(os.environ, SNK_EXACT_ROWS=rows, PYTHONPATH=root)
+        out = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        sums.append([l for l in out.stdout.splitlines() if l.startswith("SUM")][0])
+    assert sums[0] == sums[1]

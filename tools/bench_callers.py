@@ -1,0 +1,147 @@
+#!/usr/bin/env python3
+"""Throughput of the two reference callers on top of the batched env (BASELINE.json configs[2] and [3]).
+
+    python tools/bench_callers.py ppo [--envs 65536]                 # PPO rollout collection (ppo/train.py:112-140)
+    torchrun ... tools/bench_callers.py ars [--envs-per-gpu 32768]    # ARS perturbation sweep (ars/train.py:74-116,208-219)
+
+The policies are the callers' (stock torch, out of the kernel scope; restated here because /root/reference does
+not exist on the GPU box): ActorCritic 56->256->256->{value, tanh mean, sigmoid+1e-3 std} (ppo/model.py:17-45,
+init N(0,0.1)/0.1) and the ARS linear policy a = W_i x, W_i = W + v delta_i (ars/train.py:40-41), one W_i per
+environment.  Everything stays on the device: actions are sampled there, the env kernel writes straight into the
+rollout buffers, and only the ARS return vector crosses GPUs (one all-gather per rollout)."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def ppo(args):
+    import torch
+    import torch.nn as nn
+    from bullet_envs_b200 import SnakeVecEnv
+
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+
+    class ActorCritic(nn.Module):
+        def __init__(self, ni=56, no=8, hs=(256, 256)):
+            super().__init__()
+            self.critic = nn.Sequential(nn.Linear(ni, hs[0]), nn.ReLU(), nn.Linear(hs[0], hs[1]), nn.ReLU(), nn.Linear(hs[1], 1))
+            self.actor = nn.Sequential(nn.Linear(ni, hs[0]), nn.ReLU(), nn.Linear(hs[0], hs[1]), nn.ReLU())
+            self.mu = nn.Linear(hs[1], no)
+            self.sigma = nn.Sequential(nn.Linear(hs[1], no), nn.Sigmoid())
+            for m in self.modules():
+                if isinstance(m, nn.Linear):
+                    nn.init.normal_(m.weight, mean=0.0, std=0.1); nn.init.constant_(m.bias, 0.1)
+
+        def forward(self, x):
+            h = self.actor(x)
+            return torch.distributions.Normal(torch.tanh(self.mu(h)), self.sigma(h) + 0.001), self.critic(x)
+
+    net = ActorCritic().to(dev)
+    assert sum(p.numel() for p in net.parameters()) == 165137
+    n, T = args.envs, 20  # ppo/params.py:10
+    env = SnakeVecEnv(num_envs=n, device=0)
+    obs = torch.empty((T + 1, n, 56), device=dev); act = torch.empty((T, n, 8), device=dev)
+    rew = torch.empty((T, n), device=dev); done = torch.empty((T, n), dtype=torch.uint8, device=dev)
+    logp = torch.empty((T, n, 8), device=dev); val = torch.empty((T, n, 1), device=dev)
+
+    def rollout():
+        with torch.no_grad():
+            for t in range(T):
+                dist, v = net(obs[t])
+                a = dist.sample()
+                act[t] = a; logp[t] = dist.log_prob(a); val[t] = v
+                env.step(a, out=(obs[t + 1], rew[t], done[t]))
+            obs[0] = obs[T]
+
+    obs[0] = env.reset(as_torch=True)
+    rollout()  # warm-up
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.rollouts):
+        rollout()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(json.dumps({"workload": "PPO rollout collection, ppo/train.py policy in torch", "envs": n, "num_steps": T, "rollouts": args.rollouts,
+                      "env_steps_per_s": n * T * args.rollouts / (ms * 1e-3), "ms_per_rollout": ms / args.rollouts,
+                      "mean_reward": float(rew.mean()), "done_rate": float(done.float().mean()), "n_gpus": 1}))
+
+
+def ars(args):
+    import torch
+    import torch.distributed as dist
+    from bullet_envs_b200 import SnakeVecEnv
+    from bullet_envs_b200 import dist as sd
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs_per_gpu          # = 2 x directions on this GPU: +delta and -delta
+    ndir = n // 2
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)  # Philox keyed by rank (directions are sharded)
+    delta = torch.randn((ndir, 8, 56), device=dev, generator=gen)
+    W = torch.zeros((8, 56), device=dev)
+    Wenv = torch.cat([W + 0.03 * delta, W - 0.03 * delta])       # ars/train.py:208-219, v = 0.03
+    env = SnakeVecEnv(num_envs=n, device=local)
+    T = 50                                                          # ars/train.py:87
+    obs = torch.empty((n, 56), device=dev); rew = torch.empty((n,), device=dev); done = torch.empty((n,), dtype=torch.uint8, device=dev)
+    cnt = torch.zeros((), device=dev, dtype=torch.float64); mean = torch.zeros(56, device=dev, dtype=torch.float64); m2 = torch.zeros(56, device=dev, dtype=torch.float64)
+
+    def sweep():
+        nonlocal cnt, mean, m2
+        ret = torch.zeros((n,), device=dev)
+        obs.copy_(env.reset(as_torch=True))
+        for t in range(T):
+            # running normaliser (ars/train.py:152-169), batch form of Welford
+            x = obs.double(); b = x.shape[0]
+            bm = x.mean(0); bm2 = ((x - bm) ** 2).sum(0)
+            tot = cnt + b; d = bm - mean
+            mean = mean + d * b / tot; m2 = m2 + bm2 + d * d * cnt * b / tot; cnt = tot
+            std = (m2 / cnt.clamp_min(2)).sqrt().clamp_min(1e-2)
+            xn = ((x - mean) / std).float()
+            a = torch.bmm(Wenv, xn.unsqueeze(-1)).squeeze(-1)      # one 8x56 mat-vec per environment
+            env.step(a, out=(obs, rew, done))
+            ret += rew
+        full = sd.gather_returns(ret, n * world)                    # the only cross-GPU traffic
+        stats = sd.merge_welford(cnt.clone(), mean.clone(), m2.clone())
+        return full, stats
+
+    sweep()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.rollouts):
+        full, stats = sweep()
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({"workload": "ARS perturbation sweep, linear policy per environment, all-gather of returns", "envs_total": n * world,
+                          "directions": ndir * world, "steps_per_rollout": T, "rollouts": args.rollouts, "n_gpus": world,
+                          "env_steps_per_s": n * world * T * args.rollouts / (ms * 1e-3), "ms_per_sweep": ms / args.rollouts,
+                          "returns_gathered": int(full.numel()), "mean_return": float(full.mean()), "welford_count": float(stats[0])}))
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("workload", choices=["ppo", "ars"])
+    ap.add_argument("--envs", type=int, default=65536)
+    ap.add_argument("--envs-per-gpu", type=int, default=32768)
+    ap.add_argument("--rollouts", type=int, default=3)
+    a = ap.parse_args()
+    {"ppo": ppo, "ars": ars}[a.workload](a)
