@@ -101,7 +101,9 @@ def ars(args):
         obs.copy_(env.reset(as_torch=True))
         for t in range(T):
             # running normaliser (ars/train.py:152-169), batch form of Welford
-            x = obs.double(); b = x.shape[0]
+            # the reference's exploration noise on the state, U[0,1) per element (ars/train.py:81,90): without it a
+            # zero-mean linear policy never leaves the rest pose (all observations equal their running mean)
+            x = (obs + torch.rand(obs.shape, device=dev, generator=gen)).double(); b = x.shape[0]
             bm = x.mean(0); bm2 = ((x - bm) ** 2).sum(0)
             tot = cnt + b; d = bm - mean
             mean = mean + d * b / tot; m2 = m2 + bm2 + d * d * cnt * b / tot; cnt = tot
@@ -131,7 +133,8 @@ def ars(args):
         print(json.dumps({"workload": "ARS perturbation sweep, linear policy per environment, all-gather of returns", "envs_total": n * world,
                           "directions": ndir * world, "steps_per_rollout": T, "rollouts": args.rollouts, "n_gpus": world,
                           "env_steps_per_s": n * world * T * args.rollouts / (ms * 1e-3), "ms_per_sweep": ms / args.rollouts,
-                          "returns_gathered": int(full.numel()), "mean_return": float(full.mean()), "welford_count": float(stats[0])}))
+                          "returns_gathered": int(full.numel()), "mean_return": float(full.mean()), "welford_count": float(stats[0]),
+                          "ticks_last_step_mean": float(env.last_ticks.float().mean())}))
     env.close()
     if world > 1:
         dist.destroy_process_group()
