@@ -216,6 +216,14 @@ static int ensure_staging(snk_handle* h) {
     return 0;
 }
 
+// true when `p` is page-locked host memory known to CUDA (cudaMallocHost / cudaHostRegister / torch pinned):
+// such a buffer is the DMA source/target itself and needs no staging copy
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int snk_step_host(snk_handle* h, const float* actions_host, float* obs_host, float* rew_host, uint8_t* done_host, int32_t* ticks_host) {
     if (!h || !actions_host || !obs_host || !rew_host || !done_host) return fail(SNK_E_ARG, "snk_step_host: null pointer%s");
     CU(cudaSetDevice(h->device));
@@ -223,20 +231,23 @@ int snk_step_host(snk_handle* h, const float* actions_host, float* obs_host, flo
     if (rc) return rc;
     size_t n = (size_t)h->n, na = n * h->P.actdim * sizeof(float);
     cudaStream_t st = h->hstream;
-    memcpy(h->h_act, actions_host, na);
-    CU(cudaMemcpyAsync(h->d_act, h->h_act, na, cudaMemcpyHostToDevice, st));
+    // pageable caller buffers go through the handle's pinned staging buffers; pinned ones are used directly
+    const bool pa = is_pinned(actions_host), po = is_pinned(obs_host), pr = is_pinned(rew_host), pd = is_pinned(done_host),
+               pt = ticks_host && is_pinned(ticks_host);
+    if (!pa) memcpy(h->h_act, actions_host, na);
+    CU(cudaMemcpyAsync(h->d_act, pa ? actions_host : h->h_act, na, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
     CU(launch_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_ticks, st));
     h->launches++;
-    CU(cudaMemcpyAsync(h->h_obs, h->d_obs, n * SNK_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h->h_rew, h->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h->h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
-    if (ticks_host) CU(cudaMemcpyAsync(h->h_ticks, h->d_ticks, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(po ? obs_host : h->h_obs, h->d_obs, n * SNK_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(pr ? rew_host : h->h_rew, h->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(pd ? done_host : h->h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
+    if (ticks_host) CU(cudaMemcpyAsync(pt ? ticks_host : h->h_ticks, h->d_ticks, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    memcpy(obs_host, h->h_obs, n * SNK_OBS_DIM * sizeof(float));
-    memcpy(rew_host, h->h_rew, n * sizeof(float));
-    memcpy(done_host, h->h_done, n);
-    if (ticks_host) memcpy(ticks_host, h->h_ticks, n * sizeof(int32_t));
+    if (!po) memcpy(obs_host, h->h_obs, n * SNK_OBS_DIM * sizeof(float));
+    if (!pr) memcpy(rew_host, h->h_rew, n * sizeof(float));
+    if (!pd) memcpy(done_host, h->h_done, n);
+    if (ticks_host && !pt) memcpy(ticks_host, h->h_ticks, n * sizeof(int32_t));
     return 0;
 }
 

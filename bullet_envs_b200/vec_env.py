@@ -29,11 +29,15 @@ from .urdf_model import OBS_DIM, STATE_STRIDE, NJ, build_model
 
 class SnakeVecEnv:
     def __init__(self, env_fns=None, num_envs=None, args=None, device=None, urdf_path=None, params=None,
-                 model=None, obs_dtype=np.float64):
+                 model=None, obs_dtype=np.float64, pinned_io=False):
         """``env_fns``: list of thunks as given to ``SubprocVecEnv`` (only its length is used -- the
         thunks would build PyBullet-backed envs) *or* pass ``num_envs``.  ``args``: the reference's
         argparse namespace (``ppo/params.py``) or None for the defaults.  ``device``: CUDA device
-        index / ``torch.device``."""
+        index / ``torch.device``.  ``obs_dtype``: dtype of the numpy results (the reference returns float64;
+        ``np.float32`` skips the conversion).  ``pinned_io``: the numpy path keeps persistent page-locked
+        result buffers that the library uses as DMA targets directly; the arrays returned by ``step`` /
+        ``reset`` are then views that stay valid until the next call (the reference's callers convert or
+        consume them immediately: ``ppo/train.py:114,131-136``, ``ars/train.py:99-110``)."""
         import torch
 
         if env_fns is not None and num_envs is None:
@@ -69,6 +73,12 @@ class SnakeVecEnv:
         self.observation_space = Box(-hi, hi)
         self.action_space = Box(-np.ones(self.act_dim), np.ones(self.act_dim))
         self.last_ticks = None
+        self._pin = None
+        if pinned_io:
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+            self._pin = dict(act=pin((self.num_envs, self.act_dim), torch.float32), obs=pin((self.num_envs, OBS_DIM), torch.float32),
+                             rew=pin((self.num_envs,), torch.float32), done=pin((self.num_envs,), torch.uint8),
+                             ticks=pin((self.num_envs,), torch.int32))
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -118,11 +128,16 @@ class SnakeVecEnv:
                                           self._stream()), self._lib)
             self._pending = ("torch", obs, rew, done, ticks)
         else:
-            a = np.ascontiguousarray(np.asarray(actions), np.float32).reshape(self.num_envs, self.act_dim)
-            obs = np.empty((self.num_envs, OBS_DIM), np.float32)
-            rew = np.empty(self.num_envs, np.float32)
-            done = np.empty(self.num_envs, np.uint8)
-            ticks = np.empty(self.num_envs, np.int32)
+            if self._pin is not None:
+                a = self._pin["act"]
+                a[...] = np.asarray(actions).reshape(self.num_envs, self.act_dim)
+                obs, rew, done, ticks = (self._pin[k] for k in ("obs", "rew", "done", "ticks"))
+            else:
+                a = np.ascontiguousarray(np.asarray(actions), np.float32).reshape(self.num_envs, self.act_dim)
+                obs = np.empty((self.num_envs, OBS_DIM), np.float32)
+                rew = np.empty(self.num_envs, np.float32)
+                done = np.empty(self.num_envs, np.uint8)
+                ticks = np.empty(self.num_envs, np.int32)
             p = lambda x: ctypes.c_void_p(x.ctypes.data)
             _abi.check(self._lib.snk_step_host(self._h, p(a), p(obs), p(rew), p(done), p(ticks)), self._lib)
             self._pending = ("numpy", obs, rew, done, ticks)
@@ -137,7 +152,7 @@ class SnakeVecEnv:
         self.last_ticks = ticks
         if kind == "torch":
             return obs, rew, done.bool(), self._infos
-        return obs.astype(self.obs_dtype, copy=False), rew.astype(self.obs_dtype, copy=False), done.astype(bool), self._infos
+        return obs.astype(self.obs_dtype, copy=False), rew.astype(self.obs_dtype, copy=False), done.view(np.bool_), self._infos
 
     def step(self, actions, out=None):
         self.step_async(actions, out=out)

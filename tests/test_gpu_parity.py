@@ -214,15 +214,18 @@ def test_numpy_path_equals_device_path(torch):
     n = 97
     rng = np.random.default_rng(2)
     a = rng.uniform(-1, 1, (2, n, 8)).astype(np.float32)
-    e1 = make_env(n); e2 = make_env(n)
-    e1.reset(); e2.reset()
+    e1 = make_env(n); e2 = make_env(n); e3 = make_env(n, obs_dtype=np.float32, pinned_io=True)
+    e1.reset(); e2.reset(); e3.reset()
     for t in range(2):
         o1, r1, d1, _ = e1.step(a[t])
         o2, r2, d2, _ = e2.step(torch.from_numpy(a[t]).cuda())
+        o3, r3, d3, _ = e3.step(a[t])                           # page-locked result buffers, DMA without staging
+        assert o3.dtype == np.float32 and d3.dtype == bool
+        assert np.array_equal(o3, o2.cpu().numpy()) and np.array_equal(r3, r2.cpu().numpy()) and np.array_equal(d3, d2.cpu().numpy())
         assert o1.dtype == np.float64 and d1.dtype == bool
         assert np.array_equal(o1.astype(np.float32), o2.cpu().numpy()) and np.array_equal(r1.astype(np.float32), r2.cpu().numpy())
         assert np.array_equal(d1, d2.cpu().numpy())
-    e1.close(); e2.close()
+    e1.close(); e2.close(); e3.close()
 
 
 def test_edge_cases(torch):
