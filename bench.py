@@ -228,13 +228,13 @@ def run_ours(args):
     # ---- e2e: the reference-facing call with HOST buffers (numpy in -> numpy out through snk_step_host):
     # every step copies that step's actions H2D and obs/reward/done/ticks D2H inside the timed region
     Ke = max(1, min(K, args.e2e_steps))
-    host_acts = acts[W:W + Ke].cpu().numpy()
+    host_acts = acts[W - 1:W + Ke].cpu().numpy()  # [0] = untimed warm-up action, distinct from the first timed one
 
     def e2e_leg(e):
         e.step(host_acts[0])  # allocates the staging buffers outside the timed region
         barrier()
         t0 = time.perf_counter()
-        for t in range(Ke):
+        for t in range(1, Ke + 1):
             o_h, r_h, d_h, _ = e.step(host_acts[t])
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
