@@ -132,7 +132,7 @@ template <bool CONE>
 __global__ void __launch_bounds__((TWARPS + SWARPS) * 32, 1)
 snk_exact_step_kernel(const KParams P, float* __restrict__ state, const float* __restrict__ actions, float* __restrict__ obs,
                       float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks, unsigned long long* __restrict__ counters,
-                      int64_t n) {
+                      int64_t n, int active_warps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StepSmem& S = *reinterpret_cast<StepSmem*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -145,7 +145,9 @@ snk_exact_step_kernel(const KParams P, float* __restrict__ state, const float* _
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tbase = S.tmem_base;
-    if (warp < TWARPS) {
+    if (warp >= active_warps) {
+        // ablation switch (SNK_EXACT_WARPS): this warp takes no environments
+    } else if (warp < TWARPS) {
         RowsT R;
         R.taddr = tbase + ((uint32_t)(32 * warp) << 16);
         R.s = &S.t[warp];
@@ -219,6 +221,7 @@ snk_exact_tick_kernel(const KParams P, float* __restrict__ state, const float* _
 // ---------------------------------------------------------------------------------------------
 static int g_sms = 0, g_smem_ctas = 0;
 static bool g_rows_tmem = true; // SNK_EXACT_ROWS=smem selects the shared-memory-only variant
+static int g_active_warps = TWARPS + SWARPS; // SNK_EXACT_WARPS=1..6: ablation of the number of working warps per SM
 
 size_t snk_exact_smem_bytes() { return g_rows_tmem ? sizeof(StepSmem) : sizeof(RowsSmemStore); }
 
@@ -227,6 +230,8 @@ const char* snk_exact_variant() { return g_rows_tmem ? "rows in TMEM (4 warps) +
 cudaError_t snk_exact_configure(const ExTables* host_tables) {
     const char* v = getenv("SNK_EXACT_ROWS");
     g_rows_tmem = !(v && v[0] == 's');
+    const char* w = getenv("SNK_EXACT_WARPS");
+    if (w && atoi(w) >= 1 && atoi(w) <= TWARPS + SWARPS) g_active_warps = atoi(w);
     cudaError_t e = cudaMemcpyToSymbol(cT, host_tables, sizeof(ExTables));
     const void* k1[4] = {(const void*)snk_exact_step_kernel_smem<true>, (const void*)snk_exact_step_kernel_smem<false>,
                          (const void*)snk_exact_tick_kernel<true>, (const void*)snk_exact_tick_kernel<false>};
@@ -250,8 +255,8 @@ cudaError_t snk_exact_launch_step(const KParams& P, float* state, const float* a
         const int per_cta = (TWARPS + SWARPS) * 32;
         const int64_t want = (n + per_cta - 1) / per_cta;
         dim3 grid((unsigned)(want < g_sms ? want : g_sms)), block(per_cta);
-        if (P.cone) snk_exact_step_kernel<true><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, n);
-        else snk_exact_step_kernel<false><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, n);
+        if (P.cone) snk_exact_step_kernel<true><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, n, g_active_warps);
+        else snk_exact_step_kernel<false><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, n, g_active_warps);
     } else {
         const int64_t warps = (n + EB - 1) / EB;
         dim3 grid((unsigned)(warps < g_smem_ctas ? warps : g_smem_ctas)), block(EB);
