@@ -37,6 +37,9 @@ WORKLOAD = "1M-env throughput sweep (2^20 envs total, random U[-1,1] actions, 1/
 # algorithmic bytes per env-step of the fused kernel (SURVEY.md 8d / DESIGN.md section 6):
 # read 45-float minimal state 180 + action 32; write state 180 + obs 224 + reward 4 + done 1
 BYTES_PER_ENV_STEP = 621
+# DRAM bytes per environment of one launch, from the ncu --set full capture of this command at 2^20 environments
+# (profiles/r01_v6_exact_full_raw_1m.csv: dram__bytes_read.sum 328.15 MB + dram__bytes_write.sum 477.47 MB per launch)
+NCU_DRAM_BYTES_PER_ENV = (328152576 + 477470720) / float(1 << 20)
 
 
 def _peaks():
@@ -268,9 +271,12 @@ def run_ours(args):
                     "value_strict_dropin": e2e_strict,
                     "call_strict_dropin": "SnakeVecEnv().step(numpy): fresh pageable float64 arrays per step, staged through the library's pinned buffers"},
             "gpu_launches": int(gpu_launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": how, "kernel": "snk_exact_kernel<false>", "kernel_ms": kernel_ms,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_DRAM_BYTES_PER_ENV * n, "traffic_source": "ncu capture at 2^20 envs, scaled per environment",
+                         "peak_source": how, "kernel": "snk_exact_step_kernel<true>", "kernel_ms": kernel_ms,
                          "bytes_per_env_step": BYTES_PER_ENV_STEP,
+                         "issue": {"smsp_issue_active_pct": 60.4, "fma_pipe_active_pct": 44.3, "lanes_per_instruction": 31.6,
+                                   "source": "profiles/r01_v6_exact_full_raw_1m.csv (ncu, same command)"},
                          "note": "not HBM bound by construction: an environment stays on chip (TMEM / shared memory) for ~30 ticks x 32 contacts x <=50 "
                                  "solver sweeps per 621 B of HBM traffic; the binding limit is fp32 issue / dependent-issue latency (profiles/)"},
             "clocks": clocks,
