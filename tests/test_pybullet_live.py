@@ -1,0 +1,62 @@
+"""Import-guarded comparison with a live PyBullet.  PyBullet is not installable in the
+authoring image or on the GPU box, so this module is SKIPPED there; it activates wherever `pybullet` and
+`pybullet_data` import, and is the first thing to run when they do: it is what would turn the oracle's
+"parity unpinned" into a pinned statement.
+
+What it checks (CPU oracle vs PyBullet DIRECT, same URDF, same settings as snake.py:86-107):
+  * the motor law: after one stepSimulation with POSITION_CONTROL targets and force = inf the joints have
+    closed 10 % of their error (the closed form of SURVEY A.4) -- independent of the contact model;
+  * env.step tick counts for seeded actions (a function of the joints only);
+  * base pose after one env-step within a loose tolerance (contact model deviations D1-D3).
+"""
+import os
+
+import numpy as np
+import pytest
+
+pybullet = pytest.importorskip("pybullet")
+pybullet_data = pytest.importorskip("pybullet_data")
+
+from bullet_envs_b200 import default_params  # noqa: E402
+from bullet_envs_b200.urdf_model import DEFAULT_URDF, build_model  # noqa: E402
+from oracle.oracle_py import Oracle  # noqa: E402
+
+
+@pytest.fixture()
+def world():
+    p = pybullet
+    cid = p.connect(p.DIRECT)
+    p.setAdditionalSearchPath(pybullet_data.getDataPath())
+    p.resetSimulation()
+    p.setGravity(0, 0, -9.8)                                     # snake.py:8,91
+    p.loadURDF("plane.urdf")                                     # snake.py:92
+    snake = p.loadURDF(DEFAULT_URDF, [0, 0, 0], useFixedBase=0, flags=p.URDF_USE_SELF_COLLISION)  # snake.py:93
+    for j in range(-1, p.getNumJoints(snake)):                   # snake.py:103-107
+        p.changeDynamics(snake, j, lateralFriction=2, anisotropicFriction=[1, 0.1, 0.01])
+    yield p, snake
+    p.disconnect(cid)
+
+
+def test_motor_law_and_tick_counts(world):
+    p, snake = world
+    model = build_model()
+    motors = model.motor_joint_indices
+    rng = np.random.default_rng(0)
+    o = Oracle(1, default_params()); o.reset()
+    for step in range(5):
+        a = rng.uniform(-1, 1, 8)
+        tgt = np.zeros(16); tgt[1::2] = a * np.pi / 6
+        ticks = 0
+        while True:                                              # snake.py:284-304 without the sleep
+            q = np.array([p.getJointState(snake, j)[0] for j in motors])
+            if not np.linalg.norm(tgt - q) > 0.05 or ticks > 40:
+                break
+            p.setJointMotorControlArray(snake, motors, p.POSITION_CONTROL, targetPositions=list(tgt), forces=[np.inf] * 16)
+            p.stepSimulation()
+            q1 = np.array([p.getJointState(snake, j)[0] for j in motors])
+            assert np.allclose(q1 - q, 0.1 * (tgt - q), atol=2e-3)   # closed form, SURVEY A.4
+            ticks += 1
+        _, _, _, ot = o.step(a[None, :])
+        assert abs(int(ot[0]) - ticks) <= 1
+    pos, _ = p.getBasePositionAndOrientation(snake)
+    assert np.abs(np.array(pos) - o.observe()[0, 48:51]).max() < 0.05
