@@ -21,13 +21,14 @@ cudaError_t snk_pgs_launch_tick(const DevTables* T, const KParams& P, float* sta
 // thread-per-env kernel with the motor rows eliminated (snake_exact.cu)
 cudaError_t snk_exact_configure(const ExTables* host_tables);
 cudaError_t snk_exact_launch_step(const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
-                                  int32_t* ticks, unsigned long long* counters, int64_t n, cudaStream_t st);
+                                  int32_t* ticks, unsigned long long* counters, uint8_t* bucket, int32_t* order, int64_t n, cudaStream_t st,
+                                  int* launches);
 cudaError_t snk_exact_launch_tick(const KParams& P, float* state, const float* targets, unsigned long long* counters, int64_t n,
                                   int n_ticks, cudaStream_t st);
 // reset / observe (snake_pgs.cu)
 cudaError_t snk_launch_reset(const KParams& P, float* state, const uint8_t* mask, float* obs, int64_t n, int mode, cudaStream_t st);
 
-#define NCOUNTERS 8
+#define NCOUNTERS (8 + 64) // 8 counters + 2 x 64 32-bit words of the hand-out scheduler (histogram, cursors)
 
 static thread_local char g_err[512] = "";
 
@@ -48,6 +49,8 @@ struct snk_handle {
     KParams P;
     DevTables* T;                 // device (warp-per-env kernel only)
     float* state;                 // device [n][64]
+    uint8_t* bucket;              // device [n]: predicted tick count of the coming env-step (exact kernel)
+    int32_t* order;               // device [n]: longest-first hand-out order
     unsigned long long* counters; // device [NCOUNTERS]: ticks, sweeps, dones, non-finite, work-queue head
     int64_t launches;
     // staging for the *_host entry points (allocated on first use)
@@ -62,8 +65,11 @@ struct snk_handle {
 };
 
 static cudaError_t launch_step(snk_handle* h, const float* act, float* obs, float* rew, uint8_t* done, int32_t* ticks, cudaStream_t st) {
-    if (h->exact) return snk_exact_launch_step(h->P, h->state, act, obs, rew, done, ticks, h->counters, h->n, st);
-    return snk_pgs_launch_step(h->T, h->P, h->state, act, obs, rew, done, ticks, h->counters, h->n, st);
+    int launches = 1;
+    cudaError_t e = h->exact ? snk_exact_launch_step(h->P, h->state, act, obs, rew, done, ticks, h->counters, h->bucket, h->order, h->n, st, &launches)
+                             : snk_pgs_launch_step(h->T, h->P, h->state, act, obs, rew, done, ticks, h->counters, h->n, st);
+    h->launches += launches;
+    return e;
 }
 
 extern "C" {
@@ -117,6 +123,8 @@ int snk_create(const snk_model* model, const snk_params* params, int64_t n_envs,
         if (snk_to_extables(model, &xt)) { delete h; return fail(SNK_E_ARG, "snk_create: model layout not supported by the exact motor solver%s"); }
         h->exact = true;
         err = snk_exact_configure(&xt);
+        if (err == cudaSuccess) err = cudaMalloc(&h->bucket, (size_t)n_envs);
+        if (err == cudaSuccess) err = cudaMalloc(&h->order, (size_t)n_envs * sizeof(int32_t));
     } else {
         DevTables host_tables;
         snk_to_tables(model, &host_tables);
@@ -130,7 +138,7 @@ int snk_create(const snk_model* model, const snk_params* params, int64_t n_envs,
     if (err == cudaSuccess) err = snk_launch_reset(h->P, h->state, nullptr, nullptr, h->n, 1, 0);
     if (err == cudaSuccess) err = cudaDeviceSynchronize();
     if (err != cudaSuccess) {
-        cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters);
+        cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters); cudaFree(h->bucket); cudaFree(h->order);
         delete h;
         return fail(SNK_E_CUDA, "snk_create: %s", cudaGetErrorString(err));
     }
@@ -149,7 +157,7 @@ int snk_destroy(snk_handle* h) {
         cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_ticks); cudaFree(h->d_mask);
         cudaStreamDestroy(h->hstream);
     }
-    cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters);
+    cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters); cudaFree(h->bucket); cudaFree(h->order);
     delete h;
     return 0;
 }
@@ -181,7 +189,6 @@ int snk_step(snk_handle* h, const float* actions_dev, float* obs_dev, float* rew
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
     CU(launch_step(h, actions_dev, obs_dev, rew_dev, done_dev, ticks_dev, st));
-    h->launches++;
     return 0;
 }
 
@@ -238,7 +245,6 @@ int snk_step_host(snk_handle* h, const float* actions_host, float* obs_host, flo
     CU(cudaMemcpyAsync(h->d_act, pa ? actions_host : h->h_act, na, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
     CU(launch_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_ticks, st));
-    h->launches++;
     CU(cudaMemcpyAsync(po ? obs_host : h->h_obs, h->d_obs, n * SNK_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(pr ? rew_host : h->h_rew, h->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(pd ? done_host : h->h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));

@@ -60,7 +60,7 @@ __device__ __forceinline__ void load_targets(const KParams& P, const Rows& R, co
 template <bool CONE, class Rows>
 __device__ __forceinline__ void run_warp(const KParams& P, const Rows& R, float* __restrict__ state, const float* __restrict__ actions,
                                          float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks,
-                                         unsigned long long* __restrict__ counters, int64_t n) {
+                                         unsigned long long* __restrict__ counters, const int32_t* __restrict__ order, int64_t n) {
     const int lane = R.lane;
     const unsigned lt_mask = (1u << lane) - 1u;
     ExEnv e; // a lane without an environment computes (masked) on record 0 in the rest pose
@@ -88,7 +88,7 @@ __device__ __forceinline__ void run_warp(const KParams& P, const Rows& R, float*
             if (!have) {
                 const int64_t cand = (int64_t)base + __popc(need & lt_mask);
                 if (cand < n) {
-                    env = cand; have = true;
+                    env = order ? (int64_t)order[cand] : cand; have = true; // longest-first order when the batch exceeds the lanes
                     e.st = state + env * SNK_STATE_STRIDE;
                     load_targets(P, R, actions + env * P.actdim);
                     ex_load_base(e);
@@ -132,7 +132,7 @@ template <bool CONE>
 __global__ void __launch_bounds__((TWARPS + SWARPS) * 32, 1)
 snk_exact_step_kernel(const KParams P, float* __restrict__ state, const float* __restrict__ actions, float* __restrict__ obs,
                       float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks, unsigned long long* __restrict__ counters,
-                      int64_t n, int active_warps) {
+                      const int32_t* __restrict__ order, int64_t n, int active_warps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StepSmem& S = *reinterpret_cast<StepSmem*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -152,12 +152,12 @@ snk_exact_step_kernel(const KParams P, float* __restrict__ state, const float* _
         R.taddr = tbase + ((uint32_t)(32 * warp) << 16);
         R.s = &S.t[warp];
         R.lane = lane;
-        run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, n);
+        run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, order, n);
     } else {
         RowsS R;
         R.s = &S.s[warp - TWARPS];
         R.lane = lane;
-        run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, n);
+        run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, order, n);
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
@@ -170,12 +170,12 @@ template <bool CONE>
 __global__ void __launch_bounds__(EB, 3)
 snk_exact_step_kernel_smem(const KParams P, float* __restrict__ state, const float* __restrict__ actions, float* __restrict__ obs,
                            float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks,
-                           unsigned long long* __restrict__ counters, int64_t n) {
+                           unsigned long long* __restrict__ counters, const int32_t* __restrict__ order, int64_t n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RowsS R;
     R.s = reinterpret_cast<RowsSmemStore*>(smem_raw);
     R.lane = threadIdx.x;
-    run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, n);
+    run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, order, n);
 }
 
 // n_ticks raw ticks with explicit targets[N,16] (gait script): every environment runs the same number of
@@ -217,10 +217,74 @@ snk_exact_tick_kernel(const KParams P, float* __restrict__ state, const float* _
 }
 
 // ---------------------------------------------------------------------------------------------
+// Longest-first hand-out order.  The tick count of an env-step is known before it runs: with the motor
+// rows imposed exactly the joint error shrinks by (1 - kp) per tick, so ticks = ceil(log(thr / |e|) /
+// log(1 - kp)).  When the batch is larger than the lanes of the persistent grid, environments are handed out
+// in descending predicted tick count (counting sort, 64 buckets), so the launch ends on the short jobs
+// instead of on a half-empty GPU waiting for a 30-tick straggler.  Results do not depend on the order.
+// ---------------------------------------------------------------------------------------------
+#define SCHED_BUCKETS 64
+
+__global__ void snk_exact_predict_kernel(const KParams P, const float* __restrict__ state, const float* __restrict__ actions, int64_t n,
+                                         uint8_t* __restrict__ bucket, unsigned* __restrict__ hist) {
+    __shared__ unsigned cnt[SCHED_BUCKETS];
+    if (threadIdx.x < SCHED_BUCKETS) cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env < n) {
+        float tgt[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; j++) tgt[j] = 0.f;
+        for (int k = 0; k < P.actdim; k++) {
+            float a = actions[env * P.actdim + k];
+            a = (a < -1.f) ? -1.f : a;
+            a = (a > 1.f) ? 1.f : a;
+            const int j = (P.gait == 0) ? 2 * k : (P.gait == 1) ? 2 * k + 1 : k;
+#pragma unroll
+            for (int jj = 0; jj < NJ; jj++) if (jj == j) tgt[jj] = a * P.sf;
+        }
+        const float* q = state + env * SNK_STATE_STRIDE + SNK_S_Q;
+        float e2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; j++) { const float d = tgt[j] - q[j]; e2 += d * d; }
+        const float err = sqrtf(e2);
+        int k = 0;
+        if (err > P.errthr) { // a NaN error compares false: zero ticks, as in the step itself
+            const float shrink = 1.f - P.kp;
+            k = (shrink > 0.f && shrink < 1.f) ? (int)ceilf(__logf(P.errthr / err) / __logf(shrink)) : 1;
+            k = max(1, min(k, min(P.maxticks, SCHED_BUCKETS - 1)));
+        }
+        bucket[env] = (uint8_t)k;
+        atomicAdd(&cnt[k], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < SCHED_BUCKETS && cnt[threadIdx.x]) atomicAdd(&hist[threadIdx.x], cnt[threadIdx.x]);
+}
+
+__global__ void snk_exact_order_kernel(int64_t n, const uint8_t* __restrict__ bucket, const unsigned* __restrict__ hist,
+                                       unsigned* __restrict__ cursor, int32_t* __restrict__ order) {
+    __shared__ unsigned cnt[SCHED_BUCKETS], base[SCHED_BUCKETS];
+    if (threadIdx.x < SCHED_BUCKETS) cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned b = 0, my = 0;
+    if (env < n) { b = bucket[env]; my = atomicAdd(&cnt[b], 1u); }
+    __syncthreads();
+    if (threadIdx.x < SCHED_BUCKETS) {
+        unsigned off = 0; // environments in longer buckets come first
+        for (int j = threadIdx.x + 1; j < SCHED_BUCKETS; j++) off += hist[j];
+        base[threadIdx.x] = off + (cnt[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], cnt[threadIdx.x]) : 0u);
+    }
+    __syncthreads();
+    if (env < n) order[base[b] + my] = (int32_t)env;
+}
+
+// ---------------------------------------------------------------------------------------------
 // launch wrappers used by the C-ABI host code (snake_abi.cu)
 // ---------------------------------------------------------------------------------------------
 static int g_sms = 0, g_smem_ctas = 0;
 static bool g_rows_tmem = true; // SNK_EXACT_ROWS=smem selects the shared-memory-only variant
+static bool g_no_sort = false; // SNK_EXACT_ORDER=index disables the longest-first hand-out (ablation)
 static int g_active_warps = TWARPS + SWARPS; // SNK_EXACT_WARPS=1..6: ablation of the number of working warps per SM
 
 size_t snk_exact_smem_bytes() { return g_rows_tmem ? sizeof(StepSmem) : sizeof(RowsSmemStore); }
@@ -230,6 +294,8 @@ const char* snk_exact_variant() { return g_rows_tmem ? "rows in TMEM (4 warps) +
 cudaError_t snk_exact_configure(const ExTables* host_tables) {
     const char* v = getenv("SNK_EXACT_ROWS");
     g_rows_tmem = !(v && v[0] == 's');
+    const char* so = getenv("SNK_EXACT_ORDER");
+    g_no_sort = so && so[0] == 'i';
     const char* w = getenv("SNK_EXACT_WARPS");
     if (w && atoi(w) >= 1 && atoi(w) <= TWARPS + SWARPS) g_active_warps = atoi(w);
     cudaError_t e = cudaMemcpyToSymbol(cT, host_tables, sizeof(ExTables));
@@ -249,19 +315,34 @@ cudaError_t snk_exact_configure(const ExTables* host_tables) {
     return e;
 }
 
+// sched = {bucket[n] u8, order[n] i32} owned by the handle (null: hand out in index order); hist/cursor are the
+// 2 x 64 words after the 8 counters (zeroed with them)
 cudaError_t snk_exact_launch_step(const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
-                                  int32_t* ticks, unsigned long long* counters, int64_t n, cudaStream_t st) {
+                                  int32_t* ticks, unsigned long long* counters, uint8_t* bucket, int32_t* order, int64_t n, cudaStream_t st,
+                                  int* launches) {
+    const int lanes = g_rows_tmem ? g_sms * (TWARPS + SWARPS) * 32 : g_smem_ctas * EB;
+    const int32_t* use_order = nullptr;
+    *launches = 1;
+    if (bucket && order && n > lanes && !g_no_sort) {
+        unsigned* hist = reinterpret_cast<unsigned*>(counters + 8);
+        unsigned* cursor = hist + SCHED_BUCKETS;
+        dim3 g((unsigned)((n + 255) / 256)), b(256);
+        snk_exact_predict_kernel<<<g, b, 0, st>>>(P, state, actions, n, bucket, hist);
+        snk_exact_order_kernel<<<g, b, 0, st>>>(n, bucket, hist, cursor, order);
+        use_order = order;
+        *launches = 3;
+    }
     if (g_rows_tmem) {
         const int per_cta = (TWARPS + SWARPS) * 32;
         const int64_t want = (n + per_cta - 1) / per_cta;
         dim3 grid((unsigned)(want < g_sms ? want : g_sms)), block(per_cta);
-        if (P.cone) snk_exact_step_kernel<true><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, n, g_active_warps);
-        else snk_exact_step_kernel<false><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, n, g_active_warps);
+        if (P.cone) snk_exact_step_kernel<true><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n, g_active_warps);
+        else snk_exact_step_kernel<false><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n, g_active_warps);
     } else {
         const int64_t warps = (n + EB - 1) / EB;
         dim3 grid((unsigned)(warps < g_smem_ctas ? warps : g_smem_ctas)), block(EB);
-        if (P.cone) snk_exact_step_kernel_smem<true><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, actions, obs, rew, done, ticks, counters, n);
-        else snk_exact_step_kernel_smem<false><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, actions, obs, rew, done, ticks, counters, n);
+        if (P.cone) snk_exact_step_kernel_smem<true><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n);
+        else snk_exact_step_kernel_smem<false><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n);
     }
     return cudaGetLastError();
 }
