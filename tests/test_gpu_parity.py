@@ -266,3 +266,33 @@ def test_edge_cases(torch):
     # closed handle
     with pytest.raises(RuntimeError):
         env.step(a)
+
+
+def test_single_env_facade_and_vec_surface(torch):
+    """SnakeGymEnv(robot, args)-shaped facade (SnakeGymEnv.py:4-103) and the SubprocVecEnv surface
+    (ppo/multiprocessing_env.py:31-153) that the reference's callers touch."""
+    import types
+    from bullet_envs_b200 import Snake, SnakeGymEnv, SnakeVecEnv
+    args = types.SimpleNamespace(alpha=1, beta=0.01, gamma=0.1, mode="train", gaitSelection=1, scaling_factor=6)
+    env = SnakeGymEnv(Snake(None, "snake/snake.urdf", args), args)
+    assert env.observation_space.shape == (56,) and env.action_space.shape == (8,)
+    assert env.robot.numMotors == 16 and env.alpha == 1 and env.mode == "train" and env._gaitSelection == 1
+    ob = env.reset()
+    assert ob.shape == (56,) and ob[54] == 1.0
+    a = np.array([2.0, -3.0, 0.5, 0.1, 0.0, 0.2, -0.2, 0.9])
+    ob, r, d, info = env.step(a)
+    assert a[0] == 1.0 and a[1] == -1.0                         # checkBound clips the caller's array in place
+    assert isinstance(r, float) and isinstance(d, bool) and info == {} and ob.shape == (56,)
+    assert abs(ob[1] - np.pi / 6) < 0.06 and abs(ob[3] + np.pi / 6) < 0.06   # driven (odd) joints reach the clipped targets
+    assert env.render().size == 0
+    assert env.robot.calculateEnergy(ob) == pytest.approx(float(np.sum(ob[16:32] * ob[32:48] * 0.01)))
+    env.close()
+    vec = SnakeVecEnv([None] * 16)                              # constructed from a list of env thunks, like SubprocVecEnv
+    assert len(vec) == 16 and vec.num_envs == vec.nenvs == 16
+    assert vec.observation_space.high[0] == pytest.approx(np.pi) and np.isinf(vec.observation_space.high[20]) and vec.action_space.high[0] == 1
+    s = vec.reset()
+    vec.step_async(np.zeros((16, 8))); s2, r2, d2, infos = vec.step_wait()
+    assert s.shape == s2.shape == (16, 56) and s2.dtype == np.float64 and d2.dtype == bool and len(infos) == 16
+    import torch as T
+    assert T.FloatTensor(s2).shape == (16, 56) and (1 - d2).sum() == 16        # what ppo/train.py:114,134 do with the results
+    vec.close(); vec.close()
