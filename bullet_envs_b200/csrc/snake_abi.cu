@@ -20,6 +20,7 @@ cudaError_t snk_pgs_launch_tick(const DevTables* T, const KParams& P, float* sta
                                 int n_ticks, cudaStream_t st);
 // thread-per-env kernel with the motor rows eliminated (snake_exact.cu)
 cudaError_t snk_exact_configure(const ExTables* host_tables);
+void snk_exact_release();
 cudaError_t snk_exact_launch_step(const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
                                   int32_t* ticks, unsigned long long* counters, uint8_t* bucket, int32_t* order, int64_t n, cudaStream_t st,
                                   int* launches);
@@ -121,8 +122,9 @@ int snk_create(const snk_model* model, const snk_params* params, int64_t n_envs,
     if (h->P.exact) { // thread-per-env kernel: tables in constant memory, state as [slot][env]
         ExTables xt;
         if (snk_to_extables(model, &xt)) { delete h; return fail(SNK_E_ARG, "snk_create: model layout not supported by the exact motor solver%s"); }
-        h->exact = true;
         err = snk_exact_configure(&xt);
+        if (err == cudaErrorInvalidValue) { delete h; return fail(SNK_E_ARG, "snk_create: the exact motor solver keeps one model per process; destroy the handles of the other model first%s"); }
+        h->exact = true;
         if (err == cudaSuccess) err = cudaMalloc(&h->bucket, (size_t)n_envs);
         if (err == cudaSuccess) err = cudaMalloc(&h->order, (size_t)n_envs * sizeof(int32_t));
     } else {
@@ -138,6 +140,7 @@ int snk_create(const snk_model* model, const snk_params* params, int64_t n_envs,
     if (err == cudaSuccess) err = snk_launch_reset(h->P, h->state, nullptr, nullptr, h->n, 1, 0);
     if (err == cudaSuccess) err = cudaDeviceSynchronize();
     if (err != cudaSuccess) {
+        if (h->exact) snk_exact_release();
         cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters); cudaFree(h->bucket); cudaFree(h->order);
         delete h;
         return fail(SNK_E_CUDA, "snk_create: %s", cudaGetErrorString(err));
@@ -157,6 +160,7 @@ int snk_destroy(snk_handle* h) {
         cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_ticks); cudaFree(h->d_mask);
         cudaStreamDestroy(h->hstream);
     }
+    if (h->exact) snk_exact_release();
     cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters); cudaFree(h->bucket); cudaFree(h->order);
     delete h;
     return 0;

@@ -24,6 +24,7 @@
 // ppo/multiprocessing_env.py:11-16; snake_gait_test.py:96-104 (raw ticks).
 #include <cuda_runtime.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "snake_exact_core.cuh"
 
@@ -291,7 +292,18 @@ size_t snk_exact_smem_bytes() { return g_rows_tmem ? sizeof(StepSmem) : sizeof(R
 
 const char* snk_exact_variant() { return g_rows_tmem ? "rows in TMEM (4 warps) + shared memory (2 warps), 192 envs/SM" : "rows in shared memory, 3 x 32 envs/SM"; }
 
+// The model tables live in one __constant__ symbol per device: all live handles of a process must share one
+// model.  Returns cudaErrorInvalidValue (reported by snk_create) when `host_tables` differs from the tables of
+// the handles that are alive.
+static ExTables g_tables;
+static int g_live_handles = 0;
+
+void snk_exact_release() { if (g_live_handles > 0) g_live_handles--; }
+
 cudaError_t snk_exact_configure(const ExTables* host_tables) {
+    if (g_live_handles > 0 && memcmp(&g_tables, host_tables, sizeof(ExTables)) != 0) return cudaErrorInvalidValue;
+    memcpy(&g_tables, host_tables, sizeof(ExTables));
+    g_live_handles++;
     const char* v = getenv("SNK_EXACT_ROWS");
     g_rows_tmem = !(v && v[0] == 's');
     const char* so = getenv("SNK_EXACT_ORDER");

@@ -296,3 +296,23 @@ def test_single_env_facade_and_vec_surface(torch):
     import torch as T
     assert T.FloatTensor(s2).shape == (16, 56) and (1 - d2).sum() == 16        # what ppo/train.py:114,134 do with the results
     vec.close(); vec.close()
+
+
+def test_one_model_per_process_is_enforced(torch):
+    """the thread-per-env kernel keeps the model tables in one __constant__ symbol: a second handle with a
+    DIFFERENT model must be refused while the first is alive (and accepted afterwards), never silently mixed"""
+    from bullet_envs_b200 import ImportRules, SnakeVecEnv, build_model
+    other = build_model(rules=ImportRules(unit_mass_for_missing_inertial=False))
+    e1 = make_env(8)
+    e1b = make_env(8)                                           # same model: fine
+    with pytest.raises(RuntimeError, match="one model per process"):
+        SnakeVecEnv(num_envs=8, device=0, model=other)
+    e1.close(); e1b.close()
+    e2 = SnakeVecEnv(num_envs=8, device=0, model=other)         # all handles of the first model are gone
+    o = Oracle(8, model=other)
+    a = np.full((8, 8), 0.7, np.float32)
+    e2.reset(); o.reset()
+    ob, r, d, _ = e2.step(a)
+    oo, orr, od, ot = o.step(a.astype(np.float64))
+    assert np.array_equal(np.asarray(e2.last_ticks), ot) and np.abs(ob[:, :16] - oo[:, :16]).max() < 1e-5
+    e2.close()
