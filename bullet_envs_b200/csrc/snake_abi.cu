@@ -24,6 +24,9 @@ void snk_exact_release();
 cudaError_t snk_exact_launch_step(const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
                                   int32_t* ticks, unsigned long long* counters, uint8_t* bucket, int32_t* order, int64_t n, cudaStream_t st,
                                   int* launches);
+cudaError_t snk_exact_launch_rollout(const KParams& P, float* state, const float* weights, const float* mean, const float* inv_std,
+                                     const float* noise, int n_steps, float* returns, float* trace, unsigned long long* counters, int64_t n,
+                                     cudaStream_t st);
 cudaError_t snk_exact_launch_tick(const KParams& P, float* state, const float* targets, unsigned long long* counters, int64_t n,
                                   int n_ticks, cudaStream_t st);
 // reset / observe (snake_pgs.cu)
@@ -193,6 +196,18 @@ int snk_step(snk_handle* h, const float* actions_dev, float* obs_dev, float* rew
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
     CU(launch_step(h, actions_dev, obs_dev, rew_dev, done_dev, ticks_dev, st));
+    return 0;
+}
+
+int snk_rollout_linear(snk_handle* h, const float* weights_dev, const float* mean_dev, const float* inv_std_dev, const float* noise_dev,
+                       int32_t n_steps, float* returns_dev, float* obs_trace_dev, void* stream) {
+    if (!h || !weights_dev || !returns_dev || n_steps < 1) return fail(SNK_E_ARG, "snk_rollout_linear: bad argument%s");
+    if (!h->exact) return fail(SNK_E_ARG, "snk_rollout_linear: only with the exact motor solver (motor force = inf, kd = 1)%s");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
+    CU(snk_exact_launch_rollout(h->P, h->state, weights_dev, mean_dev, inv_std_dev, noise_dev, n_steps, returns_dev, obs_trace_dev, h->counters, h->n, st));
+    h->launches++;
     return 0;
 }
 

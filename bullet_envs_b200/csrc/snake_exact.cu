@@ -128,6 +128,153 @@ __device__ __forceinline__ void run_warp(const KParams& P, const Rows& R, float*
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// n_steps env-steps per launch with a linear policy per environment (snk_rollout_linear; ARS rollouts,
+// ars/train.py:74-116).  A lane keeps its environment for the whole rollout: after every env-step it turns
+// the observation it would have returned into the next action, a = W_env ((obs + noise - mean) * inv_std),
+// so nothing but the return (and the optional observation trace) leaves the chip between steps.
+// ---------------------------------------------------------------------------------------------
+struct RolloutArgs {
+    const float* weights;  // [N, act_dim, 56]
+    const float* mean;     // [56] or null
+    const float* inv_std;  // [56] or null
+    const float* noise;    // [n_steps, N, 56] or null
+    float* returns;        // [N]
+    float* trace;          // [n_steps, N, 56] or null
+    int n_steps;
+};
+
+template <class Rows>
+__device__ __forceinline__ void policy_targets(const KParams& P, const Rows& R, const ExEnv& e, const RolloutArgs& A, int64_t env, int64_t n, int t) {
+    float x[SNK_OBS_DIM];
+    const int64_t row = ((int64_t)t * n + env) * SNK_OBS_DIM;
+#pragma unroll
+    for (int k = 0; k < SNK_OBS_DIM; k++) {
+        float v = ex_obs_of(e, k);
+        if (A.noise) v += A.noise[row + k];
+        if (A.trace) A.trace[row + k] = v;
+        x[k] = (v - (A.mean ? A.mean[k] : 0.f)) * (A.inv_std ? A.inv_std[k] : 1.f);
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; j++) R.tgt(j) = 0.f;
+#pragma unroll 1
+    for (int k = 0; k < P.actdim; k++) {
+        const float4* w = reinterpret_cast<const float4*>(A.weights + (env * P.actdim + k) * SNK_OBS_DIM); // 224 B rows: 16 B aligned
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < SNK_OBS_DIM / 4; q++) { // same summation order as the oracle (sequential over the 56 inputs)
+            const float4 wq = w[q];
+            acc = fmaf(wq.x, x[4 * q], acc); acc = fmaf(wq.y, x[4 * q + 1], acc); acc = fmaf(wq.z, x[4 * q + 2], acc); acc = fmaf(wq.w, x[4 * q + 3], acc);
+        }
+        float a = acc;
+        a = (a < -1.f) ? -1.f : a; // checkBound's comparisons (SnakeGymEnv.py:84-87)
+        a = (a > 1.f) ? 1.f : a;
+        const int j = (P.gait == 0) ? 2 * k : (P.gait == 1) ? 2 * k + 1 : k;
+        R.tgt(j) = a * P.sf;
+    }
+}
+
+template <bool CONE, class Rows>
+__device__ __forceinline__ void run_rollout_warp(const KParams& P, const Rows& R, float* __restrict__ state, const RolloutArgs A,
+                                                 unsigned long long* __restrict__ counters, int64_t n) {
+    const int lane = R.lane;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    ExEnv e;
+    e.st = state;
+    e.tid = lane;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { e.pos[k] = 0.f; e.vel[k] = 0.f; e.omg[k] = 0.f; e.quat[k] = 0.f; }
+    e.quat[3] = 1.f;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) R.tgt(j) = 0.f;
+    ExRun run;
+    run.xprev = 0.f; run.e2 = 0.f; run.height = 0.f; run.counter = 0; run.iters = 0; run.end_height = false; run.have_height = false;
+    int64_t env = -1;
+    bool have = false;
+    int t = 0;
+    float ret = 0.f;
+    unsigned long long c_ticks = 0, c_iters = 0;
+    unsigned c_done = 0, c_bad = 0;
+#pragma unroll 1
+    for (;;) {
+        const unsigned need = __ballot_sync(FULL, !have);
+        if (need) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&counters[4], (unsigned long long)__popc(need));
+            base = __shfl_sync(FULL, base, 0);
+            if (!have) {
+                const int64_t cand = (int64_t)base + __popc(need & lt_mask);
+                if (cand < n) {
+                    env = cand; have = true; t = 0; ret = 0.f;
+                    e.st = state + env * SNK_STATE_STRIDE;
+                    ex_load_base(e);
+                    policy_targets(P, R, e, A, env, n, 0);
+                    ex_step_begin(P, R, e, &run);
+                }
+            }
+        }
+        if (!__any_sync(FULL, have)) break;
+        __syncwarp();
+        if (ex_step_advance<CONE>(cT, P, R, e, have, &run)) {
+            ExStepOut o;
+            ex_step_end(cT, P, e, run, &o);
+            ret += o.rew;
+            c_ticks += (unsigned long long)o.ticks; c_iters += (unsigned long long)o.iters; c_done += o.done; c_bad += o.bad;
+            if (++t == A.n_steps) {
+                A.returns[env] = ret;
+                have = false;
+            } else {
+                policy_targets(P, R, e, A, env, n, t);
+                ex_step_begin(P, R, e, &run);
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) {
+        c_ticks += __shfl_xor_sync(FULL, c_ticks, sft); c_iters += __shfl_xor_sync(FULL, c_iters, sft);
+        c_done += __shfl_xor_sync(FULL, c_done, sft); c_bad += __shfl_xor_sync(FULL, c_bad, sft);
+    }
+    if (lane == 0) {
+        atomicAdd(&counters[0], c_ticks);
+        atomicAdd(&counters[1], c_iters);
+        if (c_done) atomicAdd(&counters[2], (unsigned long long)c_done);
+        if (c_bad) atomicAdd(&counters[3], (unsigned long long)c_bad);
+    }
+}
+
+template <bool CONE>
+__global__ void __launch_bounds__((TWARPS + SWARPS) * 32, 1)
+snk_exact_rollout_kernel(const KParams P, float* __restrict__ state, const RolloutArgs A, unsigned long long* __restrict__ counters, int64_t n) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StepSmem& S = *reinterpret_cast<StepSmem*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S.tmem_base);
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tbase = S.tmem_base;
+    if (warp < TWARPS) {
+        RowsT R;
+        R.taddr = tbase + ((uint32_t)(32 * warp) << 16);
+        R.s = &S.t[warp];
+        R.lane = lane;
+        run_rollout_warp<CONE>(P, R, state, A, counters, n);
+    } else {
+        RowsS R;
+        R.s = &S.s[warp - TWARPS];
+        R.lane = lane;
+        run_rollout_warp<CONE>(P, R, state, A, counters, n);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
+}
+
 // 6 warps per CTA, one CTA per SM: rows of warps 0-3 in tensor memory, of warps 4-5 in shared memory
 template <bool CONE>
 __global__ void __launch_bounds__((TWARPS + SWARPS) * 32, 1)
@@ -315,8 +462,9 @@ cudaError_t snk_exact_configure(const ExTables* host_tables) {
                          (const void*)snk_exact_tick_kernel<true>, (const void*)snk_exact_tick_kernel<false>};
     for (int i = 0; i < 4 && e == cudaSuccess; i++)
         e = cudaFuncSetAttribute(k1[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowsSmemStore));
-    const void* k2[2] = {(const void*)snk_exact_step_kernel<true>, (const void*)snk_exact_step_kernel<false>};
-    for (int i = 0; i < 2 && e == cudaSuccess; i++)
+    const void* k2[4] = {(const void*)snk_exact_step_kernel<true>, (const void*)snk_exact_step_kernel<false>,
+                         (const void*)snk_exact_rollout_kernel<true>, (const void*)snk_exact_rollout_kernel<false>};
+    for (int i = 0; i < 4 && e == cudaSuccess; i++)
         e = cudaFuncSetAttribute(k2[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
     if (e != cudaSuccess) return e;
     int dev = 0, per_sm = 0;
@@ -356,6 +504,19 @@ cudaError_t snk_exact_launch_step(const KParams& P, float* state, const float* a
         if (P.cone) snk_exact_step_kernel_smem<true><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n);
         else snk_exact_step_kernel_smem<false><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t snk_exact_launch_rollout(const KParams& P, float* state, const float* weights, const float* mean, const float* inv_std,
+                                     const float* noise, int n_steps, float* returns, float* trace, unsigned long long* counters, int64_t n,
+                                     cudaStream_t st) {
+    RolloutArgs A;
+    A.weights = weights; A.mean = mean; A.inv_std = inv_std; A.noise = noise; A.returns = returns; A.trace = trace; A.n_steps = n_steps;
+    const int per_cta = (TWARPS + SWARPS) * 32;
+    const int64_t want = (n + per_cta - 1) / per_cta;
+    dim3 grid((unsigned)(want < g_sms ? want : g_sms)), block(per_cta);
+    if (P.cone) snk_exact_rollout_kernel<true><<<grid, block, sizeof(StepSmem), st>>>(P, state, A, counters, n);
+    else snk_exact_rollout_kernel<false><<<grid, block, sizeof(StepSmem), st>>>(P, state, A, counters, n);
     return cudaGetLastError();
 }
 

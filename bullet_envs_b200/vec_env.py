@@ -185,6 +185,24 @@ class SnakeVecEnv:
         _abi.check(self._lib.snk_tick(self._h, self._ptr(t), int(n_ticks), self._stream()), self._lib)
         torch.cuda.current_stream(self.device).synchronize()
 
+    def rollout_linear(self, weights, n_steps, mean=None, inv_std=None, noise=None, trace=False):
+        """``n_steps`` env-steps in one launch with a linear policy per environment (ARS rollouts,
+        ``ars/train.py:74-116``): before every step ``action = W_env @ ((obs + noise[t]) - mean) * inv_std``.
+        ``weights`` [N, act_dim, 56]; ``mean`` / ``inv_std`` [56] or None; ``noise`` [n_steps, N, 56] or None.
+        Returns the per-environment sum of rewards (CUDA tensor) and, with ``trace=True``, every input the
+        policy saw [n_steps, N, 56] for the caller's running statistics."""
+        self._check_open()
+        torch = self._torch
+        dev = lambda x, shape: None if x is None else torch.as_tensor(x, dtype=torch.float32, device=self.device).contiguous().view(shape)
+        w = dev(weights, (self.num_envs, self.act_dim, OBS_DIM))
+        m, s = dev(mean, (OBS_DIM,)), dev(inv_std, (OBS_DIM,))
+        z = dev(noise, (n_steps, self.num_envs, OBS_DIM))
+        ret = torch.empty((self.num_envs,), dtype=torch.float32, device=self.device)
+        tr = torch.empty((n_steps, self.num_envs, OBS_DIM), dtype=torch.float32, device=self.device) if trace else None
+        p = lambda x: None if x is None else self._ptr(x)
+        _abi.check(self._lib.snk_rollout_linear(self._h, p(w), p(m), p(s), p(z), int(n_steps), p(ret), p(tr), self._stream()), self._lib)
+        return (ret, tr) if trace else ret
+
     def observe(self):
         torch = self._torch
         obs = torch.empty((self.num_envs, OBS_DIM), dtype=torch.float32, device=self.device)

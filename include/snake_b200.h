@@ -33,6 +33,9 @@
  *   snk_tick        <- raw setJointMotorControlArray + stepSimulation loop of the gait script
  *                      (snake_gait_test.py:96-104)
  *   snk_observe     <- Snake.getObservation (snake.py:209-217)
+ *   snk_rollout_linear <- ARS rollout with a linear policy per environment: ars/train.py:74-116 (test_envs)
+ *                      with policy() = W x (ars/train.py:40-41), normalisation (ars/train.py:152-169, statistics
+ *                      frozen for the rollout) and the state noise of ars/train.py:81,90 supplied by the caller
  *   snk_get_state / snk_set_state <- resetBasePositionAndOrientation / resetJointState
  *                      (snake.py:119-127) generalised to arbitrary states (parity harness)
  */
@@ -155,6 +158,16 @@ int snk_step(snk_handle* h, const float* actions_dev, float* obs_dev, float* rew
 int snk_step_host(snk_handle* h, const float* actions_host, float* obs_host, float* rew_host,
                   uint8_t* done_host, int32_t* ticks_host);
 int snk_reset_host(snk_handle* h, const uint8_t* mask_host, float* obs_host);
+
+/* n_steps env-steps in ONE launch with a linear policy per environment (ARS): before every
+ * step   x = obs (+ noise[t, env, :])   xn = (x - mean) * inv_std   action = W_env xn   (then clipped as in snk_step),
+ * where obs is the observation the previous step returned (the post-reset one after a done, exactly what the
+ * vector wrapper feeds back, ars/train.py:99-110).  weights_dev [N, act_dim, 56]; mean_dev / inv_std_dev [56] or
+ * NULL (identity); noise_dev [n_steps, N, 56] or NULL; returns_dev [N] receives the sum of the n_steps rewards;
+ * obs_trace_dev [n_steps, N, 56] or NULL receives every x the policy saw (for the caller's running statistics).
+ * Only with the exact motor solver (the reference configuration).  State persists as after n_steps snk_step calls. */
+int snk_rollout_linear(snk_handle* h, const float* weights_dev, const float* mean_dev, const float* inv_std_dev,
+                       const float* noise_dev, int32_t n_steps, float* returns_dev, float* obs_trace_dev, void* stream);
 
 /* Raw physics ticks with explicit joint targets [N,16] (gait script, snake_gait_test.py:96-104);
  * no task logic.  n_ticks ticks are run with the same targets. */

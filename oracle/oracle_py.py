@@ -100,6 +100,17 @@ class Oracle:
                             range(threads)))
         return obs, rew, done.astype(bool), ticks
 
+    def rollout_linear(self, weights, n_steps, mean=None, inv_std=None, noise=None, trace=False):
+        w = np.ascontiguousarray(weights, self.dtype).reshape(self.n, self.act_dim, OBS_DIM)
+        m = None if mean is None else np.ascontiguousarray(mean, self.dtype)
+        s = None if inv_std is None else np.ascontiguousarray(inv_std, self.dtype)
+        z = None if noise is None else np.ascontiguousarray(noise, self.dtype).reshape(n_steps, self.n, OBS_DIM)
+        ret = np.empty(self.n, self.dtype)
+        tr = np.empty((n_steps, self.n, OBS_DIM), self.dtype) if trace else None
+        f = self._fn("rollout_linear"); f.restype = ctypes.c_int
+        f(self._h, self._p(w), self._p(m), self._p(s), self._p(z), ctypes.c_int32(n_steps), self._p(ret), self._p(tr))
+        return (ret, tr) if trace else ret
+
     def tick(self, targets, n_ticks=1):
         t = np.ascontiguousarray(targets, self.dtype).reshape(self.n, NJ)
         iters = np.empty(self.n, np.int32)
