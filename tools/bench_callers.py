@@ -116,6 +116,24 @@ def ars(args):
         stats = sd.merge_welford(cnt.clone(), mean.clone(), m2.clone())
         return full, stats
 
+    def sweep_fused():
+        """the same sweep through snk_rollout_linear: one launch per rollout, normaliser frozen for the rollout (as
+        the parallel ARS of Mania et al. does) and updated afterwards from the observation trace"""
+        nonlocal cnt, mean, m2
+        env.reset(as_torch=True)
+        noise = torch.rand((T, n, 56), device=dev, generator=gen)
+        std = (m2 / cnt.clamp_min(2)).sqrt().clamp_min(1e-2) if float(cnt) > 0 else torch.ones(56, device=dev, dtype=torch.float64)
+        ret, trace = env.rollout_linear(Wenv, T, mean=mean.float(), inv_std=(1.0 / std).float(), noise=noise, trace=True)
+        x = trace.view(-1, 56).double(); b = x.shape[0]
+        bm = x.mean(0); bm2 = ((x - bm) ** 2).sum(0)
+        tot = cnt + b; d = bm - mean
+        mean = mean + d * b / tot; m2 = m2 + bm2 + d * d * cnt * b / tot; cnt = tot
+        full = sd.gather_returns(ret, n * world)
+        stats = sd.merge_welford(cnt.clone(), mean.clone(), m2.clone())
+        return full, stats
+
+    if args.fused:
+        sweep = sweep_fused
     sweep()
     if world > 1:
         dist.barrier()
@@ -130,11 +148,12 @@ def ars(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     if rank == 0:
-        print(json.dumps({"workload": "ARS perturbation sweep, linear policy per environment, all-gather of returns", "envs_total": n * world,
+        print(json.dumps({"workload": "ARS perturbation sweep, linear policy per environment, all-gather of returns" +
+                          (", fused rollout kernel (snk_rollout_linear)" if args.fused else ", one env.step per step + policy in torch"), "envs_total": n * world,
                           "directions": ndir * world, "steps_per_rollout": T, "rollouts": args.rollouts, "n_gpus": world,
                           "env_steps_per_s": n * world * T * args.rollouts / (ms * 1e-3), "ms_per_sweep": ms / args.rollouts,
                           "returns_gathered": int(full.numel()), "mean_return": float(full.mean()), "welford_count": float(stats[0]),
-                          "ticks_last_step_mean": float(env.last_ticks.float().mean())}))
+                          "ticks_per_env_step": env.counters()["ticks"] / float(n * T) if args.fused else float(env.last_ticks.float().mean())}))
     env.close()
     if world > 1:
         dist.destroy_process_group()
@@ -146,5 +165,6 @@ if __name__ == "__main__":
     ap.add_argument("--envs", type=int, default=65536)
     ap.add_argument("--envs-per-gpu", type=int, default=32768)
     ap.add_argument("--rollouts", type=int, default=3)
+    ap.add_argument("--fused", action="store_true", help="ars: run every rollout as one snk_rollout_linear launch")
     a = ap.parse_args()
     {"ppo": ppo, "ars": ars}[a.workload](a)
