@@ -25,8 +25,8 @@ cudaError_t snk_exact_launch_step(const KParams& P, float* state, const float* a
                                   int32_t* ticks, unsigned long long* counters, uint8_t* bucket, int32_t* order, int64_t n, cudaStream_t st,
                                   int* launches);
 cudaError_t snk_exact_launch_rollout(const KParams& P, float* state, const float* weights, const float* mean, const float* inv_std,
-                                     const float* noise, int n_steps, float* returns, float* trace, unsigned long long* counters, int64_t n,
-                                     cudaStream_t st);
+                                     const float* noise, int n_steps, float* returns, float* trace, int32_t* queue, int32_t* done_steps,
+                                     unsigned long long* counters, int64_t n, cudaStream_t st);
 cudaError_t snk_exact_launch_tick(const KParams& P, float* state, const float* targets, unsigned long long* counters, int64_t n,
                                   int n_ticks, cudaStream_t st);
 // reset / observe (snake_pgs.cu)
@@ -55,6 +55,8 @@ struct snk_handle {
     float* state;                 // device [n][64]
     uint8_t* bucket;              // device [n]: predicted tick count of the coming env-step (exact kernel)
     int32_t* order;               // device [n]: longest-first hand-out order
+    int32_t* roll_queue;          // device: ready queue of snk_rollout_linear, n * (steps - 1) entries (grown on demand)
+    size_t roll_queue_len;
     unsigned long long* counters; // device [NCOUNTERS]: ticks, sweeps, dones, non-finite, work-queue head
     int64_t launches;
     // staging for the *_host entry points (allocated on first use)
@@ -164,7 +166,7 @@ int snk_destroy(snk_handle* h) {
         cudaStreamDestroy(h->hstream);
     }
     if (h->exact) snk_exact_release();
-    cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters); cudaFree(h->bucket); cudaFree(h->order);
+    cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters); cudaFree(h->bucket); cudaFree(h->order); cudaFree(h->roll_queue);
     delete h;
     return 0;
 }
@@ -205,8 +207,18 @@ int snk_rollout_linear(snk_handle* h, const float* weights_dev, const float* mea
     if (!h->exact) return fail(SNK_E_ARG, "snk_rollout_linear: only with the exact motor solver (motor force = inf, kd = 1)%s");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
+    const size_t qlen = (size_t)h->n * (size_t)(n_steps > 1 ? n_steps - 1 : 1);
+    if (qlen > h->roll_queue_len) { // grow the ready queue (first call, or a longer rollout than before)
+        CU(cudaStreamSynchronize(st));
+        cudaFree(h->roll_queue); h->roll_queue = nullptr; h->roll_queue_len = 0;
+        CU(cudaMalloc(&h->roll_queue, qlen * sizeof(int32_t)));
+        h->roll_queue_len = qlen;
+    }
     CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
-    CU(snk_exact_launch_rollout(h->P, h->state, weights_dev, mean_dev, inv_std_dev, noise_dev, n_steps, returns_dev, obs_trace_dev, h->counters, h->n, st));
+    CU(cudaMemsetAsync(h->roll_queue, 0xff, qlen * sizeof(int32_t), st));        // -1: not pushed yet
+    CU(cudaMemsetAsync(h->order, 0, (size_t)h->n * sizeof(int32_t), st));          // env-steps done (the step kernel's order[] is rebuilt per step)
+    CU(snk_exact_launch_rollout(h->P, h->state, weights_dev, mean_dev, inv_std_dev, noise_dev, n_steps, returns_dev, obs_trace_dev, h->roll_queue,
+                                h->order, h->counters, h->n, st));
     h->launches++;
     return 0;
 }

@@ -142,6 +142,8 @@ struct RolloutArgs {
     float* returns;        // [N]
     float* trace;          // [n_steps, N, 56] or null
     int n_steps;
+    int32_t* queue;        // [N * (n_steps - 1)] ready queue, -1 = not pushed yet (handle owned)
+    int32_t* done_steps;   // [N] env-steps finished so far in this rollout (handle owned, zeroed per call)
 };
 
 template <class Rows>
@@ -174,11 +176,21 @@ __device__ __forceinline__ void policy_targets(const KParams& P, const Rows& R, 
     }
 }
 
+// Work distribution of the rollout.  The unit handed to a lane is ONE env-step of one environment; an
+// environment whose step has finished (and that has steps left) is pushed onto a ready queue in global memory
+// and taken by whichever lane frees up next, so the lanes stay busy for any ratio of environments to lanes
+// (a lane that kept its environment for the whole rollout would leave the last partial wave of rollouts on a
+// mostly idle GPU).  Tickets: ticket k < N is environment k's first step; ticket k >= N is the (k - N)-th push.
+// A lane holding a ticket whose queue slot is still empty polls it once per loop iteration -- it never blocks
+// the warp.  Ordering: the pushing lane fences its state-record stores before the push; the popping lane
+// fences (which also invalidates its SM's L1) after seeing the entry and before loading the record.
+// counters: [4] tickets handed out, [5] pushes done.
 template <bool CONE, class Rows>
 __device__ __forceinline__ void run_rollout_warp(const KParams& P, const Rows& R, float* __restrict__ state, const RolloutArgs A,
                                                  unsigned long long* __restrict__ counters, int64_t n) {
     const int lane = R.lane;
     const unsigned lt_mask = (1u << lane) - 1u;
+    const long long total = (long long)n * A.n_steps;
     ExEnv e;
     e.st = state;
     e.tid = lane;
@@ -190,43 +202,57 @@ __device__ __forceinline__ void run_rollout_warp(const KParams& P, const Rows& R
     ExRun run;
     run.xprev = 0.f; run.e2 = 0.f; run.height = 0.f; run.counter = 0; run.iters = 0; run.end_height = false; run.have_height = false;
     int64_t env = -1;
-    bool have = false;
+    long long ticket = -1;    // >= 0: waiting for that ticket's environment
+    bool have = false, exhausted = false;
     int t = 0;
-    float ret = 0.f;
     unsigned long long c_ticks = 0, c_iters = 0;
     unsigned c_done = 0, c_bad = 0;
 #pragma unroll 1
     for (;;) {
-        const unsigned need = __ballot_sync(FULL, !have);
+        // ---- idle lanes draw tickets
+        const unsigned need = __ballot_sync(FULL, !have && ticket < 0 && !exhausted);
         if (need) {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(&counters[4], (unsigned long long)__popc(need));
             base = __shfl_sync(FULL, base, 0);
-            if (!have) {
-                const int64_t cand = (int64_t)base + __popc(need & lt_mask);
-                if (cand < n) {
-                    env = cand; have = true; t = 0; ret = 0.f;
-                    e.st = state + env * SNK_STATE_STRIDE;
-                    ex_load_base(e);
-                    policy_targets(P, R, e, A, env, n, 0);
-                    ex_step_begin(P, R, e, &run);
-                }
+            if (!have && ticket < 0 && !exhausted) {
+                const long long k = (long long)base + __popc(need & lt_mask);
+                if (k < total) ticket = k; else exhausted = true;
             }
         }
-        if (!__any_sync(FULL, have)) break;
+        // ---- lanes with a ticket look whether its environment is ready
+        if (ticket >= 0) {
+            long long cand = -1;
+            if (ticket < n) cand = ticket;
+            else cand = *reinterpret_cast<volatile int32_t*>(A.queue + (ticket - n));
+            if (cand >= 0) {
+                __threadfence(); // acquire: the previous owner's stores to the record, returns[] and done_steps[]
+                env = cand; have = true; ticket = -1;
+                e.st = state + env * SNK_STATE_STRIDE;
+                t = A.done_steps[env];
+                ex_load_base(e);
+                policy_targets(P, R, e, A, env, n, t);
+                ex_step_begin(P, R, e, &run);
+            }
+        }
+        if (!__any_sync(FULL, have)) {
+            if (__all_sync(FULL, exhausted && ticket < 0)) break;
+            __nanosleep(500); // every lane of this warp waits for a push
+            continue;
+        }
         __syncwarp();
         if (ex_step_advance<CONE>(cT, P, R, e, have, &run)) {
             ExStepOut o;
             ex_step_end(cT, P, e, run, &o);
-            ret += o.rew;
+            A.returns[env] = (t == 0) ? o.rew : A.returns[env] + o.rew;
             c_ticks += (unsigned long long)o.ticks; c_iters += (unsigned long long)o.iters; c_done += o.done; c_bad += o.bad;
-            if (++t == A.n_steps) {
-                A.returns[env] = ret;
-                have = false;
-            } else {
-                policy_targets(P, R, e, A, env, n, t);
-                ex_step_begin(P, R, e, &run);
+            A.done_steps[env] = t + 1;
+            if (t + 1 < A.n_steps) {
+                __threadfence(); // release the record before the environment becomes visible to other lanes
+                const unsigned long long p = atomicAdd(&counters[5], 1ull);
+                *reinterpret_cast<volatile int32_t*>(A.queue + p) = (int32_t)env;
             }
+            have = false;
         }
         __syncwarp();
     }
@@ -508,10 +534,11 @@ cudaError_t snk_exact_launch_step(const KParams& P, float* state, const float* a
 }
 
 cudaError_t snk_exact_launch_rollout(const KParams& P, float* state, const float* weights, const float* mean, const float* inv_std,
-                                     const float* noise, int n_steps, float* returns, float* trace, unsigned long long* counters, int64_t n,
-                                     cudaStream_t st) {
+                                     const float* noise, int n_steps, float* returns, float* trace, int32_t* queue, int32_t* done_steps,
+                                     unsigned long long* counters, int64_t n, cudaStream_t st) {
     RolloutArgs A;
     A.weights = weights; A.mean = mean; A.inv_std = inv_std; A.noise = noise; A.returns = returns; A.trace = trace; A.n_steps = n_steps;
+    A.queue = queue; A.done_steps = done_steps;
     const int per_cta = (TWARPS + SWARPS) * 32;
     const int64_t want = (n + per_cta - 1) / per_cta;
     dim3 grid((unsigned)(want < g_sms ? want : g_sms)), block(per_cta);
