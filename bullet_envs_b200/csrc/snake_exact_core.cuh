@@ -16,15 +16,18 @@
 //           (getJointState()[3]), joint integration;
 //   finish  base velocity/pose integration, joint-0 reaction force.
 //
-// Data placement: the 13 base-state floats and the chain cursor live in
-// registers; the 18 floats per contact x 32 contacts live in shared memory as [contact][thread]
-// columns (bank = thread, conflict free); joint angles/velocities/torques stay in the handle's
-// structure-of-arrays state in global memory ([slot][env], one coalesced 128 B line per warp access,
-// L2 resident for the whole env-step); model tables are read from constant memory at warp-uniform
-// addresses.
+// Data placement: the 13 base-state floats, the chain cursor and the solver's
+// 6-vector live in registers; the contact-row table (32 contacts x 18 words, re-read by every sweep)
+// lives in tensor memory or shared memory behind a row-storage policy (RowsT / RowsS below); joint
+// angles/velocities/torques stay in the environment's 256 B record of the handle's [N][64] state
+// array (L1 resident while a lane owns the environment); model tables are read from constant memory
+// at warp-uniform addresses.
 //
-// Everything here is __host__ __device__ so that tests/hostemu can run the very same fp32 code on the
-// CPU (development check only; the product library contains the device instantiation only).
+// The tick is WARP CONVERGENT (every lane executes every row-storage access; masked lanes commit
+// nothing) because the tensor-memory accesses are warp-wide .sync.aligned instructions.
+//
+// Everything except RowsT is __host__ __device__ so that tests/hostemu can run the very same fp32
+// code on the CPU (development check only; the product library contains the device code only).
 #pragma once
 #include "snake_step.cuh"
 
@@ -34,7 +37,7 @@
 #define SNK_HD inline
 #endif
 
-#define EB 32 // environments (= threads) per CTA
+#define EB 32 // environments (= lanes) per warp
 
 // Model tables for the exact kernel (fp32; constant memory on the device).
 struct ExTables {
