@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""BASELINE.json configs[0]: the open-loop sinusoidal gait of snake_gait_test.py for 1000 ticks on a single
+"""(Test-side script: it uses the CPU oracle, so it lives under tests/.)  BASELINE.json configs[0]: the open-loop sinusoidal gait of snake_gait_test.py for 1000 ticks on a single
 snake -- dt = 0.01, g = -9.81, 4 N.m motors, targets theta_n(t) = -(pi/6) sin(4 n + 2 t) on the odd joints with
 t = tick * 0.01 (the script's wall clock made deterministic), obstacle block omitted (snake_gait_test.py:50-53,
 64-104).  Runs the CPU oracle (fp64) and the CUDA path (N = 1 and N = 4096 replicas) and prints one JSON line."""

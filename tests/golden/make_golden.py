@@ -11,7 +11,7 @@ recorded (obs, reward, done, ticks) pin the oracle's and the CUDA kernel's resta
 a1-a5, a8-a12, a15 of SURVEY.md section 8.  The physics tick underneath is the oracle's (PyBullet
 itself is not installable here), so these vectors do NOT pin the tick against Bullet.
 
-Run in the authoring container only (needs /root/reference):  python tools/make_golden.py
+Run in the authoring container only (needs /root/reference):  python tests/golden/make_golden.py
 """
 import os
 import sys
@@ -20,7 +20,7 @@ import types
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 REF = "/root/reference"
 

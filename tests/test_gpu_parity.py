@@ -136,7 +136,7 @@ def test_free_running_statistics(torch):
 
 
 def test_golden_scenarios_on_the_gpu(torch, golden):
-    """The reference-Python golden vectors (tests/golden, made by tools/make_golden.py): tick counts, done
+    """The reference-Python golden vectors (tests/golden, made by tests/golden/make_golden.py): tick counts, done
     flags and joint angles of every step; the contact-sensitive base pose over the first steps."""
     for name in ("const_half", "random", "clipped", "serpenoid", "terminate_q9"):
         acts = golden[name + "/actions"]

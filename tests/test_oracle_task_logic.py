@@ -1,4 +1,4 @@
-"""Task logic of the oracle vs the reference's own Python (golden vectors made by tools/make_golden.py
+"""Task logic of the oracle vs the reference's own Python (golden vectors made by tests/golden/make_golden.py
 from the unmodified SnakeGymEnv.py / snake.py) and vs the reference's documented quirks."""
 import numpy as np
 import pytest
