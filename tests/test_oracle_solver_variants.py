@@ -29,3 +29,22 @@ def test_exact_motor_rows_track_the_bullet_order_solve():
     assert np.mean(tick_eq) >= 0.65 and max(tick_d) <= 2, (tick_eq, tick_d)
     assert max(dq) < 1.5e-2, dq
     assert max(dx) < 1.5e-2 and max(dr) < 3e-2, (dx, dr)
+
+
+def test_relaxed_motor_rows_converge_to_the_motor_law():
+    """The exact elimination is the limit of Bullet's iteration: with more sweeps the relaxed motor rows approach
+    qd+ = kp (q* - q)/dt in the typical environment (the tail are environments whose redundant contact set keeps
+    the Gauss-Seidel from converging at all)."""
+    from scenarios import rollout_states
+    n = 48
+    ex = Oracle(n, default_params(motor_solver=1))
+    s, tg = rollout_states(ex)
+    law = 0.1 * (tg - s[:, 13:29]) * 240.0
+    med = {}
+    for iters in (50, 1000):
+        pg = Oracle(n, default_params(motor_solver=0, solver_iterations=iters, residual_threshold=0.0))
+        pg.set_state(s); pg.tick(tg.astype(np.float64), 1)
+        med[iters] = np.median(np.abs(pg.get_state()[:, 29:45] - law))
+    ex.set_state(s); ex.tick(tg.astype(np.float64), 1)
+    assert np.abs(ex.get_state()[:, 29:45] - law).max() < 1e-9          # imposed exactly
+    assert med[1000] < 0.25 * med[50] and med[1000] < 3e-3, med
