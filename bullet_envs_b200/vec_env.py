@@ -221,6 +221,16 @@ class SnakeVecEnv:
         _abi.check(self._lib.snk_set_state(self._h, self._ptr(s), self._stream()), self._lib)
         torch.cuda.current_stream(self.device).synchronize()
 
+    def state_dict(self):
+        """Checkpoint of the whole batch (the reference never checkpoints simulator state):
+        the [N,64] state array on the CPU plus the parameters' bytes."""
+        return {"state": self.get_state().cpu(), "num_envs": self.num_envs, "params": bytes(self.params)}
+
+    def load_state_dict(self, sd):
+        if int(sd["num_envs"]) != self.num_envs or bytes(sd["params"]) != bytes(self.params):
+            raise ValueError("checkpoint was taken from a batch with another size or other parameters")
+        self.set_state(sd["state"])
+
     def counters(self):
         """Device counters of the last step launch: ticks, PGS iterations, dones, non-finite resets."""
         out = (ctypes.c_int64 * 4)()

@@ -99,3 +99,21 @@ def test_row_storage_variants_agree(torch):
         assert out.returncode == 0, out.stderr[-2000:]
         sums.append([l for l in out.stdout.splitlines() if l.startswith("SUM")][0])
     assert sums[0] == sums[1]
+
+
+def test_checkpoint_resume_is_bit_exact(torch):
+    from bullet_envs_b200 import SnakeVecEnv
+    n = 300
+    g = torch.Generator().manual_seed(11)
+    acts = (torch.rand((6, n, 8), generator=g) * 2 - 1).cuda()
+    a = SnakeVecEnv(num_envs=n, device=0); a.reset(as_torch=True)
+    for t in range(3):
+        a.step(acts[t])
+    sd = a.state_dict()
+    b = SnakeVecEnv(num_envs=n, device=0); b.load_state_dict(sd)
+    for t in range(3, 6):
+        oa, ra, da, _ = a.step(acts[t]); ob, rb, db, _ = b.step(acts[t])
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db)
+    with pytest.raises(ValueError):
+        SnakeVecEnv(num_envs=n + 1, device=0).load_state_dict(sd)
+    a.close(); b.close()
