@@ -316,3 +316,35 @@ def test_one_model_per_process_is_enforced(torch):
     oo, orr, od, ot = o.step(a.astype(np.float64))
     assert np.array_equal(np.asarray(e2.last_ticks), ot) and np.abs(ob[:, :16] - oo[:, :16]).max() < 1e-5
     e2.close()
+
+
+def test_free_flight_matches_independent_numpy_dynamics(torch, model):
+    """Physics known-answer test of the CUDA tick that does not involve the oracle: far above the plane (no contacts)
+    the base acceleration must satisfy the hybrid dynamics  M_bb a_b + M_bj qdd = F_b  with the joint accelerations the
+    motor law prescribes, where M and F come from the dense world-frame Newton-Euler in tests/ref_dynamics_numpy.py."""
+    import ref_dynamics_numpy as rd
+    n = 16
+    rng = np.random.default_rng(21)
+    p = default_params()
+    s = np.zeros((n, 64)); tg = rng.uniform(-0.5, 0.5, (n, 16)).astype(np.float32)
+    for e in range(n):
+        s[e, 0:3] = [0.3, -0.2, 5.0]
+        q = rng.normal(size=4); s[e, 3:7] = q / np.linalg.norm(q)
+        s[e, 7:10] = rng.normal(size=3) * 0.5; s[e, 10:13] = rng.normal(size=3)
+        s[e, 13:29] = rng.uniform(-0.6, 0.6, 16); s[e, 29:45] = rng.normal(size=16) * 2.0
+    s = s.astype(np.float32).astype(np.float64)
+    env = make_env(n, p)
+    env.set_state(s); env.tick(tg, 1)
+    g = env.get_state().cpu().numpy().astype(np.float64)
+    dt = p.dt
+    for e in range(n):
+        acc_free, Mw = rd.forward_dynamics(model, s[e, 0:3], s[e, 3:7], s[e, 7:10], s[e, 10:13], s[e, 13:29], s[e, 29:45],
+                                           np.zeros(16), [0, 0, -9.8], 0.04, 0.04)
+        F = Mw @ acc_free                                            # generalized force incl. all bias terms
+        qd_new = 0.1 * (tg[e] - s[e, 13:29]) / dt                    # motor law (SURVEY A.4)
+        qdd = (qd_new - s[e, 29:45]) / dt
+        ab = np.linalg.solve(Mw[:6, :6], F[:6] - Mw[:6, 6:] @ qdd)   # [angular, linear] base acceleration, world axes
+        got = np.concatenate([g[e, 10:13] - s[e, 10:13], g[e, 7:10] - s[e, 7:10]]) / dt
+        assert np.abs(got - ab).max() < 2e-3 * max(1.0, np.abs(ab).max()), (e, got, ab)
+        assert np.abs(g[e, 29:45] - qd_new).max() < 1e-3 and np.abs(g[e, 13:29] - (s[e, 13:29] + dt * qd_new)).max() < 1e-6
+    env.close()

@@ -152,3 +152,25 @@ def test_fp32_build_tracks_fp64_without_friction(model):
         oa, ra, da, ta = a.step(act); ob, rb, db, tb = b.step(act)
         assert (ta == tb).all() and (da == db).all()
         assert np.abs(oa[:, :16] - ob[:, :16]).max() < 1e-4 and np.abs(ra - rb).max() < 1e-4
+
+
+def test_exact_motor_elimination_matches_dense_hybrid_dynamics(model):
+    """tick_exact (motor rows imposed) in free flight: the base acceleration solves
+    M_bb a_b + M_bj qdd = F_b with the prescribed joint accelerations; M, F from the dense numpy Newton-Euler."""
+    rng = np.random.default_rng(21)
+    p = default_params(motor_solver=1)
+    o = Oracle(1, p, model)
+    for _ in range(4):
+        s = _random_state(rng)
+        tg = rng.uniform(-0.5, 0.5, (1, 16))
+        o.set_state(s); o.tick(tg, 1)
+        g = o.get_state()[0]
+        acc_free, Mw = rd.forward_dynamics(model, s[0, 0:3], s[0, 3:7], s[0, 7:10], s[0, 10:13], s[0, 13:29], s[0, 29:45],
+                                           np.zeros(16), [0, 0, -9.8], 0.04, 0.04)
+        F = Mw @ acc_free
+        qd_new = 0.1 * (tg[0] - s[0, 13:29]) / p.dt
+        qdd = (qd_new - s[0, 29:45]) / p.dt
+        ab = np.linalg.solve(Mw[:6, :6], F[:6] - Mw[:6, 6:] @ qdd)
+        got = np.concatenate([g[10:13] - s[0, 10:13], g[7:10] - s[0, 7:10]]) / p.dt
+        assert np.abs(got - ab).max() < 1e-8 * max(1.0, np.abs(ab).max())
+        assert np.allclose(g[29:45], qd_new, atol=1e-12)
