@@ -348,3 +348,23 @@ def test_free_flight_matches_independent_numpy_dynamics(torch, model):
         assert np.abs(got - ab).max() < 2e-3 * max(1.0, np.abs(ab).max()), (e, got, ab)
         assert np.abs(g[e, 29:45] - qd_new).max() < 1e-3 and np.abs(g[e, 13:29] - (s[e, 13:29] + dt * qd_new)).max() < 1e-6
     env.close()
+
+
+def test_rest_on_the_plane_and_gait_makes_progress(torch):
+    """contact known-answers of the CUDA path: the reset pose is a resting contact (the chain neither sinks nor drifts),
+    and the serpenoid gait on the anisotropic-friction skin moves the snake along its body axis like the oracle's."""
+    n = 32
+    env = make_env(n)
+    env.reset(as_torch=True)
+    env.tick(np.zeros((n, 16), np.float32), 120)                      # half a second at rest
+    s = env.get_state().cpu().numpy()
+    assert np.abs(s[:, 7:13]).max() < 2e-3 and np.abs(s[:, 2]).max() < 1.5e-3 and np.abs(s[:, 0:2]).max() < 1e-3
+    assert np.abs(s[:, 13:45]).max() == 0.0 and np.abs(np.linalg.norm(s[:, 3:7], axis=1) - 1).max() < 1e-6
+    env.reset(as_torch=True)
+    o = Oracle(n); o.reset()
+    acts = serpenoid_actions(40, n).astype(np.float32)
+    for t in range(40):
+        obs, _, _, _ = env.step(acts[t]); oo, _, _, _ = o.step(acts[t].astype(np.float64), threads=8)
+    dx_gpu, dx_ref = float(np.mean(obs[:, 48])), float(np.mean(oo[:, 48]))
+    assert abs(dx_ref) > 0.02 and np.sign(dx_gpu) == np.sign(dx_ref) and abs(dx_gpu - dx_ref) < 0.25 * abs(dx_ref), (dx_gpu, dx_ref)
+    env.close()
