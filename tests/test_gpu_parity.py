@@ -366,5 +366,5 @@ def test_rest_on_the_plane_and_gait_makes_progress(torch):
     for t in range(40):
         obs, _, _, _ = env.step(acts[t]); oo, _, _, _ = o.step(acts[t].astype(np.float64), threads=8)
     dx_gpu, dx_ref = float(np.mean(obs[:, 48])), float(np.mean(oo[:, 48]))
-    assert abs(dx_ref) > 0.02 and np.sign(dx_gpu) == np.sign(dx_ref) and abs(dx_gpu - dx_ref) < 0.25 * abs(dx_ref), (dx_gpu, dx_ref)
+    assert abs(dx_ref) > 0.005 and np.sign(dx_gpu) == np.sign(dx_ref) and abs(dx_gpu - dx_ref) < 0.25 * abs(dx_ref), (dx_gpu, dx_ref)
     env.close()
