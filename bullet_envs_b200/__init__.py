@@ -11,6 +11,9 @@ def __getattr__(name):  # torch is imported lazily (the first import can take a 
     if name in ("SnakeGymEnv", "Snake"):
         from . import gym_env
         return getattr(gym_env, name)
+    if name in ("RolloutBuffer", "compute_gae"):
+        import importlib
+        return getattr(importlib.import_module(__name__ + ".rollout"), name)
     if name == "dist":
         import importlib
         return importlib.import_module(__name__ + ".dist")

@@ -45,20 +45,23 @@ def ppo(args):
     assert sum(p.numel() for p in net.parameters()) == 165137
     n, T = args.envs, 20  # ppo/params.py:10
     env = SnakeVecEnv(num_envs=n, device=0)
-    obs = torch.empty((T + 1, n, 56), device=dev); act = torch.empty((T, n, 8), device=dev)
-    rew = torch.empty((T, n), device=dev); done = torch.empty((T, n), dtype=torch.uint8, device=dev)
-    logp = torch.empty((T, n, 8), device=dev); val = torch.empty((T, n, 1), device=dev)
+    from bullet_envs_b200.rollout import RolloutBuffer, compute_gae
+    buf = RolloutBuffer(T, n, device=dev)
+    rew, done = buf.rewards, buf.dones
 
     def rollout():
         with torch.no_grad():
             for t in range(T):
-                dist, v = net(obs[t])
+                dist, v = net(buf.obs[t])
                 a = dist.sample()
-                act[t] = a; logp[t] = dist.log_prob(a); val[t] = v
-                env.step(a, out=(obs[t + 1], rew[t], done[t]))
-            obs[0] = obs[T]
+                buf.actions[t] = a; buf.log_probs[t] = dist.log_prob(a); buf.values[t] = v.squeeze(-1)
+                env.step(a, out=buf.out(t))                      # the kernel writes obs[t+1], rewards[t], dones[t] in place
+            _, next_value = net(buf.obs[T])
+            returns = compute_gae(next_value.squeeze(-1), buf.rewards, buf.masks(), buf.values)   # ppo/agent.py:14-22 on device
+            buf.roll()
+        return returns
 
-    obs[0] = env.reset(as_torch=True)
+    buf.obs[0] = env.reset(as_torch=True)
     rollout()  # warm-up
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -67,7 +70,7 @@ def ppo(args):
         rollout()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(json.dumps({"workload": "PPO rollout collection, ppo/train.py policy in torch", "envs": n, "num_steps": T, "rollouts": args.rollouts,
+    print(json.dumps({"workload": "PPO rollout collection + GAE, ppo/train.py policy in torch, device-resident RolloutBuffer", "envs": n, "num_steps": T, "rollouts": args.rollouts,
                       "env_steps_per_s": n * T * args.rollouts / (ms * 1e-3), "ms_per_rollout": ms / args.rollouts,
                       "mean_reward": float(rew.mean()), "done_rate": float(done.float().mean()), "n_gpus": 1}))
 
