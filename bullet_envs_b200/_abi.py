@@ -102,11 +102,13 @@ def load_library():
     lib.snk_device.argtypes = [vp]
     lib.snk_reset.argtypes = [vp, vp, vp, vp]
     lib.snk_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.snk_step_trace.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.snk_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.snk_reset_host.argtypes = [vp, vp, vp]
     lib.snk_tick.argtypes = [vp, vp, i32, vp]
     lib.snk_rollout_linear.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
     lib.snk_observe.argtypes = [vp, vp, vp]
+    lib.snk_self_clearance.argtypes = [vp, vp, vp]
     lib.snk_get_state.argtypes = [vp, vp, vp]
     lib.snk_set_state.argtypes = [vp, vp, vp]
     lib.snk_last_counters.argtypes = [vp, P(i64)]

@@ -15,7 +15,8 @@
 // warp-per-env kernel with Bullet-order motor rows (snake_pgs.cu)
 cudaError_t snk_pgs_configure();
 cudaError_t snk_pgs_launch_step(const DevTables* T, const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
-                                int32_t* ticks, unsigned long long* counters, int64_t n, cudaStream_t st);
+                                int32_t* ticks, unsigned long long* counters, int64_t n, cudaStream_t st, float* tick_obs = nullptr,
+                                float* tick_links = nullptr);
 cudaError_t snk_pgs_launch_tick(const DevTables* T, const KParams& P, float* state, const float* targets, unsigned long long* counters, int64_t n,
                                 int n_ticks, cudaStream_t st);
 // thread-per-env kernel with the motor rows eliminated (snake_exact.cu)
@@ -27,8 +28,12 @@ cudaError_t snk_exact_launch_step(const KParams& P, float* state, const float* a
 cudaError_t snk_exact_launch_rollout(const KParams& P, float* state, const float* weights, const float* mean, const float* inv_std,
                                      const float* noise, int n_steps, float* returns, float* trace, int32_t* queue, int32_t* done_steps,
                                      unsigned long long* counters, int64_t n, cudaStream_t st);
+cudaError_t snk_exact_launch_step_trace(const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
+                                        int32_t* ticks, unsigned long long* counters, int64_t n, float* tick_obs, float* tick_links, cudaStream_t st);
 cudaError_t snk_exact_launch_tick(const KParams& P, float* state, const float* targets, unsigned long long* counters, int64_t n,
                                   int n_ticks, cudaStream_t st);
+// self-collision clearance counter (snake_pgs.cu)
+cudaError_t snk_launch_self_clearance(const DevTables* T, const float* state, float* out, int64_t n, cudaStream_t st);
 // reset / observe (snake_pgs.cu)
 cudaError_t snk_launch_reset(const KParams& P, float* state, const uint8_t* mask, float* obs, int64_t n, int mode, cudaStream_t st);
 
@@ -51,7 +56,7 @@ struct snk_handle {
     int64_t n;
     bool exact;                   // thread-per-env kernel with the motor rows eliminated (else warp-per-env, Bullet-order rows)
     KParams P;
-    DevTables* T;                 // device (warp-per-env kernel only)
+    DevTables* T;                 // device: general model tables (warp-per-env kernel, clearance counter)
     float* state;                 // device [n][64]
     uint8_t* bucket;              // device [n]: predicted tick count of the coming env-step (exact kernel)
     int32_t* order;               // device [n]: longest-first hand-out order
@@ -133,9 +138,11 @@ int snk_create(const snk_model* model, const snk_params* params, int64_t n_envs,
         if (err == cudaSuccess) err = cudaMalloc(&h->bucket, (size_t)n_envs);
         if (err == cudaSuccess) err = cudaMalloc(&h->order, (size_t)n_envs * sizeof(int32_t));
     } else {
+        err = snk_pgs_configure();
+    }
+    {
         DevTables host_tables;
         snk_to_tables(model, &host_tables);
-        err = snk_pgs_configure();
         if (err == cudaSuccess) err = cudaMalloc(&h->T, sizeof(DevTables));
         if (err == cudaSuccess) err = cudaMemcpy(h->T, &host_tables, sizeof host_tables, cudaMemcpyHostToDevice);
     }
@@ -198,6 +205,21 @@ int snk_step(snk_handle* h, const float* actions_dev, float* obs_dev, float* rew
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
     CU(launch_step(h, actions_dev, obs_dev, rew_dev, done_dev, ticks_dev, st));
+    return 0;
+}
+
+int snk_step_trace(snk_handle* h, const float* actions_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, int32_t* ticks_dev,
+                   float* tick_obs_dev, float* tick_links_dev, void* stream) {
+    if (!h || !actions_dev || !obs_dev || !rew_dev || !done_dev || !ticks_dev)
+        return fail(SNK_E_ARG, "snk_step_trace: null pointer (ticks_dev is required: it says how many trace rows are valid)%s");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
+    if (h->exact) CU(snk_exact_launch_step_trace(h->P, h->state, actions_dev, obs_dev, rew_dev, done_dev, ticks_dev, h->counters, h->n, tick_obs_dev,
+                                                 tick_links_dev, st));
+    else CU(snk_pgs_launch_step(h->T, h->P, h->state, actions_dev, obs_dev, rew_dev, done_dev, ticks_dev, h->counters, h->n, st, tick_obs_dev,
+                                tick_links_dev));
+    h->launches++;
     return 0;
 }
 
@@ -304,6 +326,14 @@ int snk_reset_host(snk_handle* h, const uint8_t* mask_host, float* obs_host) {
     if (obs_host) CU(cudaMemcpyAsync(h->h_obs, h->d_obs, n * SNK_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (obs_host) memcpy(obs_host, h->h_obs, n * SNK_OBS_DIM * sizeof(float));
+    return 0;
+}
+
+int snk_self_clearance(snk_handle* h, float* clearance_dev, void* stream) {
+    if (!h || !clearance_dev) return fail(SNK_E_ARG, "snk_self_clearance: null pointer%s");
+    CU(cudaSetDevice(h->device));
+    CU(snk_launch_self_clearance(h->T, h->state, clearance_dev, h->n, (cudaStream_t)stream));
+    h->launches++;
     return 0;
 }
 

@@ -58,10 +58,13 @@ __device__ __forceinline__ void load_targets(const KParams& P, const Rows& R, co
 
 // The persistent loop of one warp.  counters: [0] ticks, [1] PGS sweeps, [2] dones, [3] non-finite resets,
 // [4] next environment to hand out.
-template <bool CONE, class Rows>
+// TRACE: the mode='test' info stream (snake.py:275-278,292-293): after every physics tick the observation goes to
+// tick_obs[env][tick][56] and the link positions to tick_links[env][tick][51] (max_ticks rows per environment).
+template <bool CONE, class Rows, bool TRACE = false>
 __device__ __forceinline__ void run_warp(const KParams& P, const Rows& R, float* __restrict__ state, const float* __restrict__ actions,
                                          float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks,
-                                         unsigned long long* __restrict__ counters, const int32_t* __restrict__ order, int64_t n) {
+                                         unsigned long long* __restrict__ counters, const int32_t* __restrict__ order, int64_t n,
+                                         float* __restrict__ tick_obs = nullptr, float* __restrict__ tick_links = nullptr) {
     const int lane = R.lane;
     const unsigned lt_mask = (1u << lane) - 1u;
     ExEnv e; // a lane without an environment computes (masked) on record 0 in the rest pose
@@ -99,7 +102,18 @@ __device__ __forceinline__ void run_warp(const KParams& P, const Rows& R, float*
         }
         if (!__any_sync(FULL, have)) break;
         __syncwarp();
-        if (ex_step_advance<CONE>(cT, P, R, e, have, &run)) { // every lane of the warp ticks together
+        const int tick0 = run.counter;
+        const bool finished = ex_step_advance<CONE>(cT, P, R, e, have, &run); // every lane of the warp ticks together
+        if (TRACE && have && run.counter > tick0) { // this lane's environment took a tick: snake.py:291-293
+            const int64_t row = env * P.maxticks + tick0;
+            if (tick_obs) {
+                float* to = tick_obs + row * SNK_OBS_DIM;
+#pragma unroll 1
+                for (int k = 0; k < SNK_OBS_DIM; k++) to[k] = ex_obs_of(e, k);
+            }
+            if (tick_links) ex_link_positions(cT, e, tick_links + row * (3 * NB));
+        }
+        if (finished) {
             ExStepOut o;
             ex_step_end(cT, P, e, run, &o);
             rew[env] = o.rew;
@@ -352,6 +366,20 @@ snk_exact_step_kernel_smem(const KParams P, float* __restrict__ state, const flo
     run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, order, n);
 }
 
+// the env-step with the mode='test' info stream (snk_step_trace): an analysis path for a handful of environments,
+// so the plain shared-memory variant carries it and the benchmarked kernel stays untouched
+template <bool CONE>
+__global__ void __launch_bounds__(EB, 3)
+snk_exact_step_trace_kernel(const KParams P, float* __restrict__ state, const float* __restrict__ actions, float* __restrict__ obs,
+                            float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks,
+                            unsigned long long* __restrict__ counters, int64_t n, float* __restrict__ tick_obs, float* __restrict__ tick_links) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RowsS R;
+    R.s = reinterpret_cast<RowsSmemStore*>(smem_raw);
+    R.lane = threadIdx.x;
+    run_warp<CONE, RowsS, true>(P, R, state, actions, obs, rew, done, ticks, counters, nullptr, n, tick_obs, tick_links);
+}
+
 // n_ticks raw ticks with explicit targets[N,16] (gait script): every environment runs the same number of
 // ticks, so the assignment is static (thread = environment); rows in shared memory
 template <bool CONE>
@@ -484,9 +512,10 @@ cudaError_t snk_exact_configure(const ExTables* host_tables) {
     const char* w = getenv("SNK_EXACT_WARPS");
     if (w && atoi(w) >= 1 && atoi(w) <= TWARPS + SWARPS) g_active_warps = atoi(w);
     cudaError_t e = cudaMemcpyToSymbol(cT, host_tables, sizeof(ExTables));
-    const void* k1[4] = {(const void*)snk_exact_step_kernel_smem<true>, (const void*)snk_exact_step_kernel_smem<false>,
-                         (const void*)snk_exact_tick_kernel<true>, (const void*)snk_exact_tick_kernel<false>};
-    for (int i = 0; i < 4 && e == cudaSuccess; i++)
+    const void* k1[6] = {(const void*)snk_exact_step_kernel_smem<true>, (const void*)snk_exact_step_kernel_smem<false>,
+                         (const void*)snk_exact_tick_kernel<true>, (const void*)snk_exact_tick_kernel<false>,
+                         (const void*)snk_exact_step_trace_kernel<true>, (const void*)snk_exact_step_trace_kernel<false>};
+    for (int i = 0; i < 6 && e == cudaSuccess; i++)
         e = cudaFuncSetAttribute(k1[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowsSmemStore));
     const void* k2[4] = {(const void*)snk_exact_step_kernel<true>, (const void*)snk_exact_step_kernel<false>,
                          (const void*)snk_exact_rollout_kernel<true>, (const void*)snk_exact_rollout_kernel<false>};
@@ -530,6 +559,15 @@ cudaError_t snk_exact_launch_step(const KParams& P, float* state, const float* a
         if (P.cone) snk_exact_step_kernel_smem<true><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n);
         else snk_exact_step_kernel_smem<false><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t snk_exact_launch_step_trace(const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
+                                        int32_t* ticks, unsigned long long* counters, int64_t n, float* tick_obs, float* tick_links, cudaStream_t st) {
+    const int64_t warps = (n + EB - 1) / EB;
+    dim3 grid((unsigned)(warps < g_smem_ctas ? warps : g_smem_ctas)), block(EB);
+    if (P.cone) snk_exact_step_trace_kernel<true><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, actions, obs, rew, done, ticks, counters, n, tick_obs, tick_links);
+    else snk_exact_step_trace_kernel<false><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, actions, obs, rew, done, ticks, counters, n, tick_obs, tick_links);
     return cudaGetLastError();
 }
 

@@ -660,6 +660,23 @@ SNK_HD float ex_height(const ExTables& T, const ExEnv& e) {
     return hsum * (1.f / NB);
 }
 
+// world COM positions of URDF links arange(0,49,3) of the current state as [x0..x16 | y0..y16 | z0..z16]
+// (Snake.getLinkPositions, snake.py:138-146; the points checkSnakeHeight averages): mode='test' info stream only
+SNK_HD void ex_link_positions(const ExTables& T, const ExEnv& e, float* out) {
+    M3 R = quat_to_m3(e.quat);
+    V3 p = ld3(e.pos);
+#pragma unroll 1
+    for (int i = 0; i < NB; i++) {
+        if (i > 0) {
+            const int j = i - 1;
+            p = p + mul(R, ld3(T.jt[j]));
+            R = mul(R, joint_rot(T, j, slot(e, SNK_S_Q + j)));
+        }
+        const V3 w = p + mul(R, ld3(T.hpt[i]));
+        out[i] = w.x; out[NB + i] = w.y; out[2 * NB + i] = w.z;
+    }
+}
+
 // -----------------------------------------------------------------------------------------------
 // task logic around the tick: one SubprocVecEnv.step of one environment (oracle: env_step).
 // S.tgt[.][tid] must hold the 16 joint targets (checkBound + createAction + scaling already applied).

@@ -579,6 +579,102 @@ __global__ void snk_reset_kernel(const KParams P, float* __restrict__ state, con
 }
 
 // ---------------------------------------------------------------------------------------------
+// Self-collision clearance.  The reference loads the snake with
+// URDF_USE_SELF_COLLISION (snake.py:93): Bullet then tests every pair of links except parent-child pairs, i.e.
+// every pair of the 32 cylinders that are not consecutive along the chain (465 pairs).  The step kernels omit
+// those pairs because they cannot touch at the joint angles the task reaches (|q| <= pi/6 + the 0.5 rad
+// termination); this kernel is the counter that proves it for a given batch state: per environment, a LOWER
+// BOUND of the smallest distance between two non-consecutive cylinders -- for every pair the best separation
+//   gap(d) = d.(cB - cA) - support_A(d) - support_B(-d),  support(d) = h |d.a| + r sqrt(1 - (d.a)^2)
+// over nine candidate directions d (the two axes, both signs; the centre line; the centre line with each axis
+// projected out; the common normal, both signs).  Any unit d gives a valid bound, so the result can only
+// under-estimate the true distance.  One warp per environment, lanes over pairs.
+// ---------------------------------------------------------------------------------------------
+struct WarpMemFk {
+    float s[SNK_STATE_STRIDE];
+    float Rw[NB][9];
+    float pw[NB][3];
+    float Rj[NB][9];
+    float cc[NC][3]; // cylinder centres, world
+    float ca[NC][3]; // cylinder axes, world
+};
+#define CLR_WARPS 4
+
+__device__ __forceinline__ float cyl_support(const float* d, const float* a, float h, float r) {
+    const float t = dot3(d, a);
+    return h * fabsf(t) + r * sqrtf(fmaxf(0.f, 1.f - t * t));
+}
+
+__global__ void __launch_bounds__(CLR_WARPS * 32)
+snk_self_clearance_kernel(const DevTables* __restrict__ T, const float* __restrict__ state, float* __restrict__ out, int64_t n) {
+    __shared__ WarpMemFk Ws[CLR_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t env = (int64_t)blockIdx.x * CLR_WARPS + warp;
+    if (env >= n) return;
+    WarpMemFk& W = Ws[warp];
+    const float* gs = state + env * SNK_STATE_STRIDE;
+    W.s[lane] = gs[lane];
+    W.s[lane + 32] = gs[lane + 32];
+    __syncwarp();
+    fk(W, T, lane);
+    { // lane = cylinder
+        const int b = __ldg(&T->cbody[lane]);
+        float c[3] = {__ldg(&T->ccen[lane][0]), __ldg(&T->ccen[lane][1]), __ldg(&T->ccen[lane][2])}, cw[3];
+        float a[3] = {__ldg(&T->cax[lane][0]), __ldg(&T->cax[lane][1]), __ldg(&T->cax[lane][2])}, aw[3];
+        m3v(W.Rw[b], c, cw);
+        m3v(W.Rw[b], a, aw);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { W.cc[lane][k] = W.pw[b][k] + cw[k]; W.ca[lane][k] = aw[k]; }
+    }
+    __syncwarp();
+    float best = 3.0e38f;
+#pragma unroll 1
+    for (int i = 0; i < NC - 2; i++) {
+        const float hi = __ldg(&T->chl[i]), ri = __ldg(&T->crad[i]);
+#pragma unroll 1
+        for (int j = i + 2 + lane; j < NC; j += 32) {
+            const float hj = __ldg(&T->chl[j]), rj = __ldg(&T->crad[j]);
+            const float* ai = W.ca[i];
+            const float* aj = W.ca[j];
+            const float dc[3] = {W.cc[j][0] - W.cc[i][0], W.cc[j][1] - W.cc[i][1], W.cc[j][2] - W.cc[i][2]};
+            float cand[9][3];
+            int nc = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) { cand[0][k] = ai[k]; cand[1][k] = -ai[k]; cand[2][k] = aj[k]; cand[3][k] = -aj[k]; }
+            nc = 4;
+            const float nd = sqrtf(dot3(dc, dc));
+            if (nd > 1e-9f) { for (int k = 0; k < 3; k++) cand[nc][k] = dc[k] / nd; nc++; }
+            for (int w = 0; w < 2; w++) { // centre line with one axis projected out
+                const float* ax = w ? aj : ai;
+                const float t = dot3(ax, dc);
+                float pr[3] = {dc[0] - ax[0] * t, dc[1] - ax[1] * t, dc[2] - ax[2] * t};
+                const float np_ = sqrtf(dot3(pr, pr));
+                if (np_ > 1e-9f) { for (int k = 0; k < 3; k++) cand[nc][k] = pr[k] / np_; nc++; }
+            }
+            float x[3];
+            cross3(ai, aj, x);
+            const float nx = sqrtf(dot3(x, x));
+            if (nx > 1e-9f) {
+                for (int k = 0; k < 3; k++) { cand[nc][k] = x[k] / nx; cand[nc + 1][k] = -x[k] / nx; }
+                nc += 2;
+            }
+            float g = -3.0e38f;
+            for (int q = 0; q < nc; q++) g = fmaxf(g, dot3(cand[q], dc) - cyl_support(cand[q], ai, hi, ri) - cyl_support(cand[q], aj, hj, rj));
+            best = fminf(best, g);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(FULL, best, o));
+    if (lane == 0) out[env] = best;
+}
+
+cudaError_t snk_launch_self_clearance(const DevTables* T, const float* state, float* out, int64_t n, cudaStream_t st) {
+    dim3 grid((unsigned)((n + CLR_WARPS - 1) / CLR_WARPS)), block(CLR_WARPS * 32);
+    snk_self_clearance_kernel<<<grid, block, 0, st>>>(T, state, out, n);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // launch wrappers used by the C-ABI host code (snake_abi.cu)
 // ---------------------------------------------------------------------------------------------
 size_t snk_pgs_smem_bytes() { return sizeof(WarpMemPgs) * WARPS_PER_CTA; }
@@ -590,9 +686,10 @@ cudaError_t snk_pgs_configure() {
 }
 
 cudaError_t snk_pgs_launch_step(const DevTables* T, const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
-                            int32_t* ticks, unsigned long long* counters, int64_t n, cudaStream_t st) {
+                            int32_t* ticks, unsigned long long* counters, int64_t n, cudaStream_t st, float* tick_obs, float* tick_links) {
     dim3 grid((unsigned)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA)), block(WARPS_PER_CTA * 32);
-    snk_env_kernel<WarpMemPgs, false, WARPS_PER_CTA, 2><<<grid, block, snk_pgs_smem_bytes(), st>>>(T, P, state, actions, obs, rew, done, ticks, counters, n, 0);
+    snk_env_kernel<WarpMemPgs, false, WARPS_PER_CTA, 2><<<grid, block, snk_pgs_smem_bytes(), st>>>(T, P, state, actions, obs, rew, done, ticks, counters, n, 0,
+                                                                                                    tick_obs, tick_links);
     return cudaGetLastError();
 }
 

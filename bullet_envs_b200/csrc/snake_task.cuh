@@ -30,7 +30,8 @@ template <class WM, bool RAW, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 snk_env_kernel(const DevTables* __restrict__ T, const KParams P, float* __restrict__ state, const float* __restrict__ in,
                 float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks,
-                unsigned long long* __restrict__ counters, int64_t n, int n_ticks) {
+                unsigned long long* __restrict__ counters, int64_t n, int n_ticks, float* __restrict__ tick_obs = nullptr,
+                float* __restrict__ tick_links = nullptr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t env = (int64_t)blockIdx.x * WARPS + warp;
@@ -72,8 +73,21 @@ snk_env_kernel(const DevTables* __restrict__ T, const KParams P, float* __restri
             for (int j = 0; j < NJ; j++) { float d = W.target[j] - W.s[SNK_S_Q + j]; e2 += d * d; }
             if (!(sqrtf(e2) > P.errthr)) break;
             iters += tick(W, T, P, lane);
-            counter++;
             height = fk(W, T, lane);
+            if (tick_obs) { // mode='test' info stream (snake.py:291-292): the observation after this tick
+                float* to = tick_obs + (env * P.maxticks + counter) * SNK_OBS_DIM;
+                to[lane] = obs_of(W, lane);
+                if (lane + 32 < SNK_OBS_DIM) to[lane + 32] = obs_of(W, lane + 32);
+            }
+            if (tick_links && lane < NB) { // snake.py:293,138-146: [x0..x16 | y0..y16 | z0..z16], lane = link
+                const int b = __ldg(&T->hbody[lane]);
+                float* tl = tick_links + (env * P.maxticks + counter) * (3 * NB);
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    tl[k * NB + lane] = W.pw[b][k] + W.Rw[b][3 * k] * __ldg(&T->hpt[lane][0]) + W.Rw[b][3 * k + 1] * __ldg(&T->hpt[lane][1]) +
+                                        W.Rw[b][3 * k + 2] * __ldg(&T->hpt[lane][2]);
+            }
+            counter++;
             if (height > P.hthr) { end_height = true; break; }
             if (counter >= P.maxticks) break;
         }

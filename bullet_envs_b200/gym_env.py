@@ -48,7 +48,8 @@ class SnakeGymEnv:
         self._action_bound = 1
         urdf = getattr(self.robot, "_urdf", None)
         import os
-        self._vec = SnakeVecEnv(num_envs=1, args=args, device=device, urdf_path=urdf if (urdf and os.path.exists(urdf)) else None)
+        self._vec = SnakeVecEnv(num_envs=1, args=args, device=device, urdf_path=urdf if (urdf and os.path.exists(urdf)) else None,
+                                mode=self.mode)
         self.observation_space = self._vec.observation_space
         self.action_space = self._vec.action_space
         self._observation = None
@@ -63,11 +64,12 @@ class SnakeGymEnv:
             for i in range(len(action)):
                 if action[i] < -1 or action[i] > 1:
                     action[i] = np.clip(action[i], -1, 1)
-        obs, r, d, _ = self._vec.step(a[None, :])
+        self._vec.mode = self.mode  # the reference reads self.mode at every step (SnakeGymEnv.py:43)
+        obs, r, d, infos = self._vec.step(a[None, :])
         self._observation = obs[0]
-        return obs[0], float(r[0]), bool(d[0]), {}
+        return obs[0], float(r[0]), bool(d[0]), infos[0]  # {} in train mode, the per-tick stream in test mode (SnakeGymEnv.py:43-46)
 
-    def render(self):  # SnakeGymEnv.py:52-58 (train mode)
+    def render(self):  # SnakeGymEnv.py:52-58: train mode; test mode would need a display (out of scope)
         return np.array([])
 
     def close(self):

@@ -26,10 +26,12 @@ from . import _abi
 from .spaces import Box
 from .urdf_model import OBS_DIM, STATE_STRIDE, NJ, build_model
 
+LINK_POS_DIM = 51  # SNK_LINK_POS_DIM: 17 links x (x, y, z), snake.py:138-146
+
 
 class SnakeVecEnv:
     def __init__(self, env_fns=None, num_envs=None, args=None, device=None, urdf_path=None, params=None,
-                 model=None, obs_dtype=np.float64, pinned_io=False):
+                 model=None, obs_dtype=np.float64, pinned_io=False, mode=None):
         """``env_fns``: list of thunks as given to ``SubprocVecEnv`` (only its length is used -- the
         thunks would build PyBullet-backed envs) *or* pass ``num_envs``.  ``args``: the reference's
         argparse namespace (``ppo/params.py``) or None for the defaults.  ``device``: CUDA device
@@ -37,7 +39,10 @@ class SnakeVecEnv:
         ``np.float32`` skips the conversion).  ``pinned_io``: the numpy path keeps persistent page-locked
         result buffers that the library uses as DMA targets directly; the arrays returned by ``step`` /
         ``reset`` are then views that stay valid until the next call (the reference's callers convert or
-        consume them immediately: ``ppo/train.py:114,131-136``, ``ars/train.py:99-110``)."""
+        consume them immediately: ``ppo/train.py:114,131-136``, ``ars/train.py:99-110``).  ``mode``: ``'train'``
+        (default, or ``args.mode``) returns empty info dicts; ``'test'`` returns the reference's per-tick info stream
+        (``SnakeGymEnv.py:43-44``): ``info['internal_observations']`` / ``info['link_positions']`` = one array per
+        physics tick of the env-step (``snake.py:292-293``), ``info['frames']`` = [] (rendering needs a display)."""
         import torch
 
         if env_fns is not None and num_envs is None:
@@ -65,6 +70,8 @@ class SnakeVecEnv:
         self.closed = False
         self._pending = None
         self._infos = tuple({} for _ in range(self.num_envs))  # SnakeGymEnv.py:45-46 (train mode)
+        self.mode = mode if mode is not None else (getattr(args, "mode", "train") if args is not None else "train")
+        self.max_ticks = int(self.params.max_ticks)
         # spaces: snake.py:166-177, SnakeGymEnv.py:60-79
         hi = np.zeros(OBS_DIM)
         hi[0:NJ] = np.pi
@@ -108,9 +115,38 @@ class SnakeVecEnv:
                                             ctypes.c_void_p(obs.ctypes.data)), self._lib)
         return obs.astype(self.obs_dtype, copy=False)
 
+    def _step_test_mode(self, actions, out):
+        """mode='test' (snake.py:275-278,292-293): the step through ``snk_step_trace`` with the per-tick info stream."""
+        torch = self._torch
+        n, cuda_in = self.num_envs, torch.is_tensor(actions) and actions.is_cuda
+        a = (actions if cuda_in else torch.as_tensor(np.ascontiguousarray(np.asarray(actions), np.float32), device=self.device))
+        a = a.to(dtype=torch.float32).contiguous().view(n, self.act_dim)
+        if out is None or not cuda_in:
+            obs = torch.empty((n, OBS_DIM), dtype=torch.float32, device=self.device)
+            rew = torch.empty((n,), dtype=torch.float32, device=self.device)
+            done = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        else:
+            obs, rew, done = out
+        ticks = torch.empty((n,), dtype=torch.int32, device=self.device)
+        tobs = torch.empty((n, self.max_ticks, OBS_DIM), dtype=torch.float32, device=self.device)
+        tlnk = torch.empty((n, self.max_ticks, LINK_POS_DIM), dtype=torch.float32, device=self.device)
+        _abi.check(self._lib.snk_step_trace(self._h, self._ptr(a), self._ptr(obs), self._ptr(rew), self._ptr(done), self._ptr(ticks),
+                                            self._ptr(tobs), self._ptr(tlnk), self._stream()), self._lib)
+        tk = ticks.cpu().numpy()
+        tobs_h, tlnk_h = tobs.cpu().numpy().astype(self.obs_dtype), tlnk.cpu().numpy().astype(self.obs_dtype)
+        infos = tuple({"frames": [], "internal_observations": [tobs_h[e, k] for k in range(tk[e])],
+                       "link_positions": [tlnk_h[e, k] for k in range(tk[e])]} for e in range(n))
+        if cuda_in:
+            self._pending = ("torch", obs, rew, done, ticks, infos)
+        else:
+            self._pending = ("numpy", obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy(), tk, infos)
+        self.waiting = True
+
     def step_async(self, actions, out=None):
         self._check_open()
         torch = self._torch
+        if self.mode == "test":
+            return self._step_test_mode(actions, out)
         if torch.is_tensor(actions) and actions.is_cuda:
             a = actions.to(dtype=torch.float32).contiguous().view(self.num_envs, self.act_dim)
             if out is None:
@@ -126,7 +162,7 @@ class SnakeVecEnv:
             ticks = torch.empty((self.num_envs,), dtype=torch.int32, device=self.device)
             _abi.check(self._lib.snk_step(self._h, self._ptr(a), self._ptr(obs), self._ptr(rew), self._ptr(done), self._ptr(ticks),
                                           self._stream()), self._lib)
-            self._pending = ("torch", obs, rew, done, ticks)
+            self._pending = ("torch", obs, rew, done, ticks, self._infos)
         else:
             if self._pin is not None:
                 a = self._pin["act"]
@@ -140,19 +176,19 @@ class SnakeVecEnv:
                 ticks = np.empty(self.num_envs, np.int32)
             p = lambda x: ctypes.c_void_p(x.ctypes.data)
             _abi.check(self._lib.snk_step_host(self._h, p(a), p(obs), p(rew), p(done), p(ticks)), self._lib)
-            self._pending = ("numpy", obs, rew, done, ticks)
+            self._pending = ("numpy", obs, rew, done, ticks, self._infos)
         self.waiting = True
 
     def step_wait(self):
         if self._pending is None:
             raise RuntimeError("step_wait() without step_async()")
-        kind, obs, rew, done, ticks = self._pending
+        kind, obs, rew, done, ticks, infos = self._pending
         self._pending = None
         self.waiting = False
         self.last_ticks = ticks
         if kind == "torch":
-            return obs, rew, done.bool(), self._infos
-        return obs.astype(self.obs_dtype, copy=False), rew.astype(self.obs_dtype, copy=False), done.view(np.bool_), self._infos
+            return obs, rew, done.bool(), infos
+        return obs.astype(self.obs_dtype, copy=False), rew.astype(self.obs_dtype, copy=False), done.view(np.bool_), infos
 
     def step(self, actions, out=None):
         self.step_async(actions, out=out)
@@ -208,6 +244,15 @@ class SnakeVecEnv:
         obs = torch.empty((self.num_envs, OBS_DIM), dtype=torch.float32, device=self.device)
         _abi.check(self._lib.snk_observe(self._h, self._ptr(obs), self._stream()), self._lib)
         return obs
+
+    def self_clearance(self):
+        """Lower bound [N] (metres, CUDA tensor) of the smallest distance between two non-consecutive cylinders of every
+        environment -- the pairs ``URDF_USE_SELF_COLLISION`` (``snake.py:93``) makes Bullet test.  Positive over a run =
+        no self-contact was missed."""
+        torch = self._torch
+        c = torch.empty((self.num_envs,), dtype=torch.float32, device=self.device)
+        _abi.check(self._lib.snk_self_clearance(self._h, self._ptr(c), self._stream()), self._lib)
+        return c
 
     def get_state(self):
         torch = self._torch

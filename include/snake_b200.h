@@ -32,10 +32,13 @@
  *   snk_step_host   <- the same call made with numpy arrays (ppo/train.py:122, ars/train.py:99)
  *   snk_tick        <- raw setJointMotorControlArray + stepSimulation loop of the gait script
  *                      (snake_gait_test.py:96-104)
+ *   snk_step_trace  <- the same step in mode='test': Snake.step's per-tick step_internal_observations / link_positions
+ *                      (snake.py:275-278,292-293,138-146) returned through info (SnakeGymEnv.py:43-44; read by ppo/test.py:93-105)
  *   snk_observe     <- Snake.getObservation (snake.py:209-217)
  *   snk_rollout_linear <- ARS rollout with a linear policy per environment: ars/train.py:74-116 (test_envs)
  *                      with policy() = W x (ars/train.py:40-41), normalisation (ars/train.py:152-169, statistics
  *                      frozen for the rollout) and the state noise of ars/train.py:81,90 supplied by the caller
+ *   snk_self_clearance <- loadURDF(..., flags=URDF_USE_SELF_COLLISION) (snake.py:93): the pairs Bullet would test
  *   snk_get_state / snk_set_state <- resetBasePositionAndOrientation / resetJointState
  *                      (snake.py:119-127) generalised to arbitrary states (parity harness)
  */
@@ -159,6 +162,16 @@ int snk_step_host(snk_handle* h, const float* actions_host, float* obs_host, flo
                   uint8_t* done_host, int32_t* ticks_host);
 int snk_reset_host(snk_handle* h, const uint8_t* mask_host, float* obs_host);
 
+/* snk_step plus the mode='test' info stream of the reference (snake.py:275-278,292-293; SnakeGymEnv.py:43-44): for every
+ * physics tick k < ticks_dev[e] of environment e, the observation after that tick (info['internal_observations'][k]) goes to
+ * tick_obs_dev[e][k][0..55] and the world COM positions of URDF links arange(0,49,3) (info['link_positions'][k],
+ * Snake.getLinkPositions, snake.py:138-146) to tick_links_dev[e][k][0..50], laid out [x0..x16 | y0..y16 | z0..z16].
+ * Both arrays hold params.max_ticks (41) rows per environment; rows k >= ticks_dev[e] are left untouched.  Either trace
+ * pointer may be NULL; ticks_dev is required.  An analysis path (a handful of environments): not the benchmarked kernel. */
+#define SNK_LINK_POS_DIM 51
+int snk_step_trace(snk_handle* h, const float* actions_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev,
+                   int32_t* ticks_dev, float* tick_obs_dev, float* tick_links_dev, void* stream);
+
 /* n_steps env-steps in ONE launch with a linear policy per environment (ARS): before every
  * step   x = obs (+ noise[t, env, :])   xn = (x - mean) * inv_std   action = W_env xn   (then clipped as in snk_step),
  * where obs is the observation the previous step returned (the post-reset one after a done, exactly what the
@@ -175,6 +188,13 @@ int snk_tick(snk_handle* h, const float* targets_dev, int32_t n_ticks, void* str
 
 /* Observation of the current state (snake.py:209-217) without stepping. */
 int snk_observe(snk_handle* h, float* obs_dev, void* stream);
+
+/* Self-collision clearance of the current state: clearance_dev[e] = a lower bound, in metres, of the
+ * smallest distance between two cylinders of environment e that Bullet would test under URDF_USE_SELF_COLLISION
+ * (snake.py:93: all link pairs except parent-child, i.e. the 465 pairs of non-consecutive cylinders).  The step
+ * kernels do not generate self-contacts (deviation D3); a positive clearance over a run proves none was missed.
+ * Bullet's hulls are 32-gons inscribed in these cylinders plus a 0.001 margin each. */
+int snk_self_clearance(snk_handle* h, float* clearance_dev, void* stream);
 
 /* Copy the [N, SNK_STATE_STRIDE] fp32 state array out of / into the handle (device pointers). */
 int snk_get_state(snk_handle* h, float* state_dev, void* stream);

@@ -100,6 +100,21 @@ class Oracle:
                             range(threads)))
         return obs, rew, done.astype(bool), ticks
 
+    def step_trace(self, actions):
+        """Twin of ``snk_step_trace`` (mode='test' info stream, snake.py:275-278,292-293): ``step`` plus the per-tick
+        observations [n, max_ticks, 56] and link positions [n, max_ticks, 51]; rows >= ticks[e] are NaN."""
+        a = np.ascontiguousarray(actions, self.dtype).reshape(self.n, self.act_dim)
+        mt = int(self.params.max_ticks)
+        obs = np.empty((self.n, OBS_DIM), self.dtype)
+        rew = np.empty(self.n, self.dtype)
+        done = np.empty(self.n, np.uint8)
+        ticks = np.empty(self.n, np.int32)
+        tobs = np.full((self.n, mt, OBS_DIM), np.nan, self.dtype)
+        tlnk = np.full((self.n, mt, 51), np.nan, self.dtype)
+        f = self._fn("step_trace"); f.restype = ctypes.c_int
+        f(self._h, self._p(a), self._p(obs), self._p(rew), self._p(done), self._p(ticks), self._p(tobs), self._p(tlnk))
+        return obs, rew, done.astype(bool), ticks, tobs, tlnk
+
     def rollout_linear(self, weights, n_steps, mean=None, inv_std=None, noise=None, trace=False):
         w = np.ascontiguousarray(weights, self.dtype).reshape(self.n, self.act_dim, OBS_DIM)
         m = None if mean is None else np.ascontiguousarray(mean, self.dtype)
@@ -135,6 +150,13 @@ class Oracle:
         out = (ctypes.c_int64 * 4)()
         self._fn("counters")(self._h, out, ctypes.c_int(int(clear)))
         return dict(ticks=out[0], pgs_iterations=out[1], dones=out[2], nonfinite=out[3])
+
+    def self_clearance(self):
+        """Twin of ``snk_self_clearance``: lower bound [n] of the smallest distance between non-consecutive cylinders."""
+        out = np.empty(self.n, self.dtype)
+        f = self._fn("self_clearance"); f.restype = ctypes.c_int
+        f(self._h, self._p(out))
+        return out
 
     def kinematics(self, e=0):
         Rw = np.empty((17, 3, 3), self.dtype)

@@ -29,3 +29,9 @@ def _built_oracle():
 def golden():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "reference_python_task_logic.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_test_mode():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_python_test_mode.npz"))

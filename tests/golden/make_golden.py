@@ -111,7 +111,12 @@ class FakeClient:
             b = self.model.height_body[h]
             p = pw[b] + Rw[b] @ self.model.height_pt[h]
             out.append((tuple(p), (0, 0, 0, 1)))
-        return out
+        # Snake.getLinkPositions does np.array(data) on these ragged tuples (snake.py:143), which numpy >= 1.24
+        # refuses; hand the same tuples back in the object array that older numpy built implicitly
+        arr = np.empty((len(out), 2), dtype=object)
+        for i, (p, q) in enumerate(out):
+            arr[i, 0], arr[i, 1] = p, q
+        return arr
 
     def setJointMotorControlArray(self, body, joints, mode, targetPositions=None, forces=None, **k):
         self.calls += 1
@@ -181,6 +186,36 @@ def main():
     out["meta/obs_high"] = np.asarray(env.observation_space.high)
     path = os.path.join(ROOT, "tests", "golden", "reference_python_task_logic.npz")
     np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+    # mode='test' info stream (snake.py:275-278,292-293; SnakeGymEnv.py:43-44): per-tick observations and link
+    # positions recorded by the reference's own code; valid rows of all steps concatenated, `ticks` gives the split
+    tm = {}
+    for name in ("serpenoid", "terminate_q9"):
+        actions = scenario_actions()[name][:14]
+        client = FakeClient(default_params())
+        robot = ref_snake.Snake(client, "snake/snake.urdf")
+        env = ref_env.SnakeGymEnv(robot)
+        robot.mode = env.mode = "test"
+        env.reset()
+        io, lp, tk, ob_l, rw, dn = [], [], [], [], [], []
+        for a in actions:
+            ob, r, d, info = env.step(np.array(a, dtype=np.float64))
+            assert info["frames"] == [] and len(info["internal_observations"]) == len(info["link_positions"])
+            tk.append(len(info["internal_observations"]))
+            io += [np.asarray(x, np.float64) for x in info["internal_observations"]]
+            lp += [np.asarray(x, np.float64) for x in info["link_positions"]]
+            if d:
+                ob = env.reset()
+            ob_l.append(np.array(ob)); rw.append(float(r)); dn.append(bool(d))
+        tm[name + "/actions"] = np.asarray(actions, np.float64)
+        tm[name + "/ticks"] = np.asarray(tk, np.int32)
+        tm[name + "/internal_observations"] = np.asarray(io).reshape(-1, 56)
+        tm[name + "/link_positions"] = np.asarray(lp).reshape(-1, 51)
+        tm[name + "/obs"] = np.asarray(ob_l); tm[name + "/rew"] = np.asarray(rw); tm[name + "/done"] = np.asarray(dn)
+        print("test-mode %-14s steps %d ticks %d dones %d" % (name, len(actions), int(np.sum(tk)), int(np.sum(dn))))
+    path = os.path.join(ROOT, "tests", "golden", "reference_python_test_mode.npz")
+    np.savez_compressed(path, **tm)
     print("wrote", path, os.path.getsize(path), "bytes")
 
 

@@ -59,6 +59,11 @@ class Emu:
         self.lib.emu_step(self._h, self._p(a), self._p(obs), self._p(rew), self._p(done), self._p(ticks))
         return obs, rew, done.astype(bool), ticks
 
+    def link_positions(self):
+        out = np.empty((self.n, 51), np.float32)
+        self.lib.emu_link_positions(self._h, self._p(out))
+        return out
+
     def counters(self, clear=False):
         out = (ctypes.c_int64 * 4)()
         self.lib.emu_counters(self._h, out, ctypes.c_int(int(clear)))

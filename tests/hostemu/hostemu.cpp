@@ -100,6 +100,14 @@ int emu_step(Emu* h, const float* actions, float* obs, float* rew, uint8_t* done
     }
     return 0;
 }
+int emu_link_positions(Emu* h, float* out /*[n][51]*/) {
+    for (int64_t e = 0; e < h->n; e++) {
+        ExEnv env; env.st = h->state + e * 64; env.tid = 0;
+        ex_load_base(env);
+        ex_link_positions(h->T, env, out + e * 3 * NB);
+    }
+    return 0;
+}
 int emu_counters(Emu* h, int64_t out[4], int clear) {
     for (int k = 0; k < 4; k++) { out[k] = h->counters[k]; if (clear) h->counters[k] = 0; }
     return 0;

@@ -57,6 +57,18 @@ def test_fp32_core_env_steps_vs_oracle():
         assert np.median(np.abs(orr - er)[same]) < 1e-3               # reward (contact sensitive)
 
 
+def test_link_positions_core_vs_oracle(states):
+    """ex_link_positions (mode='test' info stream) vs the oracle's forward kinematics on rollout states."""
+    o, s, tg = states
+    e = ep.Emu(o.n, default_params(motor_solver=1))
+    e.set_state(s); o.set_state(s)
+    lp = e.link_positions()
+    for env in (0, 17, 255):
+        Rw, pw, _ = o.kinematics(env)
+        want = np.stack([pw[b] + Rw[b] @ o.model.height_pt[b] for b in range(17)]).T.reshape(-1)
+        assert np.abs(lp[env] - want).max() < 2e-6
+
+
 def test_fp64_core_matches_oracle_to_roundoff(states):
     """The same core compiled in fp64 (-DEMU_DOUBLE): the world-frame / centre-of-mass formulation of the
     kernel equals the oracle's body-frame formulation up to round-off amplified by the solver."""
