@@ -64,7 +64,11 @@ template <bool CONE, class Rows, bool TRACE = false>
 __device__ __forceinline__ void run_warp(const KParams& P, const Rows& R, float* __restrict__ state, const float* __restrict__ actions,
                                          float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks,
                                          unsigned long long* __restrict__ counters, const int32_t* __restrict__ order, int64_t n,
-                                         float* __restrict__ tick_obs = nullptr, float* __restrict__ tick_links = nullptr) {
+                                         int64_t first_base, int64_t dyn_base, float* __restrict__ tick_obs = nullptr,
+                                         float* __restrict__ tick_links = nullptr) {
+    // Hand-out positions: the warp's first 32 are static, [first_base, first_base + 32), laid out warp-major over the
+    // grid by the caller so that a batch smaller than the grid's lanes spreads over all SMs (one warp per scheduler
+    // before a second one anywhere); every later position comes from the global counter, which starts at dyn_base.
     const int lane = R.lane;
     const unsigned lt_mask = (1u << lane) - 1u;
     ExEnv e; // a lane without an environment computes (masked) on record 0 in the rest pose
@@ -81,14 +85,18 @@ __device__ __forceinline__ void run_warp(const KParams& P, const Rows& R, float*
     bool have = false;
     unsigned long long c_ticks = 0, c_iters = 0;
     unsigned c_done = 0, c_bad = 0;
+    bool first = true;
 #pragma unroll 1
     for (;;) {
-        // ---- lanes without an environment take the next ones from the global counter
+        // ---- lanes without an environment take the next ones (first: the static positions, then the global counter)
         const unsigned need = __ballot_sync(FULL, !have);
         if (need) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&counters[4], (unsigned long long)__popc(need));
-            base = __shfl_sync(FULL, base, 0);
+            unsigned long long base = (unsigned long long)first_base;
+            if (!first) {
+                if (lane == 0) base = (unsigned long long)dyn_base + atomicAdd(&counters[4], (unsigned long long)__popc(need));
+                base = __shfl_sync(FULL, base, 0);
+            }
+            first = false;
             if (!have) {
                 const int64_t cand = (int64_t)base + __popc(need & lt_mask);
                 if (cand < n) {
@@ -201,7 +209,7 @@ __device__ __forceinline__ void policy_targets(const KParams& P, const Rows& R, 
 // counters: [4] tickets handed out, [5] pushes done.
 template <bool CONE, class Rows>
 __device__ __forceinline__ void run_rollout_warp(const KParams& P, const Rows& R, float* __restrict__ state, const RolloutArgs A,
-                                                 unsigned long long* __restrict__ counters, int64_t n) {
+                                                 unsigned long long* __restrict__ counters, int64_t n, int64_t first_base, int64_t dyn_base) {
     const int lane = R.lane;
     const unsigned lt_mask = (1u << lane) - 1u;
     const long long total = (long long)n * A.n_steps;
@@ -217,7 +225,7 @@ __device__ __forceinline__ void run_rollout_warp(const KParams& P, const Rows& R
     run.xprev = 0.f; run.e2 = 0.f; run.height = 0.f; run.counter = 0; run.iters = 0; run.end_height = false; run.have_height = false;
     int64_t env = -1;
     long long ticket = -1;    // >= 0: waiting for that ticket's environment
-    bool have = false, exhausted = false;
+    bool have = false, exhausted = false, first = true;
     int t = 0;
     unsigned long long c_ticks = 0, c_iters = 0;
     unsigned c_done = 0, c_bad = 0;
@@ -225,9 +233,13 @@ __device__ __forceinline__ void run_rollout_warp(const KParams& P, const Rows& R
     for (;;) {
         // ---- idle lanes draw tickets
         const unsigned need = __ballot_sync(FULL, !have && ticket < 0 && !exhausted);
-        if (need) {
+        if (first) { // static first tickets, warp-major over the grid (see run_warp); the counter starts at dyn_base <= n
+            first = false;
+            const long long k = (long long)first_base + lane;
+            if (k < n) ticket = k;
+        } else if (need) {
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&counters[4], (unsigned long long)__popc(need));
+            if (lane == 0) base = (unsigned long long)dyn_base + atomicAdd(&counters[4], (unsigned long long)__popc(need));
             base = __shfl_sync(FULL, base, 0);
             if (!have && ticket < 0 && !exhausted) {
                 const long long k = (long long)base + __popc(need & lt_mask);
@@ -298,17 +310,19 @@ snk_exact_rollout_kernel(const KParams P, float* __restrict__ state, const Rollo
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tbase = S.tmem_base;
+    const int64_t first_base = ((int64_t)warp * gridDim.x + blockIdx.x) * 32;
+    const int64_t dyn_base = min((int64_t)gridDim.x * (TWARPS + SWARPS) * 32, n);
     if (warp < TWARPS) {
         RowsT R;
         R.taddr = tbase + ((uint32_t)(32 * warp) << 16);
         R.s = &S.t[warp];
         R.lane = lane;
-        run_rollout_warp<CONE>(P, R, state, A, counters, n);
+        run_rollout_warp<CONE>(P, R, state, A, counters, n, first_base, dyn_base);
     } else {
         RowsS R;
         R.s = &S.s[warp - TWARPS];
         R.lane = lane;
-        run_rollout_warp<CONE>(P, R, state, A, counters, n);
+        run_rollout_warp<CONE>(P, R, state, A, counters, n, first_base, dyn_base);
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
@@ -320,7 +334,7 @@ template <bool CONE>
 __global__ void __launch_bounds__((TWARPS + SWARPS) * 32, 1)
 snk_exact_step_kernel(const KParams P, float* __restrict__ state, const float* __restrict__ actions, float* __restrict__ obs,
                       float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks, unsigned long long* __restrict__ counters,
-                      const int32_t* __restrict__ order, int64_t n, int active_warps) {
+                      const int32_t* __restrict__ order, int64_t n, int active_warps, int spread) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StepSmem& S = *reinterpret_cast<StepSmem*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -333,6 +347,9 @@ snk_exact_step_kernel(const KParams P, float* __restrict__ state, const float* _
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tbase = S.tmem_base;
+    // warp-major: tensor-memory warps fill first (spread = 0, SNK_EXACT_SPREAD=0: CTA-major, the ablation)
+    const int64_t first_base = spread ? ((int64_t)warp * gridDim.x + blockIdx.x) * 32 : ((int64_t)blockIdx.x * active_warps + warp) * 32;
+    const int64_t dyn_base = min((int64_t)gridDim.x * active_warps * 32, n);
     if (warp >= active_warps) {
         // ablation switch (SNK_EXACT_WARPS): this warp takes no environments
     } else if (warp < TWARPS) {
@@ -340,12 +357,12 @@ snk_exact_step_kernel(const KParams P, float* __restrict__ state, const float* _
         R.taddr = tbase + ((uint32_t)(32 * warp) << 16);
         R.s = &S.t[warp];
         R.lane = lane;
-        run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, order, n);
+        run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, order, n, first_base, dyn_base);
     } else {
         RowsS R;
         R.s = &S.s[warp - TWARPS];
         R.lane = lane;
-        run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, order, n);
+        run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, order, n, first_base, dyn_base);
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
@@ -363,7 +380,7 @@ snk_exact_step_kernel_smem(const KParams P, float* __restrict__ state, const flo
     RowsS R;
     R.s = reinterpret_cast<RowsSmemStore*>(smem_raw);
     R.lane = threadIdx.x;
-    run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, order, n);
+    run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, order, n, (int64_t)blockIdx.x * EB, min((int64_t)gridDim.x * EB, n));
 }
 
 // the env-step with the mode='test' info stream (snk_step_trace): an analysis path for a handful of environments,
@@ -377,7 +394,8 @@ snk_exact_step_trace_kernel(const KParams P, float* __restrict__ state, const fl
     RowsS R;
     R.s = reinterpret_cast<RowsSmemStore*>(smem_raw);
     R.lane = threadIdx.x;
-    run_warp<CONE, RowsS, true>(P, R, state, actions, obs, rew, done, ticks, counters, nullptr, n, tick_obs, tick_links);
+    run_warp<CONE, RowsS, true>(P, R, state, actions, obs, rew, done, ticks, counters, nullptr, n, (int64_t)blockIdx.x * EB,
+                                min((int64_t)gridDim.x * EB, n), tick_obs, tick_links);
 }
 
 // n_ticks raw ticks with explicit targets[N,16] (gait script): every environment runs the same number of
@@ -487,6 +505,7 @@ __global__ void snk_exact_order_kernel(int64_t n, const uint8_t* __restrict__ bu
 static int g_sms = 0, g_smem_ctas = 0;
 static bool g_rows_tmem = true; // SNK_EXACT_ROWS=smem selects the shared-memory-only variant
 static bool g_no_sort = false; // SNK_EXACT_ORDER=index disables the longest-first hand-out (ablation)
+static bool g_spread = true; // SNK_EXACT_SPREAD=0: fill SM after SM instead of spreading a small batch over all SMs (ablation)
 static int g_active_warps = TWARPS + SWARPS; // SNK_EXACT_WARPS=1..6: ablation of the number of working warps per SM
 
 size_t snk_exact_smem_bytes() { return g_rows_tmem ? sizeof(StepSmem) : sizeof(RowsSmemStore); }
@@ -509,6 +528,8 @@ cudaError_t snk_exact_configure(const ExTables* host_tables) {
     g_rows_tmem = !(v && v[0] == 's');
     const char* so = getenv("SNK_EXACT_ORDER");
     g_no_sort = so && so[0] == 'i';
+    const char* sp = getenv("SNK_EXACT_SPREAD");
+    g_spread = !(sp && sp[0] == '0');
     const char* w = getenv("SNK_EXACT_WARPS");
     if (w && atoi(w) >= 1 && atoi(w) <= TWARPS + SWARPS) g_active_warps = atoi(w);
     cudaError_t e = cudaMemcpyToSymbol(cT, host_tables, sizeof(ExTables));
@@ -549,10 +570,11 @@ cudaError_t snk_exact_launch_step(const KParams& P, float* state, const float* a
     }
     if (g_rows_tmem) {
         const int per_cta = (TWARPS + SWARPS) * 32;
-        const int64_t want = (n + per_cta - 1) / per_cta;
+        // a small batch gets one CTA per warp of environments: all SMs before a second warp per SM
+        const int64_t want = g_spread ? (n + EB - 1) / EB : (n + per_cta - 1) / per_cta;
         dim3 grid((unsigned)(want < g_sms ? want : g_sms)), block(per_cta);
-        if (P.cone) snk_exact_step_kernel<true><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n, g_active_warps);
-        else snk_exact_step_kernel<false><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n, g_active_warps);
+        if (P.cone) snk_exact_step_kernel<true><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n, g_active_warps, (int)g_spread);
+        else snk_exact_step_kernel<false><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n, g_active_warps, (int)g_spread);
     } else {
         const int64_t warps = (n + EB - 1) / EB;
         dim3 grid((unsigned)(warps < g_smem_ctas ? warps : g_smem_ctas)), block(EB);
@@ -578,7 +600,7 @@ cudaError_t snk_exact_launch_rollout(const KParams& P, float* state, const float
     A.weights = weights; A.mean = mean; A.inv_std = inv_std; A.noise = noise; A.returns = returns; A.trace = trace; A.n_steps = n_steps;
     A.queue = queue; A.done_steps = done_steps;
     const int per_cta = (TWARPS + SWARPS) * 32;
-    const int64_t want = (n + per_cta - 1) / per_cta;
+    const int64_t want = (n + EB - 1) / EB;
     dim3 grid((unsigned)(want < g_sms ? want : g_sms)), block(per_cta);
     if (P.cone) snk_exact_rollout_kernel<true><<<grid, block, sizeof(StepSmem), st>>>(P, state, A, counters, n);
     else snk_exact_rollout_kernel<false><<<grid, block, sizeof(StepSmem), st>>>(P, state, A, counters, n);
