@@ -54,8 +54,8 @@ class SnakeGymEnv:
         self.action_space = self._vec.action_space
         self._observation = None
 
-    def reset(self, hardReset=False):
-        self._observation = self._vec.reset()[0]
+    def reset(self, hardReset=False):  # SnakeGymEnv.py:28-31
+        self._observation = self._vec.reset(hard=bool(hardReset))[0]
         return self._observation
 
     def step(self, action):

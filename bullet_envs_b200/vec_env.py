@@ -100,10 +100,19 @@ class SnakeVecEnv:
             raise RuntimeError("SnakeVecEnv is closed")
 
     # ------------------------------------------------------------------ SubprocVecEnv surface
-    def reset(self, mask=None, as_torch=False):
-        """Soft reset (``snake.py:119-127``) of all environments (or of ``mask``); returns obs [N,56]."""
+    def reset(self, mask=None, as_torch=False, hard=False):
+        """Soft reset (``snake.py:119-127``) of all environments (or of ``mask``); returns obs [N,56].  ``hard=True`` is
+        ``Snake.reset(hardReset=True)`` (``snake.py:88-95``): the world is rebuilt, so the applied-torque / reaction-force
+        slots that a soft reset leaves stale read zero as well."""
         self._check_open()
         torch = self._torch
+        if hard:
+            st = self.get_state()
+            m = torch.ones(self.num_envs, dtype=torch.bool, device=self.device) if mask is None else \
+                torch.as_tensor(np.asarray(mask) if not torch.is_tensor(mask) else mask, device=self.device).bool()
+            st[m] = 0.0
+            st[m, 6] = 1.0  # SNK_S_QUAT + 3
+            self.set_state(st)
         if as_torch or (mask is not None and torch.is_tensor(mask) and mask.is_cuda):
             obs = torch.empty((self.num_envs, OBS_DIM), dtype=torch.float32, device=self.device)
             m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()

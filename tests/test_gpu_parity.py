@@ -286,6 +286,10 @@ def test_single_env_facade_and_vec_surface(torch):
     assert abs(ob[1] - np.pi / 6) < 0.06 and abs(ob[3] + np.pi / 6) < 0.06   # driven (odd) joints reach the clipped targets
     assert env.render().size == 0
     assert env.robot.calculateEnergy(ob) == pytest.approx(float(np.sum(ob[16:32] * ob[32:48] * 0.01)))
+    soft = env.reset()
+    assert np.abs(soft[32:48]).max() > 0 and np.allclose(soft[:32], 0)        # Q9: a soft reset keeps the last applied torques
+    hard = env.reset(hardReset=True)                                          # snake.py:88-95: world rebuilt, nothing stale
+    assert np.allclose(hard[:54], 0) and hard[54] == 1.0 and hard[55] == 0.0
     env.close()
     vec = SnakeVecEnv([None] * 16)                              # constructed from a list of env thunks, like SubprocVecEnv
     assert len(vec) == 16 and vec.num_envs == vec.nenvs == 16
