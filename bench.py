@@ -281,7 +281,7 @@ def run_ours(args):
             "pgs_sweeps_per_tick_last_step": stats[1].item() / max(1.0, stats[2].item()),
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(total * 8 * 4),
                     "d2h_bytes_per_step": int(total * (56 * 4 + 4 + 1 + 4)), "steps": Ke,
-                    "call": "SnakeVecEnv(obs_dtype=float32, pinned_io=True).step(numpy) -> snk_step_host (pinned DMA of actions/obs/reward/done/ticks + kernel + sync)",
+                    "call": "SnakeVecEnv(obs_dtype=float32, pinned_io=True).step(numpy) -> snk_step_host: the step's actions are copied into page-locked host memory, the kernel reads each environment's action row from it and posts obs/reward/done/ticks rows back to page-locked host memory over PCIe as environments finish (mapped host buffers, no staging copy), then a stream sync",
                     "value_strict_dropin": e2e_strict,
                     "call_strict_dropin": "SnakeVecEnv().step(numpy): fresh pageable float64 arrays per step, staged through the library's pinned buffers"},
             "gpu_launches": int(gpu_launches),

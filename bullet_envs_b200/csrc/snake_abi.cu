@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -165,6 +166,7 @@ int snk_create(const snk_model* model, const snk_params* params, int64_t n_envs,
 int snk_destroy(snk_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
+    if (h->hstream && !h->staged) { cudaStreamSynchronize(h->hstream); cudaStreamDestroy(h->hstream); }
     if (h->staged) {
         cudaStreamSynchronize(h->hstream);
         cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_done); cudaFreeHost(h->h_ticks);
@@ -256,10 +258,16 @@ int snk_tick(snk_handle* h, const float* targets_dev, int32_t n_ticks, void* str
     return 0;
 }
 
+static int ensure_stream(snk_handle* h) {
+    if (!h->hstream) CU(cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+    return 0;
+}
+
 static int ensure_staging(snk_handle* h) {
     if (h->staged) return 0;
     size_t n = (size_t)h->n;
-    CU(cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+    int rc0 = ensure_stream(h);
+    if (rc0) return rc0;
     CU(cudaMallocHost(&h->h_act, n * NJ * sizeof(float)));
     CU(cudaMallocHost(&h->h_obs, n * SNK_OBS_DIM * sizeof(float)));
     CU(cudaMallocHost(&h->h_rew, n * sizeof(float)));
@@ -278,22 +286,43 @@ static int ensure_staging(snk_handle* h) {
 
 // true when `p` is page-locked host memory known to CUDA (cudaMallocHost / cudaHostRegister / torch pinned):
 // such a buffer is the DMA source/target itself and needs no staging copy
-static bool is_pinned(const void* p) {
+static bool is_pinned(const void* p, void** dev = nullptr) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (dev) *dev = a.devicePointer;
     return a.type == cudaMemoryTypeHost;
+}
+
+// SNK_HOST_ZEROCOPY=0 disables the mapped-host-memory path of snk_step_host (ablation)
+static bool zero_copy_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SNK_HOST_ZEROCOPY"); v = !(e && e[0] == '0'); }
+    return v != 0;
 }
 
 int snk_step_host(snk_handle* h, const float* actions_host, float* obs_host, float* rew_host, uint8_t* done_host, int32_t* ticks_host) {
     if (!h || !actions_host || !obs_host || !rew_host || !done_host) return fail(SNK_E_ARG, "snk_step_host: null pointer%s");
     CU(cudaSetDevice(h->device));
+    void *da = nullptr, *dob = nullptr, *dr = nullptr, *dd = nullptr, *dt = nullptr;
+    const bool pa = is_pinned(actions_host, &da), po = is_pinned(obs_host, &dob), pr = is_pinned(rew_host, &dr), pd = is_pinned(done_host, &dd),
+               pt = ticks_host && is_pinned(ticks_host, &dt);
+    if (zero_copy_enabled() && pa && po && pr && pd && (!ticks_host || pt) && da && dob && dr && dd && (!ticks_host || dt)) {
+        // Every caller buffer is page-locked and mapped: the kernel reads the 32 B action row of an environment straight from
+        // host memory when a lane takes it and posts the observation row / reward / done / ticks straight back over PCIe when
+        // the environment finishes, spread over the whole launch -- no copy before or after the kernel.
+        int rc0 = ensure_stream(h);
+        if (rc0) return rc0;
+        cudaStream_t zs = h->hstream;
+        CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), zs));
+        CU(launch_step(h, (const float*)da, (float*)dob, (float*)dr, (uint8_t*)dd, (int32_t*)dt, zs));
+        CU(cudaStreamSynchronize(zs));
+        return 0;
+    }
     int rc = ensure_staging(h);
     if (rc) return rc;
     size_t n = (size_t)h->n, na = n * h->P.actdim * sizeof(float);
     cudaStream_t st = h->hstream;
-    // pageable caller buffers go through the handle's pinned staging buffers; pinned ones are used directly
-    const bool pa = is_pinned(actions_host), po = is_pinned(obs_host), pr = is_pinned(rew_host), pd = is_pinned(done_host),
-               pt = ticks_host && is_pinned(ticks_host);
+    // pageable caller buffers go through the handle's pinned staging buffers; pinned ones are DMA sources / targets themselves
     if (!pa) memcpy(h->h_act, actions_host, na);
     CU(cudaMemcpyAsync(h->d_act, pa ? actions_host : h->h_act, na, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));

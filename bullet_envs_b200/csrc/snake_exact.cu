@@ -47,12 +47,18 @@ __device__ __forceinline__ void load_targets(const KParams& P, const Rows& R, co
 #pragma unroll
     for (int j = 0; j < NJ; j++) R.tgt(j) = 0.f;
 #pragma unroll 1
-    for (int k = 0; k < P.actdim; k++) {
-        float a = act[k];
-        a = (a < -1.f) ? -1.f : a; // checkBound's comparisons: a NaN passes through (SnakeGymEnv.py:84-87)
-        a = (a > 1.f) ? 1.f : a;
-        const int j = (P.gait == 0) ? 2 * k : (P.gait == 1) ? 2 * k + 1 : k;
-        R.tgt(j) = a * P.sf;
+    for (int k4 = 0; k4 < P.actdim; k4 += 4) { // act_dim is 8 or 16: the row is read as 16 B vectors (it may live in mapped host memory)
+        const float4 v = *reinterpret_cast<const float4*>(act + k4);
+        const float av[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = k4 + q;
+            float a = av[q];
+            a = (a < -1.f) ? -1.f : a; // checkBound's comparisons: a NaN passes through (SnakeGymEnv.py:84-87)
+            a = (a > 1.f) ? 1.f : a;
+            const int j = (P.gait == 0) ? 2 * k : (P.gait == 1) ? 2 * k + 1 : k;
+            R.tgt(j) = a * P.sf;
+        }
     }
 }
 
