@@ -283,7 +283,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(total * (56 * 4 + 4 + 1 + 4)), "steps": Ke,
                     "call": "SnakeVecEnv(obs_dtype=float32, pinned_io=True).step(numpy) -> snk_step_host: the step's actions are copied into page-locked host memory, the kernel reads each environment's action row from it and posts obs/reward/done/ticks rows back to page-locked host memory over PCIe as environments finish (mapped host buffers, no staging copy), then a stream sync",
                     "value_strict_dropin": e2e_strict,
-                    "call_strict_dropin": "SnakeVecEnv().step(numpy): fresh pageable float64 arrays per step, staged through the library's pinned buffers"},
+                    "call_strict_dropin": "SnakeVecEnv().step(numpy) -> snk_step_host_f64: float64 actions in, fresh pageable float64 obs/reward arrays out every step (the reference's dtypes), narrowed / widened by the library's host threads around the kernel on its mapped pinned buffers"},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_ENV * n, "traffic_source": "ncu capture at 2^20 envs, scaled per environment",

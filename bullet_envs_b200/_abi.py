@@ -104,6 +104,7 @@ def load_library():
     lib.snk_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.snk_step_trace.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.snk_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.snk_step_host_f64.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.snk_reset_host.argtypes = [vp, vp, vp]
     lib.snk_tick.argtypes = [vp, vp, i32, vp]
     lib.snk_rollout_linear.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]

@@ -10,6 +10,8 @@
 #include <string.h>
 
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "snake_host.h"
 
@@ -82,6 +84,31 @@ static cudaError_t launch_step(snk_handle* h, const float* act, float* obs, floa
                              : snk_pgs_launch_step(h->T, h->P, h->state, act, obs, rew, done, ticks, h->counters, h->n, st);
     h->launches += launches;
     return e;
+}
+
+// host-side worker threads of the float64 entry point (SNK_HOST_THREADS, default min(hardware threads, 16))
+static int host_threads() {
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("SNK_HOST_THREADS");
+        int hw = (int)std::thread::hardware_concurrency();
+        v = e ? atoi(e) : (hw > 16 ? 16 : hw);
+        if (v < 1) v = 1;
+    }
+    return v;
+}
+template <class F>
+static void parallel_chunks(size_t n, F f) { // f(begin, end) over [0, n) on host_threads() threads
+    const int nt = (n < (size_t)1 << 16) ? 1 : host_threads();
+    if (nt == 1) { f((size_t)0, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; t++) {
+        const size_t b = (size_t)t * per, e = b + per < n ? b + per : n;
+        if (b >= e) break;
+        th.emplace_back([=] { f(b, e); });
+    }
+    for (auto& x : th) x.join();
 }
 
 extern "C" {
@@ -336,6 +363,39 @@ int snk_step_host(snk_handle* h, const float* actions_host, float* obs_host, flo
     if (!pr) memcpy(rew_host, h->h_rew, n * sizeof(float));
     if (!pd) memcpy(done_host, h->h_done, n);
     if (ticks_host && !pt) memcpy(ticks_host, h->h_ticks, n * sizeof(int32_t));
+    return 0;
+}
+
+// The call the reference's numpy callers make (ppo/train.py:122, ars/train.py:99): float64 arrays in and out, as
+// SubprocVecEnv.step returns them.  Actions are narrowed into the handle's page-locked buffer, the kernel runs on the
+// mapped page-locked buffers (see snk_step_host), and the results are widened into the caller's arrays by a few threads.
+int snk_step_host_f64(snk_handle* h, const double* actions_host, double* obs_host, double* rew_host, uint8_t* done_host, int32_t* ticks_host) {
+    if (!h || !actions_host || !obs_host || !rew_host || !done_host) return fail(SNK_E_ARG, "snk_step_host_f64: null pointer%s");
+    CU(cudaSetDevice(h->device));
+    int rc = ensure_staging(h);
+    if (rc) return rc;
+    const size_t n = (size_t)h->n, na = n * h->P.actdim;
+    float* ha = h->h_act;
+    parallel_chunks(na, [=](size_t b, size_t e) { for (size_t i = b; i < e; i++) ha[i] = (float)actions_host[i]; });
+    cudaStream_t st = h->hstream;
+    CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
+    if (zero_copy_enabled()) {
+        CU(launch_step(h, h->h_act, h->h_obs, h->h_rew, h->h_done, h->h_ticks, st)); // cudaMallocHost memory is mapped (UVA)
+    } else {
+        CU(cudaMemcpyAsync(h->d_act, h->h_act, na * sizeof(float), cudaMemcpyHostToDevice, st));
+        CU(launch_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_ticks, st));
+        CU(cudaMemcpyAsync(h->h_obs, h->d_obs, n * SNK_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h->h_rew, h->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h->h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h->h_ticks, h->d_ticks, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    const float* ho = h->h_obs;
+    parallel_chunks(n * SNK_OBS_DIM, [=](size_t b, size_t e) { for (size_t i = b; i < e; i++) obs_host[i] = (double)ho[i]; });
+    const float* hr = h->h_rew;
+    parallel_chunks(n, [=](size_t b, size_t e) { for (size_t i = b; i < e; i++) rew_host[i] = (double)hr[i]; });
+    memcpy(done_host, h->h_done, n);
+    if (ticks_host) memcpy(ticks_host, h->h_ticks, n * sizeof(int32_t));
     return 0;
 }
 

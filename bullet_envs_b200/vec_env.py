@@ -178,13 +178,16 @@ class SnakeVecEnv:
                 a[...] = np.asarray(actions).reshape(self.num_envs, self.act_dim)
                 obs, rew, done, ticks = (self._pin[k] for k in ("obs", "rew", "done", "ticks"))
             else:
-                a = np.ascontiguousarray(np.asarray(actions), np.float32).reshape(self.num_envs, self.act_dim)
-                obs = np.empty((self.num_envs, OBS_DIM), np.float32)
-                rew = np.empty(self.num_envs, np.float32)
+                f64 = np.dtype(self.obs_dtype) == np.float64  # the reference's dtypes: snk_step_host_f64 converts on its threads
+                dt = np.float64 if f64 else np.float32
+                a = np.ascontiguousarray(np.asarray(actions), dt).reshape(self.num_envs, self.act_dim)
+                obs = np.empty((self.num_envs, OBS_DIM), dt)
+                rew = np.empty(self.num_envs, dt)
                 done = np.empty(self.num_envs, np.uint8)
                 ticks = np.empty(self.num_envs, np.int32)
             p = lambda x: ctypes.c_void_p(x.ctypes.data)
-            _abi.check(self._lib.snk_step_host(self._h, p(a), p(obs), p(rew), p(done), p(ticks)), self._lib)
+            fn = self._lib.snk_step_host_f64 if obs.dtype == np.float64 else self._lib.snk_step_host
+            _abi.check(fn(self._h, p(a), p(obs), p(rew), p(done), p(ticks)), self._lib)
             self._pending = ("numpy", obs, rew, done, ticks, self._infos)
         self.waiting = True
 

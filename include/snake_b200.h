@@ -162,6 +162,12 @@ int snk_step_host(snk_handle* h, const float* actions_host, float* obs_host, flo
                   uint8_t* done_host, int32_t* ticks_host);
 int snk_reset_host(snk_handle* h, const uint8_t* mask_host, float* obs_host);
 
+/* snk_step_host with the reference's own dtypes: float64 actions in, float64 obs / reward out, exactly the arrays
+ * SubprocVecEnv.step exchanges with ppo/train.py:122 and ars/train.py:99 (np.stack of the workers' float64 results,
+ * ppo/multiprocessing_env.py:126-128).  The narrowing / widening runs on a few host threads (SNK_HOST_THREADS). */
+int snk_step_host_f64(snk_handle* h, const double* actions_host, double* obs_host, double* rew_host,
+                      uint8_t* done_host, int32_t* ticks_host);
+
 /* snk_step plus the mode='test' info stream of the reference (snake.py:275-278,292-293; SnakeGymEnv.py:43-44): for every
  * physics tick k < ticks_dev[e] of environment e, the observation after that tick (info['internal_observations'][k]) goes to
  * tick_obs_dev[e][k][0..55] and the world COM positions of URDF links arange(0,49,3) (info['link_positions'][k],
