@@ -91,7 +91,7 @@ __device__ __forceinline__ void run_warp(const KParams& P, const Rows& R, float*
     bool have = false;
     unsigned long long c_ticks = 0, c_iters = 0;
     unsigned c_done = 0, c_bad = 0;
-    bool first = true;
+    bool first = first_base >= 0; // a negative first_base: no static wave
 #pragma unroll 1
     for (;;) {
         // ---- lanes without an environment take the next ones (first: the static positions, then the global counter)
@@ -353,9 +353,12 @@ snk_exact_step_kernel(const KParams P, float* __restrict__ state, const float* _
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tbase = S.tmem_base;
-    // warp-major: tensor-memory warps fill first (spread = 0, SNK_EXACT_SPREAD=0: CTA-major, the ablation)
-    const int64_t first_base = spread ? ((int64_t)warp * gridDim.x + blockIdx.x) * 32 : ((int64_t)blockIdx.x * active_warps + warp) * 32;
-    const int64_t dyn_base = min((int64_t)gridDim.x * active_warps * 32, n);
+    // first wave (SNK_EXACT_SPREAD): 3 (default) = warp-major, the two warps that have a scheduler to themselves (2, 3)
+    // first -- with the longest-first order the longest env-steps of the launch go to the fastest warps; 1 = warp-major in
+    // warp-index order; 0 = CTA-major; 2 = no static wave, everything from the global counter (ablations)
+    const int rank = (spread == 3) ? ((warp == 2) ? 0 : (warp == 3) ? 1 : (warp == 0) ? 2 : (warp == 1) ? 3 : warp) : warp;
+    const int64_t first_base = (spread == 2) ? -1 : (spread ? ((int64_t)rank * gridDim.x + blockIdx.x) * 32 : ((int64_t)blockIdx.x * active_warps + warp) * 32);
+    const int64_t dyn_base = (spread == 2) ? 0 : min((int64_t)gridDim.x * active_warps * 32, n);
     if (warp >= active_warps) {
         // ablation switch (SNK_EXACT_WARPS): this warp takes no environments
     } else if (warp < TWARPS) {
@@ -511,7 +514,7 @@ __global__ void snk_exact_order_kernel(int64_t n, const uint8_t* __restrict__ bu
 static int g_sms = 0, g_smem_ctas = 0;
 static bool g_rows_tmem = true; // SNK_EXACT_ROWS=smem selects the shared-memory-only variant
 static bool g_no_sort = false; // SNK_EXACT_ORDER=index disables the longest-first hand-out (ablation)
-static bool g_spread = true; // SNK_EXACT_SPREAD=0: fill SM after SM instead of spreading a small batch over all SMs (ablation)
+static int g_spread = 3; // SNK_EXACT_SPREAD: first-wave hand-out policy (see snk_exact_step_kernel)
 static int g_active_warps = TWARPS + SWARPS; // SNK_EXACT_WARPS=1..6: ablation of the number of working warps per SM
 
 size_t snk_exact_smem_bytes() { return g_rows_tmem ? sizeof(StepSmem) : sizeof(RowsSmemStore); }
@@ -535,7 +538,7 @@ cudaError_t snk_exact_configure(const ExTables* host_tables) {
     const char* so = getenv("SNK_EXACT_ORDER");
     g_no_sort = so && so[0] == 'i';
     const char* sp = getenv("SNK_EXACT_SPREAD");
-    g_spread = !(sp && sp[0] == '0');
+    g_spread = (sp && sp[0] >= '0' && sp[0] <= '3') ? sp[0] - '0' : 3;
     const char* w = getenv("SNK_EXACT_WARPS");
     if (w && atoi(w) >= 1 && atoi(w) <= TWARPS + SWARPS) g_active_warps = atoi(w);
     cudaError_t e = cudaMemcpyToSymbol(cT, host_tables, sizeof(ExTables));
@@ -577,10 +580,10 @@ cudaError_t snk_exact_launch_step(const KParams& P, float* state, const float* a
     if (g_rows_tmem) {
         const int per_cta = (TWARPS + SWARPS) * 32;
         // a small batch gets one CTA per warp of environments: all SMs before a second warp per SM
-        const int64_t want = g_spread ? (n + EB - 1) / EB : (n + per_cta - 1) / per_cta;
+        const int64_t want = (g_spread == 1 || g_spread == 3) ? (n + EB - 1) / EB : (n + per_cta - 1) / per_cta;
         dim3 grid((unsigned)(want < g_sms ? want : g_sms)), block(per_cta);
-        if (P.cone) snk_exact_step_kernel<true><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n, g_active_warps, (int)g_spread);
-        else snk_exact_step_kernel<false><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n, g_active_warps, (int)g_spread);
+        if (P.cone) snk_exact_step_kernel<true><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n, g_active_warps, g_spread);
+        else snk_exact_step_kernel<false><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n, g_active_warps, g_spread);
     } else {
         const int64_t warps = (n + EB - 1) / EB;
         dim3 grid((unsigned)(warps < g_smem_ctas ? warps : g_smem_ctas)), block(EB);

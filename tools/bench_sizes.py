@@ -32,7 +32,7 @@ def main():
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
         print(json.dumps({"envs": n, "ms_per_step": round(ms, 4), "env_steps_per_s": round(n / ms * 1e3, 1),
-                          "spread": os.environ.get("SNK_EXACT_SPREAD", "1")}), flush=True)
+                          "spread": os.environ.get("SNK_EXACT_SPREAD", "3")}), flush=True)
         env.close()
 
 
