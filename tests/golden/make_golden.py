@@ -218,6 +218,26 @@ def main():
     np.savez_compressed(path, **tm)
     print("wrote", path, os.path.getsize(path), "bytes")
 
+    # raw single-env use (no vector wrapper; a3c/agent.py:99-125 keeps stepping after `done`): SnakeGymEnv.step returns the
+    # TERMINAL observation and the next step's reward uses the dead episode's x as x_prev
+    raw = {}
+    for name in ("serpenoid", "clipped"):
+        actions = scenario_actions()[name]
+        client = FakeClient(default_params())
+        robot = ref_snake.Snake(client, "snake/snake.urdf")
+        env = ref_env.SnakeGymEnv(robot)
+        ob0 = env.reset()
+        ob_l, rw, dn = [np.array(ob0)], [], []
+        for a in actions:
+            ob, r, d, info = env.step(np.array(a, dtype=np.float64))   # NO reset by the caller
+            ob_l.append(np.array(ob)); rw.append(float(r)); dn.append(bool(d))
+        raw[name + "/actions"] = np.asarray(actions, np.float64)
+        raw[name + "/obs"] = np.asarray(ob_l); raw[name + "/rew"] = np.asarray(rw); raw[name + "/done"] = np.asarray(dn)
+        print("raw single-env %-12s steps %d dones %d return %.4f" % (name, len(actions), int(np.sum(dn)), float(np.sum(rw))))
+    path = os.path.join(ROOT, "tests", "golden", "reference_python_raw_single_env.npz")
+    np.savez_compressed(path, **raw)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
 
 if __name__ == "__main__":
     main()

@@ -143,3 +143,32 @@ def test_no_self_contact_is_missed_over_a_rollout(torch):
         worst = torch.minimum(worst, env.self_clearance().min())
     assert float(worst) > 0.015, float(worst)
     env.close()
+
+
+def test_facade_raw_single_env_semantics_vs_reference_python(torch):
+    """SnakeGymEnv (the facade) behaves like the reference class used without the vector wrapper (a3c/agent.py:99-125):
+    on done it returns the terminal observation and the next reward uses the dead episode's x.  Golden: the reference's own Python
+    stepping on after done (tests/golden/reference_python_raw_single_env.npz); free running, so contact-sensitive values are
+    compared with tolerances and the joints (motor law) to round-off while the tick counts agree."""
+    import os
+    from bullet_envs_b200 import SnakeGymEnv
+    g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "reference_python_raw_single_env.npz"))
+    env = SnakeGymEnv()
+    wrap = SnakeGymEnv(raw_semantics=False)
+    env.reset(); wrap.reset()
+    acts, G_ob, G_r, G_d = g["clipped/actions"], g["clipped/obs"], g["clipped/rew"], g["clipped/done"]
+    n_done = 0
+    for t, a in enumerate(acts):
+        ob, r, d, info = env.step(np.array(a))
+        wob, wr, wd, _ = wrap.step(np.array(a))
+        assert d == bool(G_d[t]) == wd
+        assert np.abs(ob[:16] - G_ob[t + 1][:16]).max() < 1e-4
+        assert abs(r - G_r[t]) < 0.05 and info == {}
+        if d:
+            n_done += 1
+            assert np.abs(ob[:16]).max() > 0.4                 # terminal observation: the joints are where the episode died
+            assert np.allclose(wob[:32], 0) and wob[54] == 1   # wrapper semantics: the post-reset observation
+        elif t > 0 and G_d[t - 1]:
+            assert abs((r - wr) + G_ob[t][48]) < 0.02          # Q8: the raw reward carries -alpha * x_terminal
+    assert n_done >= 3
+    env.close(); wrap.close()
