@@ -68,6 +68,8 @@ struct snk_handle {
     unsigned long long* counters; // device [NCOUNTERS]: ticks, sweeps, dones, non-finite, work-queue head
     int64_t launches;
     // staging for the *_host entry points (allocated on first use)
+    cudaEvent_t ev_dev;           // recorded after every state-touching launch on a caller stream; the *_host entry points
+    bool ev_valid;                // make their own stream wait on it (a device-path call may still be in flight)
     cudaStream_t hstream;
     float *h_act, *h_obs, *h_rew; // pinned
     uint8_t *h_done, *h_mask;
@@ -78,11 +80,23 @@ struct snk_handle {
     bool staged;
 };
 
+// Ordering between the caller's streams (device-path entry points, asynchronous) and the handle's own stream (host-path entry
+// points, synchronous): a device-path call records ev_dev behind its work, a host-path call waits for it before touching the state.
+static void mark_device_work(snk_handle* h, cudaStream_t st) {
+    if (st == h->hstream && h->hstream) return;
+    if (!h->ev_valid) { if (cudaEventCreateWithFlags(&h->ev_dev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return; } h->ev_valid = true; }
+    cudaEventRecord(h->ev_dev, st);
+}
+static void wait_device_work(snk_handle* h) {
+    if (h->ev_valid && h->hstream) cudaStreamWaitEvent(h->hstream, h->ev_dev, 0);
+}
+
 static cudaError_t launch_step(snk_handle* h, const float* act, float* obs, float* rew, uint8_t* done, int32_t* ticks, cudaStream_t st) {
     int launches = 1;
     cudaError_t e = h->exact ? snk_exact_launch_step(h->P, h->state, act, obs, rew, done, ticks, h->counters, h->bucket, h->order, h->n, st, &launches)
                              : snk_pgs_launch_step(h->T, h->P, h->state, act, obs, rew, done, ticks, h->counters, h->n, st);
     h->launches += launches;
+    mark_device_work(h, st);
     return e;
 }
 
@@ -201,6 +215,7 @@ int snk_destroy(snk_handle* h) {
         cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_ticks); cudaFree(h->d_mask);
         cudaStreamDestroy(h->hstream);
     }
+    if (h->ev_valid) cudaEventDestroy(h->ev_dev);
     if (h->exact) snk_exact_release();
     cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters); cudaFree(h->bucket); cudaFree(h->order); cudaFree(h->roll_queue);
     delete h;
@@ -217,6 +232,7 @@ int snk_reset(snk_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stre
     CU(cudaSetDevice(h->device));
     CU(snk_launch_reset(h->P, h->state, mask_dev, obs_dev, h->n, 0, (cudaStream_t)stream));
     h->launches++;
+    mark_device_work(h, (cudaStream_t)stream);
     return 0;
 }
 
@@ -249,6 +265,7 @@ int snk_step_trace(snk_handle* h, const float* actions_dev, float* obs_dev, floa
     else CU(snk_pgs_launch_step(h->T, h->P, h->state, actions_dev, obs_dev, rew_dev, done_dev, ticks_dev, h->counters, h->n, st, tick_obs_dev,
                                 tick_links_dev));
     h->launches++;
+    mark_device_work(h, st);
     return 0;
 }
 
@@ -271,6 +288,7 @@ int snk_rollout_linear(snk_handle* h, const float* weights_dev, const float* mea
     CU(snk_exact_launch_rollout(h->P, h->state, weights_dev, mean_dev, inv_std_dev, noise_dev, n_steps, returns_dev, obs_trace_dev, h->roll_queue,
                                 h->order, h->counters, h->n, st));
     h->launches++;
+    mark_device_work(h, st);
     return 0;
 }
 
@@ -282,6 +300,7 @@ int snk_tick(snk_handle* h, const float* targets_dev, int32_t n_ticks, void* str
     if (h->exact) CU(snk_exact_launch_tick(h->P, h->state, targets_dev, h->counters, h->n, n_ticks, st));
     else CU(snk_pgs_launch_tick(h->T, h->P, h->state, targets_dev, h->counters, h->n, n_ticks, st));
     h->launches++;
+    mark_device_work(h, st);
     return 0;
 }
 
@@ -339,6 +358,7 @@ int snk_step_host(snk_handle* h, const float* actions_host, float* obs_host, flo
         // the environment finishes, spread over the whole launch -- no copy before or after the kernel.
         int rc0 = ensure_stream(h);
         if (rc0) return rc0;
+        wait_device_work(h);
         cudaStream_t zs = h->hstream;
         CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), zs));
         CU(launch_step(h, (const float*)da, (float*)dob, (float*)dr, (uint8_t*)dd, (int32_t*)dt, zs));
@@ -347,6 +367,7 @@ int snk_step_host(snk_handle* h, const float* actions_host, float* obs_host, flo
     }
     int rc = ensure_staging(h);
     if (rc) return rc;
+    wait_device_work(h);
     size_t n = (size_t)h->n, na = n * h->P.actdim * sizeof(float);
     cudaStream_t st = h->hstream;
     // pageable caller buffers go through the handle's pinned staging buffers; pinned ones are DMA sources / targets themselves
@@ -374,6 +395,7 @@ int snk_step_host_f64(snk_handle* h, const double* actions_host, double* obs_hos
     CU(cudaSetDevice(h->device));
     int rc = ensure_staging(h);
     if (rc) return rc;
+    wait_device_work(h);
     const size_t n = (size_t)h->n, na = n * h->P.actdim;
     float* ha = h->h_act;
     parallel_chunks(na, [=](size_t b, size_t e) { for (size_t i = b; i < e; i++) ha[i] = (float)actions_host[i]; });
@@ -404,6 +426,7 @@ int snk_reset_host(snk_handle* h, const uint8_t* mask_host, float* obs_host) {
     CU(cudaSetDevice(h->device));
     int rc = ensure_staging(h);
     if (rc) return rc;
+    wait_device_work(h);
     size_t n = (size_t)h->n;
     cudaStream_t st = h->hstream;
     if (mask_host) {
@@ -437,6 +460,7 @@ int snk_set_state(snk_handle* h, const float* state_dev, void* stream) {
     if (!h || !state_dev) return fail(SNK_E_ARG, "snk_set_state: null pointer%s");
     CU(cudaSetDevice(h->device));
     CU(cudaMemcpyAsync(h->state, state_dev, (size_t)h->n * SNK_STATE_STRIDE * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    mark_device_work(h, (cudaStream_t)stream);
     return 0;
 }
 

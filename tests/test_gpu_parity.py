@@ -228,6 +228,24 @@ def test_numpy_path_equals_device_path(torch):
     e1.close(); e2.close(); e3.close()
 
 
+def test_host_path_call_waits_for_device_path_work_in_flight(torch):
+    """A device-path step is asynchronous on the caller's stream; a numpy step issued right behind it runs on the library's own
+    stream and must still see its result (event ordering inside the C ABI).  Large enough that the first kernel is still running."""
+    n = 40000
+    g = torch.Generator().manual_seed(5)
+    a = (torch.rand((2, n, 8), generator=g) * 2 - 1)
+    mixed = make_env(n, obs_dtype=np.float32); plain = make_env(n)
+    mixed.reset(); plain.reset()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        mixed.step(a[0].cuda(non_blocking=True))                # enqueued on stream s, not waited for
+    o_m, r_m, d_m, _ = mixed.step(a[1].numpy())                 # host path, the library's stream
+    plain.step(a[0].cuda()); torch.cuda.synchronize()
+    o_p, r_p, d_p, _ = plain.step(a[1].cuda()); torch.cuda.synchronize()
+    assert np.array_equal(o_m, o_p.cpu().numpy()) and np.array_equal(r_m, r_p.cpu().numpy()) and np.array_equal(d_m, d_p.cpu().numpy())
+    mixed.close(); plain.close()
+
+
 def test_edge_cases(torch):
     # ragged sizes: 1 env, a partial last CTA, out-of-range actions are clipped like np.clip
     for n in (1, 31, 33):
