@@ -32,11 +32,17 @@ __constant__ ExTables cT;
 
 #define FULL 0xffffffffu
 #define TWARPS 4 // warps with rows in tensor memory (one per TMEM lane quadrant)
+#if SNK_PREB
+#define SWARPS 0 // the shared memory holds the impulse-response columns of the four tensor-memory warps (4 x 50 KB)
+#else
 #define SWARPS 2 // warps with rows in shared memory
+#endif
 
 struct StepSmem {
     RowsTmemAux t[TWARPS];
+#if SWARPS > 0
     RowsSmemStore s[SWARPS];
+#endif
     uint32_t tmem_base;
 };
 
@@ -324,12 +330,15 @@ snk_exact_rollout_kernel(const KParams P, float* __restrict__ state, const Rollo
         R.s = &S.t[warp];
         R.lane = lane;
         run_rollout_warp<CONE>(P, R, state, A, counters, n, first_base, dyn_base);
-    } else {
+    }
+#if SWARPS > 0
+    else {
         RowsS R;
         R.s = &S.s[warp - TWARPS];
         R.lane = lane;
         run_rollout_warp<CONE>(P, R, state, A, counters, n, first_base, dyn_base);
     }
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
@@ -356,7 +365,11 @@ snk_exact_step_kernel(const KParams P, float* __restrict__ state, const float* _
     // first wave (SNK_EXACT_SPREAD): 3 (default) = warp-major, the two warps that have a scheduler to themselves (2, 3)
     // first -- with the longest-first order the longest env-steps of the launch go to the fastest warps; 1 = warp-major in
     // warp-index order; 0 = CTA-major; 2 = no static wave, everything from the global counter (ablations)
+#if SWARPS > 0
     const int rank = (spread == 3) ? ((warp == 2) ? 0 : (warp == 3) ? 1 : (warp == 0) ? 2 : (warp == 1) ? 3 : warp) : warp;
+#else
+    const int rank = warp; // four equal warps, one per scheduler
+#endif
     const int64_t first_base = (spread == 2) ? -1 : (spread ? ((int64_t)rank * gridDim.x + blockIdx.x) * 32 : ((int64_t)blockIdx.x * active_warps + warp) * 32);
     const int64_t dyn_base = (spread == 2) ? 0 : min((int64_t)gridDim.x * active_warps * 32, n);
     if (warp >= active_warps) {
@@ -367,12 +380,15 @@ snk_exact_step_kernel(const KParams P, float* __restrict__ state, const float* _
         R.s = &S.t[warp];
         R.lane = lane;
         run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, order, n, first_base, dyn_base);
-    } else {
+    }
+#if SWARPS > 0
+    else {
         RowsS R;
         R.s = &S.s[warp - TWARPS];
         R.lane = lane;
         run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, order, n, first_base, dyn_base);
     }
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));

@@ -72,13 +72,31 @@ struct ExTables {
 // (sm_100a; the 512 columns of a warp's TMEM quadrant hold exactly 32 contacts x 16 words).  N2 and
 // the joint targets are always in shared memory.
 // -----------------------------------------------------------------------------------------------
-struct RowsSmemStore {  // one warp, rows in shared memory: 75 776 B
+// SNK_PREB (compile-time, default 0).  1 = the impulse-response columns of every row -- Ji (r x n), Ji (r x d1), Ji (r x d2) --
+// are computed once per tick and kept in shared memory as three float4 per contact,
+//   B[0] = (Ji rn | rhs_n invD_n)   B[1] = (Ji (r x d1) | invD_n)   B[2] = (Ji (r x d2) | unused)
+// which takes 4 / 9 instructions and 1 / 4 dependent operations off every normal row / friction pair of every sweep, but fills the
+// shared memory with the columns of the four tensor-memory warps, so the two shared-memory warps go.  MEASURED SLOWER on B200
+// (2^20 envs: 3.81 M env-steps/s against 4.37 M; a lone warp gains only 4 %, 5.79 vs 6.05 ms per step at 4 096 envs), so the
+// default is 0: only (rhs_n invD_n, invD_n) in shared memory, 4 + 2 warps per SM.  Kept as a documented, parity-green variant.
+#ifndef SNK_PREB
+#define SNK_PREB 0
+#endif
+struct RowsSmemStore {  // one warp, rows in shared memory
     float4 X[4][NC][EB];
+#if SNK_PREB
+    float4 B[3][NC][EB];
+#else
     float2 N2[NC][EB];
+#endif
     float tgt[NJ][EB];
 };
-struct RowsTmemAux {    // one warp, rows in tensor memory: 10 240 B of shared memory
+struct RowsTmemAux {    // one warp, rows in tensor memory: the shared-memory part
+#if SNK_PREB
+    float4 B[3][NC][EB];
+#else
     float2 N2[NC][EB];
+#endif
     float tgt[NJ][EB];
 };
 typedef RowsSmemStore ExSmem;
@@ -87,12 +105,18 @@ struct RowsS {
     RowsSmemStore* s;
     int lane;
     SNK_HD float& tgt(int j) const { return s->tgt[j][lane]; }
+#if SNK_PREB
+    SNK_HD void st_b(int k, float4 b0, float4 b1, float4 b2) const { s->B[0][k][lane] = b0; s->B[1][k][lane] = b1; s->B[2][k][lane] = b2; }
+    SNK_HD void ld_n(int k, float4& x0, float4& b0, float& idn) const { x0 = s->X[0][k][lane]; b0 = s->B[0][k][lane]; idn = s->B[1][k][lane].w; }
+    SNK_HD void ld_b12(int k, float4& b1, float4& b2) const { b1 = s->B[1][k][lane]; b2 = s->B[2][k][lane]; }
+#else
     SNK_HD void st_n2(int k, float a, float b) const { s->N2[k][lane] = make_float2(a, b); }
+    SNK_HD void ld_n(int k, float4& x0, float2& n2) const { x0 = s->X[0][k][lane]; n2 = s->N2[k][lane]; }
+#endif
     SNK_HD void st16(int k, float4 x0, float4 x1, float4 x2, float4 x3) const {
         s->X[0][k][lane] = x0; s->X[1][k][lane] = x1; s->X[2][k][lane] = x2; s->X[3][k][lane] = x3;
     }
     SNK_HD void st12(int k, float4 x0, float4 x1, float4 x2) const { s->X[0][k][lane] = x0; s->X[1][k][lane] = x1; s->X[2][k][lane] = x2; }
-    SNK_HD void ld_n(int k, float4& x0, float2& n2) const { x0 = s->X[0][k][lane]; n2 = s->N2[k][lane]; }
     SNK_HD void ld16(int k, float4& x0, float4& x1, float4& x2, float4& x3) const {
         x0 = s->X[0][k][lane]; x1 = s->X[1][k][lane]; x2 = s->X[2][k][lane]; x3 = s->X[3][k][lane];
     }
@@ -113,7 +137,20 @@ struct RowsT {
     RowsTmemAux* s;
     int lane;
     __device__ __forceinline__ float& tgt(int j) const { return s->tgt[j][lane]; }
+#if SNK_PREB
+    __device__ __forceinline__ void st_b(int k, float4 b0, float4 b1, float4 b2) const { s->B[0][k][lane] = b0; s->B[1][k][lane] = b1; s->B[2][k][lane] = b2; }
+    __device__ __forceinline__ void ld_b12(int k, float4& b1, float4& b2) const { b1 = s->B[1][k][lane]; b2 = s->B[2][k][lane]; }
+    __device__ __forceinline__ void ld_n(int k, float4& x0, float4& b0, float& idn) const {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(x0.x), "=f"(x0.y), "=f"(x0.z), "=f"(x0.w) : "r"(taddr + 16u * k) : "memory");
+        b0 = s->B[0][k][lane]; idn = s->B[1][k][lane].w;
+    }
+#else
     __device__ __forceinline__ void st_n2(int k, float a, float b) const { s->N2[k][lane] = make_float2(a, b); }
+    __device__ __forceinline__ void ld_n(int k, float4& x0, float2& n2) const {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(x0.x), "=f"(x0.y), "=f"(x0.z), "=f"(x0.w) : "r"(taddr + 16u * k) : "memory");
+        n2 = s->N2[k][lane];
+    }
+#endif
     __device__ __forceinline__ void st4(uint32_t col, float4 v) const {
         asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr + col), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
     }
@@ -123,10 +160,6 @@ struct RowsT {
                      "f"(x3.x), "f"(x3.y), "f"(x3.z), "f"(x3.w) : "memory");
     }
     __device__ __forceinline__ void st12(int k, float4 x0, float4 x1, float4 x2) const { st4(16u * k, x0); st4(16u * k + 4u, x1); st4(16u * k + 8u, x2); }
-    __device__ __forceinline__ void ld_n(int k, float4& x0, float2& n2) const {
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(x0.x), "=f"(x0.y), "=f"(x0.z), "=f"(x0.w) : "r"(taddr + 16u * k) : "memory");
-        n2 = s->N2[k][lane];
-    }
     __device__ __forceinline__ void ld16(int k, float4& x0, float4& x1, float4& x2, float4& x3) const {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                      : "=f"(x0.x), "=f"(x0.y), "=f"(x0.z), "=f"(x0.w), "=f"(x1.x), "=f"(x1.y), "=f"(x1.z), "=f"(x1.w), "=f"(x2.x), "=f"(x2.y), "=f"(x2.z),
@@ -442,7 +475,8 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
         const V3 vp = VC + cross(wf, r) + uJ;
         // normal row
         const V3 rn = mk(r.y, -r.x, 0.f);
-        const float Dn = invM + dot(rn, mul(Ji, rn));
+        const V3 Jn = mul(Ji, rn);
+        const float Dn = invM + dot(rn, Jn);
         const float iDn = 1.f / Dn;
         const float pen = dist + P.slop;
         float verr = -vp.z, perr = 0.f;
@@ -450,12 +484,17 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
         const float rhsn = (verr + perr) * iDn;
         // friction rows
         const V3 r1 = cross(r, d1), r2 = cross(r, d2);
-        const float D1 = dot(d1, d1) * invM + dot(r1, mul(Ji, r1)), D2 = dot(d2, d2) * invM + dot(r2, mul(Ji, r2));
+        const V3 J1 = mul(Ji, r1), J2 = mul(Ji, r2);
+        const float D1 = dot(d1, d1) * invM + dot(r1, J1), D2 = dot(d2, d2) * invM + dot(r2, J2);
         const float iD1 = 1.f / D1, iD2 = 1.f / D2;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         R.st16(k, on ? make_float4(0.f, r.x, r.y, r.z) : z4, on ? make_float4(d1.x, d1.y, d1.z, d2.x) : z4,
                on ? make_float4(d2.y, d2.z, -dot(d1, vp) * iD1, -dot(d2, vp) * iD2) : z4, on ? make_float4(iD1, iD2, 0.f, 0.f) : z4);
+#if SNK_PREB
+        R.st_b(k, on ? make_float4(Jn.x, Jn.y, Jn.z, rhsn) : z4, on ? make_float4(J1.x, J1.y, J1.z, iDn) : z4, on ? make_float4(J2.x, J2.y, J2.z, 0.f) : z4);
+#else
         R.st_n2(k, on ? rhsn : 0.f, on ? iDn : 0.f);
+#endif
     }
     R.fence_st();
 
@@ -470,6 +509,79 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
     const float sthr = sqrtf(P.resthr), mu = P.mu;
     bool frozen = !commit;
     int sweeps = 0;
+#if SNK_PREB
+    // A frozen lane re-selects its old impulse, so its impulse change is exactly zero and (dw, dV) stay put.
+#pragma unroll 1
+    for (int it = 0; it < P.iters; it++) {
+        if (ex_all(frozen)) break;
+        float viol = 0.f; // max over the rows of |d| - sqrt(thr) invD (in the row's scaled units)
+        {   // ---- normal rows; the record of row k+1 is fetched while row k is on the chain
+            float4 nx, nb; float nidn;
+            R.ld_n(0, nx, nb, nidn);
+#pragma unroll 4
+            for (int k = 0; k < NC; k++) {
+                R.fence4(nx);
+                const float4 x0 = nx, b0 = nb;  // (ln, rx, ry, rz), (Ji rn | rhs_n invD_n)
+                const float idn = nidn;
+                R.ld_n((k + 1) & (NC - 1), nx, nb, nidn);
+                const float ln = x0.x;
+                const float p = ln + b0.w;
+                float jd = fmaf(dw.x, x0.z, dV.z);
+                jd = fmaf(-dw.y, x0.y, jd);
+                const float sum = fmaxf(fmaf(-jd, idn, p), 0.f);
+                const float sel = frozen ? ln : sum;
+                const float dd = sel - ln;
+                R.st_ln(k, sel);
+                dw.x = fmaf(b0.x, dd, dw.x); dw.y = fmaf(b0.y, dd, dw.y); dw.z = fmaf(b0.z, dd, dw.z);
+                dV.z = fmaf(dd, invM, dV.z);
+                viol = fmaxf(viol, fmaf(-sthr, idn, fabsf(dd)));
+            }
+            R.fence4(nx);
+            R.fence_st();
+        }
+        {   // ---- friction pairs
+            float4 n0, n1, n2_, n3, nb1, nb2;
+            R.ld16(0, n0, n1, n2_, n3);
+            R.ld_b12(0, nb1, nb2);
+#pragma unroll 2
+            for (int k = 0; k < NC; k++) {
+                R.fence16(n0, n1, n2_, n3);
+                const float4 x0 = n0, x1 = n1, x2 = n2_, x3 = n3, b1 = nb1, b2 = nb2;
+                R.ld16((k + 1) & (NC - 1), n0, n1, n2_, n3);
+                R.ld_b12((k + 1) & (NC - 1), nb1, nb2);
+                const float rx = x0.y, ry = x0.z, rz = x0.w;
+                const float pa = x3.z + x2.z, pb = x3.w + x2.w, lim = mu * x0.x;
+                // u = dV + dw x r
+                const float ux = fmaf(-dw.z, ry, fmaf(dw.y, rz, dV.x));
+                const float uy = fmaf(-dw.x, rz, fmaf(dw.z, rx, dV.y));
+                const float uz = fmaf(-dw.y, rx, fmaf(dw.x, ry, dV.z));
+                const float g1 = fmaf(x1.z, uz, fmaf(x1.y, uy, x1.x * ux)), g2 = fmaf(x2.y, uz, fmaf(x2.x, uy, x1.w * ux));
+                float sa = fmaf(-g1, x3.x, pa), sb = fmaf(-g2, x3.y, pb);
+                if (CONE) { // implicit cone: radial projection onto the disc of radius mu * lambda_n,
+                            // s <- s min(1, lim / |s|)  (0/0 and lim/0 resolve to 1 through fminf)
+                    const float sc = fminf(1.f, lim * ex_rsqrt_fast(fmaf(sa, sa, sb * sb)));
+                    sa *= sc; sb *= sc;
+                } else {
+                    sa = fminf(fmaxf(sa, -lim), lim);
+                    sb = fminf(fmaxf(sb, -lim), lim);
+                }
+                sa = frozen ? x3.z : sa; sb = frozen ? x3.w : sb;
+                const float da = sa - x3.z, db = sb - x3.w;
+                R.st_lf(k, sa, sb);
+                const float fx = fmaf(x1.w, db, x1.x * da), fy = fmaf(x2.x, db, x1.y * da), fz = fmaf(x2.y, db, x1.z * da);
+                dV.x = fmaf(fx, invM, dV.x); dV.y = fmaf(fy, invM, dV.y); dV.z = fmaf(fz, invM, dV.z);
+                dw.x = fmaf(b1.x, da, fmaf(b2.x, db, dw.x));
+                dw.y = fmaf(b1.y, da, fmaf(b2.y, db, dw.y));
+                dw.z = fmaf(b1.z, da, fmaf(b2.z, db, dw.z));
+                // (da D1 + db D2)^2 <= thr  <=>  |da invD2 + db invD1| <= sqrt(thr) invD1 invD2
+                viol = fmaxf(viol, fmaf(-sthr * x3.x, x3.y, fabsf(fmaf(da, x3.y, db * x3.x))));
+            }
+            R.fence16(n0, n1, n2_, n3);
+            R.fence_st();
+        }
+        if (!frozen) { sweeps++; frozen = (viol <= 0.f); }
+    }
+#else
 #pragma unroll 1
     for (int it = 0; it < P.iters; it++) {
         if (ex_all(frozen)) break;
@@ -544,6 +656,7 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
         }
         if (!frozen) { sweeps++; frozen = (viol <= 0.f); }
     }
+#endif
     out->iterations = sweeps;
     out->contacts = ex_popc(act);
 
