@@ -151,6 +151,12 @@ class Oracle:
         self._fn("counters")(self._h, out, ctypes.c_int(int(clear)))
         return dict(ticks=out[0], pgs_iterations=out[1], dones=out[2], nonfinite=out[3])
 
+    def set_contact_points(self, cpp):
+        """Oracle-only sensitivity switch for deviation D1: contact points per cylinder in the exact tick (1 = default, 2 = both rims)."""
+        f = self._fn("set_contact_points"); f.restype = ctypes.c_int
+        if f(self._h, ctypes.c_int(int(cpp))) != 0:
+            raise ValueError("contact points per cylinder must be 1 or 2")
+
     def self_clearance(self):
         """Twin of ``snk_self_clearance``: lower bound [n] of the smallest distance between non-consecutive cylinders."""
         out = np.empty(self.n, self.dtype)

@@ -48,3 +48,33 @@ def test_relaxed_motor_rows_converge_to_the_motor_law():
     ex.set_state(s); ex.tick(tg.astype(np.float64), 1)
     assert np.abs(ex.get_state()[:, 29:45] - law).max() < 1e-9          # imposed exactly
     assert med[1000] < 0.25 * med[50] and med[1000] < 3e-3, med
+
+
+def test_contact_points_per_cylinder_sensitivity(model):
+    """Deviation D1 quantified (oracle only): one contact point per cylinder (the kernels) against both rims of every cylinder
+    (64 contacts, closer to the points Bullet's persistent manifolds accumulate).  From synchronised states, per env-step: tick counts
+    and episode ends identical (they depend on the joints only), base position within millimetres for the typical environment,
+    reward within 1e-2 except where the |Fz| > 10 penalty flips; a 30-step serpenoid gait returns the same to 0.1 %."""
+    from scenarios import serpenoid_actions
+    n = 48
+    a = Oracle(n, default_params(), model); b = Oracle(n, default_params(), model)
+    b.set_contact_points(2)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(0)
+    dpos, drew = [], []
+    for _ in range(3):
+        act = rng.uniform(-1, 1, (n, 8))
+        b.set_state(a.get_state())
+        oa, ra, da, ta = a.step(act, threads=8)
+        ob, rb, db, tb = b.step(act, threads=8)
+        assert np.array_equal(ta, tb) and np.array_equal(da, db)
+        assert np.abs(oa[:, :16] - ob[:, :16]).max() < 1e-9                      # joints: prescribed by the motor law
+        dpos.append(np.abs(oa[:, 48:51] - ob[:, 48:51]).max(1)); drew.append(np.abs(ra - rb))
+    dpos, drew = np.concatenate(dpos), np.concatenate(drew)
+    assert np.median(dpos) < 6e-3 and dpos.max() < 0.06, (np.median(dpos), dpos.max())
+    assert np.median(drew) < 5e-3 and np.percentile(drew, 90) < 5e-2, (np.median(drew), np.percentile(drew, 90))
+    acts = serpenoid_actions(30)
+    a = Oracle(1, default_params(), model); b = Oracle(1, default_params(), model); b.set_contact_points(2)
+    a.reset(); b.reset()
+    Ra = sum(a.step(acts[t])[1][0] for t in range(30)); Rb = sum(b.step(acts[t])[1][0] for t in range(30))
+    assert abs(Ra - Rb) < 2e-3 * abs(Ra), (Ra, Rb)
