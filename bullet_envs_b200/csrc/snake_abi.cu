@@ -152,6 +152,7 @@ int snk_default_params(snk_params* p) {
 int snk_create(const snk_model* model, const snk_params* params, int64_t n_envs, int device, snk_handle** out) {
     if (!model || !params || !out) return fail(SNK_E_ARG, "snk_create: null pointer%s");
     if (n_envs <= 0) return fail(SNK_E_ARG, "snk_create: n_envs must be positive%s");
+    if (n_envs > 0x7fffffffLL) return fail(SNK_E_ARG, "snk_create: at most 2^31 - 1 environments per handle (32-bit hand-out order); shard over handles%s");
     if (params->term_joint < 0 || params->term_joint >= SNK_OBS_DIM) return fail(SNK_E_ARG, "snk_create: term_joint out of range%s");
     if (params->solver_iterations < 1 || params->max_ticks < 0) return fail(SNK_E_ARG, "snk_create: bad iteration/tick limits%s");
     if (!(params->dt > 0)) return fail(SNK_E_ARG, "snk_create: dt must be positive%s");

@@ -535,7 +535,13 @@ static int g_active_warps = TWARPS + SWARPS; // SNK_EXACT_WARPS=1..6: ablation o
 
 size_t snk_exact_smem_bytes() { return g_rows_tmem ? sizeof(StepSmem) : sizeof(RowsSmemStore); }
 
-const char* snk_exact_variant() { return g_rows_tmem ? "rows in TMEM (4 warps) + shared memory (2 warps), 192 envs/SM" : "rows in shared memory, 3 x 32 envs/SM"; }
+const char* snk_exact_variant() {
+#if SNK_PREB
+    return g_rows_tmem ? "rows in TMEM (4 warps), impulse-response columns in shared memory, 128 envs/SM" : "rows in shared memory, 32 envs per CTA";
+#else
+    return g_rows_tmem ? "rows in TMEM (4 warps) + shared memory (2 warps), 192 envs/SM" : "rows in shared memory, 3 x 32 envs/SM";
+#endif
+}
 
 // The model tables live in one __constant__ symbol per device: all live handles of a process must share one
 // model.  Returns cudaErrorInvalidValue (reported by snk_create) when `host_tables` differs from the tables of

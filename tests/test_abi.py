@@ -55,6 +55,8 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     h = ctypes.c_void_p()
     assert lib.snk_create(None, None, 4, 0, ctypes.byref(h)) < 0
     assert lib.snk_step(None, None, None, None, None, None, None) < 0
+    assert lib.snk_step_trace(None, None, None, None, None, None, None, None, None) < 0 and lib.snk_self_clearance(None, None, None) < 0
+    assert lib.snk_step_host_f64(None, None, None, None, None, None) < 0
     assert b"sm_100a" in lib.snk_build_info()
 
 
