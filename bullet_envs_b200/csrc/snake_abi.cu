@@ -25,13 +25,13 @@ cudaError_t snk_pgs_launch_tick(const DevTables* T, const KParams& P, float* sta
 // thread-per-env kernel with the motor rows eliminated (snake_exact.cu)
 cudaError_t snk_exact_configure(const ExTables* host_tables);
 void snk_exact_release();
-cudaError_t snk_exact_launch_step(const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
+cudaError_t snk_exact_launch_step(const KParams& P, float* state, float* tgt_scratch, const float* actions, float* obs, float* rew, uint8_t* done,
                                   int32_t* ticks, unsigned long long* counters, uint8_t* bucket, int32_t* order, int64_t n, cudaStream_t st,
                                   int* launches);
-cudaError_t snk_exact_launch_rollout(const KParams& P, float* state, const float* weights, const float* mean, const float* inv_std,
+cudaError_t snk_exact_launch_rollout(const KParams& P, float* state, float* tgt_scratch, const float* weights, const float* mean, const float* inv_std,
                                      const float* noise, int n_steps, float* returns, float* trace, int32_t* queue, int32_t* done_steps,
                                      unsigned long long* counters, int64_t n, cudaStream_t st);
-cudaError_t snk_exact_launch_step_trace(const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
+cudaError_t snk_exact_launch_step_trace(const KParams& P, float* state, float* tgt_scratch, const float* actions, float* obs, float* rew, uint8_t* done,
                                         int32_t* ticks, unsigned long long* counters, int64_t n, float* tick_obs, float* tick_links, cudaStream_t st);
 cudaError_t snk_exact_launch_tick(const KParams& P, float* state, const float* targets, unsigned long long* counters, int64_t n,
                                   int n_ticks, cudaStream_t st);
@@ -61,6 +61,7 @@ struct snk_handle {
     KParams P;
     DevTables* T;                 // device: general model tables (warp-per-env kernel, clearance counter)
     float* state;                 // device [n][64]
+    float* tgt;                   // device [n + 1][16]: joint targets of the env-step in flight (exact kernel; row n stays zero)
     uint8_t* bucket;              // device [n]: predicted tick count of the coming env-step (exact kernel)
     int32_t* order;               // device [n]: longest-first hand-out order
     int32_t* roll_queue;          // device: ready queue of snk_rollout_linear, n * (steps - 1) entries (grown on demand)
@@ -93,7 +94,7 @@ static void wait_device_work(snk_handle* h) {
 
 static cudaError_t launch_step(snk_handle* h, const float* act, float* obs, float* rew, uint8_t* done, int32_t* ticks, cudaStream_t st) {
     int launches = 1;
-    cudaError_t e = h->exact ? snk_exact_launch_step(h->P, h->state, act, obs, rew, done, ticks, h->counters, h->bucket, h->order, h->n, st, &launches)
+    cudaError_t e = h->exact ? snk_exact_launch_step(h->P, h->state, h->tgt, act, obs, rew, done, ticks, h->counters, h->bucket, h->order, h->n, st, &launches)
                              : snk_pgs_launch_step(h->T, h->P, h->state, act, obs, rew, done, ticks, h->counters, h->n, st);
     h->launches += launches;
     mark_device_work(h, st);
@@ -180,6 +181,8 @@ int snk_create(const snk_model* model, const snk_params* params, int64_t n_envs,
         h->exact = true;
         if (err == cudaSuccess) err = cudaMalloc(&h->bucket, (size_t)n_envs);
         if (err == cudaSuccess) err = cudaMalloc(&h->order, (size_t)n_envs * sizeof(int32_t));
+        if (err == cudaSuccess) err = cudaMalloc(&h->tgt, (size_t)(n_envs + 1) * NJ * sizeof(float));
+        if (err == cudaSuccess) err = cudaMemset(h->tgt, 0, (size_t)(n_envs + 1) * NJ * sizeof(float));
     } else {
         err = snk_pgs_configure();
     }
@@ -196,7 +199,7 @@ int snk_create(const snk_model* model, const snk_params* params, int64_t n_envs,
     if (err == cudaSuccess) err = cudaDeviceSynchronize();
     if (err != cudaSuccess) {
         if (h->exact) snk_exact_release();
-        cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters); cudaFree(h->bucket); cudaFree(h->order);
+        cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters); cudaFree(h->bucket); cudaFree(h->order); cudaFree(h->tgt);
         delete h;
         return fail(SNK_E_CUDA, "snk_create: %s", cudaGetErrorString(err));
     }
@@ -218,7 +221,7 @@ int snk_destroy(snk_handle* h) {
     }
     if (h->ev_valid) cudaEventDestroy(h->ev_dev);
     if (h->exact) snk_exact_release();
-    cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters); cudaFree(h->bucket); cudaFree(h->order); cudaFree(h->roll_queue);
+    cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters); cudaFree(h->bucket); cudaFree(h->order); cudaFree(h->roll_queue); cudaFree(h->tgt);
     delete h;
     return 0;
 }
@@ -261,7 +264,7 @@ int snk_step_trace(snk_handle* h, const float* actions_dev, float* obs_dev, floa
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
-    if (h->exact) CU(snk_exact_launch_step_trace(h->P, h->state, actions_dev, obs_dev, rew_dev, done_dev, ticks_dev, h->counters, h->n, tick_obs_dev,
+    if (h->exact) CU(snk_exact_launch_step_trace(h->P, h->state, h->tgt, actions_dev, obs_dev, rew_dev, done_dev, ticks_dev, h->counters, h->n, tick_obs_dev,
                                                  tick_links_dev, st));
     else CU(snk_pgs_launch_step(h->T, h->P, h->state, actions_dev, obs_dev, rew_dev, done_dev, ticks_dev, h->counters, h->n, st, tick_obs_dev,
                                 tick_links_dev));
@@ -286,7 +289,7 @@ int snk_rollout_linear(snk_handle* h, const float* weights_dev, const float* mea
     CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
     CU(cudaMemsetAsync(h->roll_queue, 0xff, qlen * sizeof(int32_t), st));        // -1: not pushed yet
     CU(cudaMemsetAsync(h->order, 0, (size_t)h->n * sizeof(int32_t), st));          // env-steps done (the step kernel's order[] is rebuilt per step)
-    CU(snk_exact_launch_rollout(h->P, h->state, weights_dev, mean_dev, inv_std_dev, noise_dev, n_steps, returns_dev, obs_trace_dev, h->roll_queue,
+    CU(snk_exact_launch_rollout(h->P, h->state, h->tgt, weights_dev, mean_dev, inv_std_dev, noise_dev, n_steps, returns_dev, obs_trace_dev, h->roll_queue,
                                 h->order, h->counters, h->n, st));
     h->launches++;
     mark_device_work(h, st);

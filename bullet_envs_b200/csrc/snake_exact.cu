@@ -73,7 +73,7 @@ __device__ __forceinline__ void load_targets(const KParams& P, const Rows& R, co
 // TRACE: the mode='test' info stream (snake.py:275-278,292-293): after every physics tick the observation goes to
 // tick_obs[env][tick][56] and the link positions to tick_links[env][tick][51] (max_ticks rows per environment).
 template <bool CONE, class Rows, bool TRACE = false>
-__device__ __forceinline__ void run_warp(const KParams& P, const Rows& R, float* __restrict__ state, const float* __restrict__ actions,
+__device__ __forceinline__ void run_warp(const KParams& P, Rows R, float* __restrict__ state, float* __restrict__ tgt_scratch, const float* __restrict__ actions,
                                          float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks,
                                          unsigned long long* __restrict__ counters, const int32_t* __restrict__ order, int64_t n,
                                          int64_t first_base, int64_t dyn_base, float* __restrict__ tick_obs = nullptr,
@@ -89,8 +89,7 @@ __device__ __forceinline__ void run_warp(const KParams& P, const Rows& R, float*
 #pragma unroll
     for (int k = 0; k < 3; k++) { e.pos[k] = 0.f; e.vel[k] = 0.f; e.omg[k] = 0.f; e.quat[k] = 0.f; }
     e.quat[3] = 1.f;
-#pragma unroll
-    for (int j = 0; j < NJ; j++) R.tgt(j) = 0.f;
+    R.tg = tgt_scratch + n * NJ; // ... and on the spare (all-zero) target row behind the last environment
     ExRun run;
     run.xprev = 0.f; run.e2 = 0.f; run.height = 0.f; run.counter = 0; run.iters = 0; run.end_height = false; run.have_height = false;
     int64_t env = -1;
@@ -114,6 +113,7 @@ __device__ __forceinline__ void run_warp(const KParams& P, const Rows& R, float*
                 if (cand < n) {
                     env = order ? (int64_t)order[cand] : cand; have = true; // longest-first order when the batch exceeds the lanes
                     e.st = state + env * SNK_STATE_STRIDE;
+                    R.tg = tgt_scratch + env * NJ;
                     load_targets(P, R, actions + env * P.actdim);
                     ex_load_base(e);
                     ex_step_begin(P, R, e, &run);
@@ -220,7 +220,7 @@ __device__ __forceinline__ void policy_targets(const KParams& P, const Rows& R, 
 // fences (which also invalidates its SM's L1) after seeing the entry and before loading the record.
 // counters: [4] tickets handed out, [5] pushes done.
 template <bool CONE, class Rows>
-__device__ __forceinline__ void run_rollout_warp(const KParams& P, const Rows& R, float* __restrict__ state, const RolloutArgs A,
+__device__ __forceinline__ void run_rollout_warp(const KParams& P, Rows R, float* __restrict__ state, float* __restrict__ tgt_scratch, const RolloutArgs A,
                                                  unsigned long long* __restrict__ counters, int64_t n, int64_t first_base, int64_t dyn_base) {
     const int lane = R.lane;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -231,8 +231,7 @@ __device__ __forceinline__ void run_rollout_warp(const KParams& P, const Rows& R
 #pragma unroll
     for (int k = 0; k < 3; k++) { e.pos[k] = 0.f; e.vel[k] = 0.f; e.omg[k] = 0.f; e.quat[k] = 0.f; }
     e.quat[3] = 1.f;
-#pragma unroll
-    for (int j = 0; j < NJ; j++) R.tgt(j) = 0.f;
+    R.tg = tgt_scratch + n * NJ;
     ExRun run;
     run.xprev = 0.f; run.e2 = 0.f; run.height = 0.f; run.counter = 0; run.iters = 0; run.end_height = false; run.have_height = false;
     int64_t env = -1;
@@ -267,6 +266,7 @@ __device__ __forceinline__ void run_rollout_warp(const KParams& P, const Rows& R
                 __threadfence(); // acquire: the previous owner's stores to the record, returns[] and done_steps[]
                 env = cand; have = true; ticket = -1;
                 e.st = state + env * SNK_STATE_STRIDE;
+                R.tg = tgt_scratch + env * NJ;
                 t = A.done_steps[env];
                 ex_load_base(e);
                 policy_targets(P, R, e, A, env, n, t);
@@ -309,7 +309,8 @@ __device__ __forceinline__ void run_rollout_warp(const KParams& P, const Rows& R
 
 template <bool CONE>
 __global__ void __launch_bounds__((TWARPS + SWARPS) * 32, 1)
-snk_exact_rollout_kernel(const KParams P, float* __restrict__ state, const RolloutArgs A, unsigned long long* __restrict__ counters, int64_t n) {
+snk_exact_rollout_kernel(const KParams P, float* __restrict__ state, float* __restrict__ tgt_scratch, const RolloutArgs A,
+                         unsigned long long* __restrict__ counters, int64_t n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StepSmem& S = *reinterpret_cast<StepSmem*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -329,14 +330,14 @@ snk_exact_rollout_kernel(const KParams P, float* __restrict__ state, const Rollo
         R.taddr = tbase + ((uint32_t)(32 * warp) << 16);
         R.s = &S.t[warp];
         R.lane = lane;
-        run_rollout_warp<CONE>(P, R, state, A, counters, n, first_base, dyn_base);
+        run_rollout_warp<CONE>(P, R, state, tgt_scratch, A, counters, n, first_base, dyn_base);
     }
 #if SWARPS > 0
     else {
         RowsS R;
         R.s = &S.s[warp - TWARPS];
         R.lane = lane;
-        run_rollout_warp<CONE>(P, R, state, A, counters, n, first_base, dyn_base);
+        run_rollout_warp<CONE>(P, R, state, tgt_scratch, A, counters, n, first_base, dyn_base);
     }
 #endif
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -347,7 +348,7 @@ snk_exact_rollout_kernel(const KParams P, float* __restrict__ state, const Rollo
 // 6 warps per CTA, one CTA per SM: rows of warps 0-3 in tensor memory, of warps 4-5 in shared memory
 template <bool CONE>
 __global__ void __launch_bounds__((TWARPS + SWARPS) * 32, 1)
-snk_exact_step_kernel(const KParams P, float* __restrict__ state, const float* __restrict__ actions, float* __restrict__ obs,
+snk_exact_step_kernel(const KParams P, float* __restrict__ state, float* __restrict__ tgt_scratch, const float* __restrict__ actions, float* __restrict__ obs,
                       float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks, unsigned long long* __restrict__ counters,
                       const int32_t* __restrict__ order, int64_t n, int active_warps, int spread) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -379,14 +380,14 @@ snk_exact_step_kernel(const KParams P, float* __restrict__ state, const float* _
         R.taddr = tbase + ((uint32_t)(32 * warp) << 16);
         R.s = &S.t[warp];
         R.lane = lane;
-        run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, order, n, first_base, dyn_base);
+        run_warp<CONE>(P, R, state, tgt_scratch, actions, obs, rew, done, ticks, counters, order, n, first_base, dyn_base);
     }
 #if SWARPS > 0
     else {
         RowsS R;
         R.s = &S.s[warp - TWARPS];
         R.lane = lane;
-        run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, order, n, first_base, dyn_base);
+        run_warp<CONE>(P, R, state, tgt_scratch, actions, obs, rew, done, ticks, counters, order, n, first_base, dyn_base);
     }
 #endif
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -398,28 +399,28 @@ snk_exact_step_kernel(const KParams P, float* __restrict__ state, const float* _
 // (SNK_EXACT_ROWS=smem; kept for the ablation in DESIGN.md section 6)
 template <bool CONE>
 __global__ void __launch_bounds__(EB, 3)
-snk_exact_step_kernel_smem(const KParams P, float* __restrict__ state, const float* __restrict__ actions, float* __restrict__ obs,
+snk_exact_step_kernel_smem(const KParams P, float* __restrict__ state, float* __restrict__ tgt_scratch, const float* __restrict__ actions, float* __restrict__ obs,
                            float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks,
                            unsigned long long* __restrict__ counters, const int32_t* __restrict__ order, int64_t n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RowsS R;
     R.s = reinterpret_cast<RowsSmemStore*>(smem_raw);
     R.lane = threadIdx.x;
-    run_warp<CONE>(P, R, state, actions, obs, rew, done, ticks, counters, order, n, (int64_t)blockIdx.x * EB, min((int64_t)gridDim.x * EB, n));
+    run_warp<CONE>(P, R, state, tgt_scratch, actions, obs, rew, done, ticks, counters, order, n, (int64_t)blockIdx.x * EB, min((int64_t)gridDim.x * EB, n));
 }
 
 // the env-step with the mode='test' info stream (snk_step_trace): an analysis path for a handful of environments,
 // so the plain shared-memory variant carries it and the benchmarked kernel stays untouched
 template <bool CONE>
 __global__ void __launch_bounds__(EB, 3)
-snk_exact_step_trace_kernel(const KParams P, float* __restrict__ state, const float* __restrict__ actions, float* __restrict__ obs,
+snk_exact_step_trace_kernel(const KParams P, float* __restrict__ state, float* __restrict__ tgt_scratch, const float* __restrict__ actions, float* __restrict__ obs,
                             float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks,
                             unsigned long long* __restrict__ counters, int64_t n, float* __restrict__ tick_obs, float* __restrict__ tick_links) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RowsS R;
     R.s = reinterpret_cast<RowsSmemStore*>(smem_raw);
     R.lane = threadIdx.x;
-    run_warp<CONE, RowsS, true>(P, R, state, actions, obs, rew, done, ticks, counters, nullptr, n, (int64_t)blockIdx.x * EB,
+    run_warp<CONE, RowsS, true>(P, R, state, tgt_scratch, actions, obs, rew, done, ticks, counters, nullptr, n, (int64_t)blockIdx.x * EB,
                                 min((int64_t)gridDim.x * EB, n), tick_obs, tick_links);
 }
 
@@ -438,11 +439,7 @@ snk_exact_tick_kernel(const KParams P, float* __restrict__ state, const float* _
     ExEnv e;
     e.st = state + (live ? env : 0) * SNK_STATE_STRIDE;
     e.tid = threadIdx.x;
-#pragma unroll
-    for (int j = 0; j < NJ; j += 4) {
-        const float4 t = live ? *reinterpret_cast<const float4*>(targets + env * NJ + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        R.tgt(j) = t.x; R.tgt(j + 1) = t.y; R.tgt(j + 2) = t.z; R.tgt(j + 3) = t.w;
-    }
+    R.tg = const_cast<float*>(targets) + (live ? env : 0) * NJ; // the caller's row itself (only read here)
     ex_load_base(e);
     int iters = 0;
 #pragma unroll 1
@@ -584,7 +581,7 @@ cudaError_t snk_exact_configure(const ExTables* host_tables) {
 
 // sched = {bucket[n] u8, order[n] i32} owned by the handle (null: hand out in index order); hist/cursor are the
 // 2 x 64 words after the 8 counters (zeroed with them)
-cudaError_t snk_exact_launch_step(const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
+cudaError_t snk_exact_launch_step(const KParams& P, float* state, float* tgt_scratch, const float* actions, float* obs, float* rew, uint8_t* done,
                                   int32_t* ticks, unsigned long long* counters, uint8_t* bucket, int32_t* order, int64_t n, cudaStream_t st,
                                   int* launches) {
     const int lanes = g_rows_tmem ? g_sms * (TWARPS + SWARPS) * 32 : g_smem_ctas * EB;
@@ -604,27 +601,27 @@ cudaError_t snk_exact_launch_step(const KParams& P, float* state, const float* a
         // a small batch gets one CTA per warp of environments: all SMs before a second warp per SM
         const int64_t want = (g_spread == 1 || g_spread == 3) ? (n + EB - 1) / EB : (n + per_cta - 1) / per_cta;
         dim3 grid((unsigned)(want < g_sms ? want : g_sms)), block(per_cta);
-        if (P.cone) snk_exact_step_kernel<true><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n, g_active_warps, g_spread);
-        else snk_exact_step_kernel<false><<<grid, block, sizeof(StepSmem), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n, g_active_warps, g_spread);
+        if (P.cone) snk_exact_step_kernel<true><<<grid, block, sizeof(StepSmem), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n, g_active_warps, g_spread);
+        else snk_exact_step_kernel<false><<<grid, block, sizeof(StepSmem), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n, g_active_warps, g_spread);
     } else {
         const int64_t warps = (n + EB - 1) / EB;
         dim3 grid((unsigned)(warps < g_smem_ctas ? warps : g_smem_ctas)), block(EB);
-        if (P.cone) snk_exact_step_kernel_smem<true><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n);
-        else snk_exact_step_kernel_smem<false><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, actions, obs, rew, done, ticks, counters, use_order, n);
+        if (P.cone) snk_exact_step_kernel_smem<true><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n);
+        else snk_exact_step_kernel_smem<false><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n);
     }
     return cudaGetLastError();
 }
 
-cudaError_t snk_exact_launch_step_trace(const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
+cudaError_t snk_exact_launch_step_trace(const KParams& P, float* state, float* tgt_scratch, const float* actions, float* obs, float* rew, uint8_t* done,
                                         int32_t* ticks, unsigned long long* counters, int64_t n, float* tick_obs, float* tick_links, cudaStream_t st) {
     const int64_t warps = (n + EB - 1) / EB;
     dim3 grid((unsigned)(warps < g_smem_ctas ? warps : g_smem_ctas)), block(EB);
-    if (P.cone) snk_exact_step_trace_kernel<true><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, actions, obs, rew, done, ticks, counters, n, tick_obs, tick_links);
-    else snk_exact_step_trace_kernel<false><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, actions, obs, rew, done, ticks, counters, n, tick_obs, tick_links);
+    if (P.cone) snk_exact_step_trace_kernel<true><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, n, tick_obs, tick_links);
+    else snk_exact_step_trace_kernel<false><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, n, tick_obs, tick_links);
     return cudaGetLastError();
 }
 
-cudaError_t snk_exact_launch_rollout(const KParams& P, float* state, const float* weights, const float* mean, const float* inv_std,
+cudaError_t snk_exact_launch_rollout(const KParams& P, float* state, float* tgt_scratch, const float* weights, const float* mean, const float* inv_std,
                                      const float* noise, int n_steps, float* returns, float* trace, int32_t* queue, int32_t* done_steps,
                                      unsigned long long* counters, int64_t n, cudaStream_t st) {
     RolloutArgs A;
@@ -633,8 +630,8 @@ cudaError_t snk_exact_launch_rollout(const KParams& P, float* state, const float
     const int per_cta = (TWARPS + SWARPS) * 32;
     const int64_t want = (n + EB - 1) / EB;
     dim3 grid((unsigned)(want < g_sms ? want : g_sms)), block(per_cta);
-    if (P.cone) snk_exact_rollout_kernel<true><<<grid, block, sizeof(StepSmem), st>>>(P, state, A, counters, n);
-    else snk_exact_rollout_kernel<false><<<grid, block, sizeof(StepSmem), st>>>(P, state, A, counters, n);
+    if (P.cone) snk_exact_rollout_kernel<true><<<grid, block, sizeof(StepSmem), st>>>(P, state, tgt_scratch, A, counters, n);
+    else snk_exact_rollout_kernel<false><<<grid, block, sizeof(StepSmem), st>>>(P, state, tgt_scratch, A, counters, n);
     return cudaGetLastError();
 }
 

@@ -89,7 +89,6 @@ struct RowsSmemStore {  // one warp, rows in shared memory
 #else
     float2 N2[NC][EB];
 #endif
-    float tgt[NJ][EB];
 };
 struct RowsTmemAux {    // one warp, rows in tensor memory: the shared-memory part
 #if SNK_PREB
@@ -97,14 +96,16 @@ struct RowsTmemAux {    // one warp, rows in tensor memory: the shared-memory pa
 #else
     float2 N2[NC][EB];
 #endif
-    float tgt[NJ][EB];
 };
 typedef RowsSmemStore ExSmem;
 
+// Both policies also carry `tg`, the 16 joint targets of the lane's current environment: a 64 B row of the handle's target
+// scratch array in global memory (written when the lane takes the environment, L1/L2 resident while it owns it).
 struct RowsS {
     RowsSmemStore* s;
     int lane;
-    SNK_HD float& tgt(int j) const { return s->tgt[j][lane]; }
+    float* tg;
+    SNK_HD float& tgt(int j) const { return tg[j]; }
 #if SNK_PREB
     SNK_HD void st_b(int k, float4 b0, float4 b1, float4 b2) const { s->B[0][k][lane] = b0; s->B[1][k][lane] = b1; s->B[2][k][lane] = b2; }
     SNK_HD void ld_n(int k, float4& x0, float4& b0, float& idn) const { x0 = s->X[0][k][lane]; b0 = s->B[0][k][lane]; idn = s->B[1][k][lane].w; }
@@ -136,7 +137,8 @@ struct RowsT {
     uint32_t taddr;  // TMEM address of this warp's quadrant: base + (32 * (warp % 4) << 16)
     RowsTmemAux* s;
     int lane;
-    __device__ __forceinline__ float& tgt(int j) const { return s->tgt[j][lane]; }
+    float* tg;
+    __device__ __forceinline__ float& tgt(int j) const { return tg[j]; }
 #if SNK_PREB
     __device__ __forceinline__ void st_b(int k, float4 b0, float4 b1, float4 b2) const { s->B[0][k][lane] = b0; s->B[1][k][lane] = b1; s->B[2][k][lane] = b2; }
     __device__ __forceinline__ void ld_b12(int k, float4& b1, float4& b2) const { b1 = s->B[1][k][lane]; b2 = s->B[2][k][lane]; }

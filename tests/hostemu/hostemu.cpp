@@ -31,17 +31,18 @@ struct Emu {
     int64_t n;
     float* state; // [n][64]
     ExSmem S;
+    float tgt[NJ];
     int64_t counters[4];
 };
 
 static void set_targets_from_actions(Emu* h, const float* a, int tid) {
     const KParams& P = h->P;
-    for (int j = 0; j < NJ; j++) h->S.tgt[j][tid] = 0.f;
+    for (int j = 0; j < NJ; j++) h->tgt[j] = 0.f;
     for (int k = 0; k < P.actdim; k++) {
         float v = a[k];
         v = (v < -1.f) ? -1.f : v; v = (v > 1.f) ? 1.f : v;
         int j = (P.gait == 0) ? 2 * k : (P.gait == 1) ? 2 * k + 1 : k;
-        h->S.tgt[j][tid] = v * P.sf;
+        h->tgt[j] = v * P.sf;
     }
 }
 
@@ -69,12 +70,12 @@ int emu_get_state(Emu* h, float* aos) {
 int emu_tick(Emu* h, const float* targets, int n_ticks, int32_t* iters_out, int32_t* contacts_out, float* height_out) {
     for (int64_t e = 0; e < h->n; e++) {
         ExEnv env; env.st = h->state + e * 64; env.tid = (int)(e & 31);
-        for (int j = 0; j < NJ; j++) h->S.tgt[j][env.tid] = targets[e * NJ + j];
+        for (int j = 0; j < NJ; j++) h->tgt[j] = targets[e * NJ + j];
         ex_load_base(env);
         ExTickOut to = {0, 0, 0.f, 0.f};
         for (int t = 0; t < n_ticks; t++) {
             bool ab;
-            RowsS R; R.s = &h->S; R.lane = env.tid;
+            RowsS R; R.s = &h->S; R.lane = env.tid; R.tg = h->tgt;
             if (h->P.cone) ex_tick<true>(h->T, h->P, R, env, true, false, &ab, &to); else ex_tick<false>(h->T, h->P, R, env, true, false, &ab, &to);
             h->counters[0]++; h->counters[1] += to.iterations;
         }
@@ -91,7 +92,7 @@ int emu_step(Emu* h, const float* actions, float* obs, float* rew, uint8_t* done
         set_targets_from_actions(h, actions + e * h->P.actdim, env.tid);
         ex_load_base(env);
         ExStepOut o;
-        RowsS R; R.s = &h->S; R.lane = env.tid;
+        RowsS R; R.s = &h->S; R.lane = env.tid; R.tg = h->tgt;
         if (h->P.cone) ex_env_step<true>(h->T, h->P, R, env, &o); else ex_env_step<false>(h->T, h->P, R, env, &o);
         for (int k = 0; k < SNK_OBS_DIM; k++) obs[e * SNK_OBS_DIM + k] = ex_obs_of(env, k);
         rew[e] = o.rew; done[e] = (uint8_t)o.done;
