@@ -32,17 +32,15 @@ __constant__ ExTables cT;
 
 #define FULL 0xffffffffu
 #define TWARPS 4 // warps with rows in tensor memory (one per TMEM lane quadrant)
-#if SNK_PREB
-#define SWARPS 0 // the shared memory holds the impulse-response columns of the four tensor-memory warps (4 x 50 KB)
-#else
-#define SWARPS 2 // warps with rows in shared memory
-#endif
-
-struct StepSmem {
+// Warps with rows in shared memory: a template parameter SW of the kernels.  Three (4 x 4 KB + 3 x 68 KB = 220 KB of shared
+// memory, 224 environments in flight per SM) give the highest steady-state throughput but leave only ~28 KB of the SM's
+// 256 KB for L1, which the per-environment state records then miss; two (152 KB, 192 environments, ~92 KB of L1) are faster
+// whenever the batch is only a few waves of the grid.  The launcher picks per call.
+#define SW_MAX 3
+template <int SW>
+struct StepSmemT {
     RowsTmemAux t[TWARPS];
-#if SWARPS > 0
-    RowsSmemStore s[SWARPS];
-#endif
+    RowsSmemStore s[SW];
     uint32_t tmem_base;
 };
 
@@ -307,12 +305,12 @@ __device__ __forceinline__ void run_rollout_warp(const KParams& P, Rows R, float
     }
 }
 
-template <bool CONE>
-__global__ void __launch_bounds__((TWARPS + SWARPS) * 32, 1)
+template <bool CONE, int SW>
+__global__ void __launch_bounds__((TWARPS + SW) * 32, 1)
 snk_exact_rollout_kernel(const KParams P, float* __restrict__ state, float* __restrict__ tgt_scratch, const RolloutArgs A,
                          unsigned long long* __restrict__ counters, int64_t n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    StepSmem& S = *reinterpret_cast<StepSmem*>(smem_raw);
+    StepSmemT<SW>& S = *reinterpret_cast<StepSmemT<SW>*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0) {
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S.tmem_base);
@@ -324,7 +322,7 @@ snk_exact_rollout_kernel(const KParams P, float* __restrict__ state, float* __re
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tbase = S.tmem_base;
     const int64_t first_base = ((int64_t)warp * gridDim.x + blockIdx.x) * 32;
-    const int64_t dyn_base = min((int64_t)gridDim.x * (TWARPS + SWARPS) * 32, n);
+    const int64_t dyn_base = min((int64_t)gridDim.x * (TWARPS + SW) * 32, n);
     if (warp < TWARPS) {
         RowsT R;
         R.taddr = tbase + ((uint32_t)(32 * warp) << 16);
@@ -332,27 +330,25 @@ snk_exact_rollout_kernel(const KParams P, float* __restrict__ state, float* __re
         R.lane = lane;
         run_rollout_warp<CONE>(P, R, state, tgt_scratch, A, counters, n, first_base, dyn_base);
     }
-#if SWARPS > 0
     else {
         RowsS R;
         R.s = &S.s[warp - TWARPS];
         R.lane = lane;
         run_rollout_warp<CONE>(P, R, state, tgt_scratch, A, counters, n, first_base, dyn_base);
     }
-#endif
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
 }
 
 // 6 warps per CTA, one CTA per SM: rows of warps 0-3 in tensor memory, of warps 4-5 in shared memory
-template <bool CONE>
-__global__ void __launch_bounds__((TWARPS + SWARPS) * 32, 1)
+template <bool CONE, int SW>
+__global__ void __launch_bounds__((TWARPS + SW) * 32, 1)
 snk_exact_step_kernel(const KParams P, float* __restrict__ state, float* __restrict__ tgt_scratch, const float* __restrict__ actions, float* __restrict__ obs,
                       float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks, unsigned long long* __restrict__ counters,
                       const int32_t* __restrict__ order, int64_t n, int active_warps, int spread) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    StepSmem& S = *reinterpret_cast<StepSmem*>(smem_raw);
+    StepSmemT<SW>& S = *reinterpret_cast<StepSmemT<SW>*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0) { // the whole tensor memory of the SM: 512 columns x 128 lanes
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S.tmem_base);
@@ -363,14 +359,14 @@ snk_exact_step_kernel(const KParams P, float* __restrict__ state, float* __restr
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tbase = S.tmem_base;
-    // first wave (SNK_EXACT_SPREAD): 3 (default) = warp-major, the two warps that have a scheduler to themselves (2, 3)
-    // first -- with the longest-first order the longest env-steps of the launch go to the fastest warps; 1 = warp-major in
-    // warp-index order; 0 = CTA-major; 2 = no static wave, everything from the global counter (ablations)
-#if SWARPS > 0
-    const int rank = (spread == 3) ? ((warp == 2) ? 0 : (warp == 3) ? 1 : (warp == 0) ? 2 : (warp == 1) ? 3 : warp) : warp;
-#else
-    const int rank = warp; // four equal warps, one per scheduler
-#endif
+    // first wave (SNK_EXACT_SPREAD): 3 (default) = warp-major, the warps that have a scheduler to themselves first -- with
+    // the longest-first order the longest env-steps of the launch go to the fastest warps; 1 = warp-major in warp-index
+    // order; 0 = CTA-major; 2 = no static wave, everything from the global counter (ablations).
+    // Warps w and w + 4 share scheduler w: with 7 active warps scheduler 3 has a single warp, with 6 schedulers 2 and 3 do;
+    // the warps that have a scheduler to themselves are the fastest and come first
+    int rank = warp;
+    if (spread == 3 && active_warps == 7) rank = (warp == 3) ? 0 : (warp < 3) ? warp + 1 : warp;
+    else if (spread == 3 && active_warps == 6) rank = (warp == 2) ? 0 : (warp == 3) ? 1 : (warp < 2) ? warp + 2 : warp;
     const int64_t first_base = (spread == 2) ? -1 : (spread ? ((int64_t)rank * gridDim.x + blockIdx.x) * 32 : ((int64_t)blockIdx.x * active_warps + warp) * 32);
     const int64_t dyn_base = (spread == 2) ? 0 : min((int64_t)gridDim.x * active_warps * 32, n);
     if (warp >= active_warps) {
@@ -382,14 +378,12 @@ snk_exact_step_kernel(const KParams P, float* __restrict__ state, float* __restr
         R.lane = lane;
         run_warp<CONE>(P, R, state, tgt_scratch, actions, obs, rew, done, ticks, counters, order, n, first_base, dyn_base);
     }
-#if SWARPS > 0
     else {
         RowsS R;
         R.s = &S.s[warp - TWARPS];
         R.lane = lane;
         run_warp<CONE>(P, R, state, tgt_scratch, actions, obs, rew, done, ticks, counters, order, n, first_base, dyn_base);
     }
-#endif
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
@@ -528,16 +522,21 @@ static int g_sms = 0, g_smem_ctas = 0;
 static bool g_rows_tmem = true; // SNK_EXACT_ROWS=smem selects the shared-memory-only variant
 static bool g_no_sort = false; // SNK_EXACT_ORDER=index disables the longest-first hand-out (ablation)
 static int g_spread = 3; // SNK_EXACT_SPREAD: first-wave hand-out policy (see snk_exact_step_kernel)
-static int g_active_warps = TWARPS + SWARPS; // SNK_EXACT_WARPS=1..6: ablation of the number of working warps per SM
+static int g_active_warps = 0; // SNK_EXACT_WARPS=1..7 forces the number of working warps per SM (0: chosen per launch)
 
-size_t snk_exact_smem_bytes() { return g_rows_tmem ? sizeof(StepSmem) : sizeof(RowsSmemStore); }
+// working warps per SM for a batch of n environments: 7 (three shared-memory warps) once the batch is about two waves of
+// the 7-warp grid, else 6 -- a single wave finishes sooner with fewer warps per scheduler.  Measured on B200 (env-steps/s,
+// 6 / 7 warps): 32 768 envs 3.10 M / 2.9 M, 65 536 3.90 M / 4.13 M, 131 072 4.05 M / 4.19 M, 262 144 4.13 M / 4.26 M,
+// 2^20 4.24 M / 4.50 M.
+static int warps_for(int64_t n) {
+    if (g_active_warps) return g_active_warps;
+    return (10 * n >= 18LL * g_sms * (TWARPS + SW_MAX) * 32) ? TWARPS + 3 : TWARPS + 2;
+}
+
+size_t snk_exact_smem_bytes() { return g_rows_tmem ? sizeof(StepSmemT<SW_MAX>) : sizeof(RowsSmemStore); }
 
 const char* snk_exact_variant() {
-#if SNK_PREB
-    return g_rows_tmem ? "rows in TMEM (4 warps), impulse-response columns in shared memory, 128 envs/SM" : "rows in shared memory, 32 envs per CTA";
-#else
-    return g_rows_tmem ? "rows in TMEM (4 warps) + shared memory (2 warps), 192 envs/SM" : "rows in shared memory, 3 x 32 envs/SM";
-#endif
+    return g_rows_tmem ? "rows in TMEM (4 warps) + shared memory (2 or 3 warps per launch), 192 / 224 envs/SM" : "rows in shared memory, 3 x 32 envs/SM";
 }
 
 // The model tables live in one __constant__ symbol per device: all live handles of a process must share one
@@ -559,17 +558,21 @@ cudaError_t snk_exact_configure(const ExTables* host_tables) {
     const char* sp = getenv("SNK_EXACT_SPREAD");
     g_spread = (sp && sp[0] >= '0' && sp[0] <= '3') ? sp[0] - '0' : 3;
     const char* w = getenv("SNK_EXACT_WARPS");
-    if (w && atoi(w) >= 1 && atoi(w) <= TWARPS + SWARPS) g_active_warps = atoi(w);
+    g_active_warps = (w && atoi(w) >= 1 && atoi(w) <= TWARPS + SW_MAX) ? atoi(w) : 0;
     cudaError_t e = cudaMemcpyToSymbol(cT, host_tables, sizeof(ExTables));
     const void* k1[6] = {(const void*)snk_exact_step_kernel_smem<true>, (const void*)snk_exact_step_kernel_smem<false>,
                          (const void*)snk_exact_tick_kernel<true>, (const void*)snk_exact_tick_kernel<false>,
                          (const void*)snk_exact_step_trace_kernel<true>, (const void*)snk_exact_step_trace_kernel<false>};
     for (int i = 0; i < 6 && e == cudaSuccess; i++)
         e = cudaFuncSetAttribute(k1[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowsSmemStore));
-    const void* k2[4] = {(const void*)snk_exact_step_kernel<true>, (const void*)snk_exact_step_kernel<false>,
-                         (const void*)snk_exact_rollout_kernel<true>, (const void*)snk_exact_rollout_kernel<false>};
+    const void* k2[4] = {(const void*)snk_exact_step_kernel<true, 2>, (const void*)snk_exact_step_kernel<false, 2>,
+                         (const void*)snk_exact_rollout_kernel<true, 2>, (const void*)snk_exact_rollout_kernel<false, 2>};
     for (int i = 0; i < 4 && e == cudaSuccess; i++)
-        e = cudaFuncSetAttribute(k2[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
+        e = cudaFuncSetAttribute(k2[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmemT<2>));
+    const void* k3[4] = {(const void*)snk_exact_step_kernel<true, 3>, (const void*)snk_exact_step_kernel<false, 3>,
+                         (const void*)snk_exact_rollout_kernel<true, 3>, (const void*)snk_exact_rollout_kernel<false, 3>};
+    for (int i = 0; i < 4 && e == cudaSuccess; i++)
+        e = cudaFuncSetAttribute(k3[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmemT<3>));
     if (e != cudaSuccess) return e;
     int dev = 0, per_sm = 0;
     e = cudaGetDevice(&dev);
@@ -584,7 +587,8 @@ cudaError_t snk_exact_configure(const ExTables* host_tables) {
 cudaError_t snk_exact_launch_step(const KParams& P, float* state, float* tgt_scratch, const float* actions, float* obs, float* rew, uint8_t* done,
                                   int32_t* ticks, unsigned long long* counters, uint8_t* bucket, int32_t* order, int64_t n, cudaStream_t st,
                                   int* launches) {
-    const int lanes = g_rows_tmem ? g_sms * (TWARPS + SWARPS) * 32 : g_smem_ctas * EB;
+    const int aw = warps_for(n);
+    const int lanes = g_rows_tmem ? g_sms * aw * 32 : g_smem_ctas * EB;
     const int32_t* use_order = nullptr;
     *launches = 1;
     if (bucket && order && n > lanes && !g_no_sort) {
@@ -597,12 +601,15 @@ cudaError_t snk_exact_launch_step(const KParams& P, float* state, float* tgt_scr
         *launches = 3;
     }
     if (g_rows_tmem) {
-        const int per_cta = (TWARPS + SWARPS) * 32;
         // a small batch gets one CTA per warp of environments: all SMs before a second warp per SM
-        const int64_t want = (g_spread == 1 || g_spread == 3) ? (n + EB - 1) / EB : (n + per_cta - 1) / per_cta;
+        const int sw = aw > TWARPS + 2 ? 3 : 2;
+        const int per_cta = (TWARPS + sw) * 32, per_cta_active = aw * 32;
+        const int64_t want = (g_spread == 1 || g_spread == 3) ? (n + EB - 1) / EB : (n + per_cta_active - 1) / per_cta_active;
         dim3 grid((unsigned)(want < g_sms ? want : g_sms)), block(per_cta);
-        if (P.cone) snk_exact_step_kernel<true><<<grid, block, sizeof(StepSmem), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n, g_active_warps, g_spread);
-        else snk_exact_step_kernel<false><<<grid, block, sizeof(StepSmem), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n, g_active_warps, g_spread);
+#define SNK_LAUNCH_STEP(C, S) snk_exact_step_kernel<C, S><<<grid, block, sizeof(StepSmemT<S>), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n, aw, g_spread)
+        if (sw == 3) { if (P.cone) SNK_LAUNCH_STEP(true, 3); else SNK_LAUNCH_STEP(false, 3); }
+        else { if (P.cone) SNK_LAUNCH_STEP(true, 2); else SNK_LAUNCH_STEP(false, 2); }
+#undef SNK_LAUNCH_STEP
     } else {
         const int64_t warps = (n + EB - 1) / EB;
         dim3 grid((unsigned)(warps < g_smem_ctas ? warps : g_smem_ctas)), block(EB);
@@ -627,11 +634,17 @@ cudaError_t snk_exact_launch_rollout(const KParams& P, float* state, float* tgt_
     RolloutArgs A;
     A.weights = weights; A.mean = mean; A.inv_std = inv_std; A.noise = noise; A.returns = returns; A.trace = trace; A.n_steps = n_steps;
     A.queue = queue; A.done_steps = done_steps;
-    const int per_cta = (TWARPS + SWARPS) * 32;
+    const int sw = warps_for(n) > TWARPS + 2 ? 3 : 2;
+    const int per_cta = (TWARPS + sw) * 32;
     const int64_t want = (n + EB - 1) / EB;
     dim3 grid((unsigned)(want < g_sms ? want : g_sms)), block(per_cta);
-    if (P.cone) snk_exact_rollout_kernel<true><<<grid, block, sizeof(StepSmem), st>>>(P, state, tgt_scratch, A, counters, n);
-    else snk_exact_rollout_kernel<false><<<grid, block, sizeof(StepSmem), st>>>(P, state, tgt_scratch, A, counters, n);
+    if (sw == 3) {
+        if (P.cone) snk_exact_rollout_kernel<true, 3><<<grid, block, sizeof(StepSmemT<3>), st>>>(P, state, tgt_scratch, A, counters, n);
+        else snk_exact_rollout_kernel<false, 3><<<grid, block, sizeof(StepSmemT<3>), st>>>(P, state, tgt_scratch, A, counters, n);
+    } else {
+        if (P.cone) snk_exact_rollout_kernel<true, 2><<<grid, block, sizeof(StepSmemT<2>), st>>>(P, state, tgt_scratch, A, counters, n);
+        else snk_exact_rollout_kernel<false, 2><<<grid, block, sizeof(StepSmemT<2>), st>>>(P, state, tgt_scratch, A, counters, n);
+    }
     return cudaGetLastError();
 }
 

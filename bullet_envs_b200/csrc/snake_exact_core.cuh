@@ -59,43 +59,28 @@ struct ExTables {
 };
 
 // -----------------------------------------------------------------------------------------------
-// Contact-row storage.  One record of 18 words per contact and environment:
+// Contact-row storage.  One record of 17 words per contact and environment:
 //   word  0      normal impulse                      (solver state)
-//   words 1-3    lever arm r about the chain's centre of mass
-//   words 4-9    friction directions d1, d2 (anisotropic, not normalised)
+//   words 1-2    lever arm r.x, r.y about the chain's centre of mass
+//   word  3      invD_n                              (words 0-3 are all the normal sweep reads from the record)
+//   word  4      r.z
+//   words 5-9    friction directions d1.xyz, d2.x, d2.z (anisotropic, not normalised).  d2.y is not stored: the directions are
+//                columns of the symmetric matrix A = Rl diag(aniso) Rl^T (d1 = -A e_y, d2 = A e_x), so d2.y = -d1.x
 //   words 10-11  rhs_1 invD_1, rhs_2 invD_2
 //   words 12-13  invD_1, invD_2
 //   words 14-15  friction impulses                   (solver state)
-//   N2           rhs_n invD_n, invD_n                (only the normal sweep reads these)
+//   N1           rhs_n invD_n                        (only the normal sweep reads it)
 // Words 0-15 live either in shared memory as [word/4][contact][lane] float4 columns (bank = lane) or in
 // TENSOR MEMORY: TMEM lane = thread, column = 16 * contact + word, moved with tcgen05.ld/st 32x32b
-// (sm_100a; the 512 columns of a warp's TMEM quadrant hold exactly 32 contacts x 16 words).  N2 and
-// the joint targets are always in shared memory.
+// (sm_100a; the 512 columns of a warp's TMEM quadrant hold exactly 32 contacts x 16 words).  N1 is always in
+// shared memory (4 KB per warp); the joint targets are in global memory (RowsS/RowsT::tg).
 // -----------------------------------------------------------------------------------------------
-// SNK_PREB (compile-time, default 0).  1 = the impulse-response columns of every row -- Ji (r x n), Ji (r x d1), Ji (r x d2) --
-// are computed once per tick and kept in shared memory as three float4 per contact,
-//   B[0] = (Ji rn | rhs_n invD_n)   B[1] = (Ji (r x d1) | invD_n)   B[2] = (Ji (r x d2) | unused)
-// which takes 4 / 9 instructions and 1 / 4 dependent operations off every normal row / friction pair of every sweep, but fills the
-// shared memory with the columns of the four tensor-memory warps, so the two shared-memory warps go.  MEASURED SLOWER on B200
-// (2^20 envs: 3.81 M env-steps/s against 4.37 M; a lone warp gains only 4 %, 5.79 vs 6.05 ms per step at 4 096 envs), so the
-// default is 0: only (rhs_n invD_n, invD_n) in shared memory, 4 + 2 warps per SM.  Kept as a documented, parity-green variant.
-#ifndef SNK_PREB
-#define SNK_PREB 0
-#endif
-struct RowsSmemStore {  // one warp, rows in shared memory
+struct RowsSmemStore {  // one warp, rows in shared memory: 69 632 B
     float4 X[4][NC][EB];
-#if SNK_PREB
-    float4 B[3][NC][EB];
-#else
-    float2 N2[NC][EB];
-#endif
+    float N1[NC][EB];
 };
-struct RowsTmemAux {    // one warp, rows in tensor memory: the shared-memory part
-#if SNK_PREB
-    float4 B[3][NC][EB];
-#else
-    float2 N2[NC][EB];
-#endif
+struct RowsTmemAux {    // one warp, rows in tensor memory: the shared-memory part, 4 096 B
+    float N1[NC][EB];
 };
 typedef RowsSmemStore ExSmem;
 
@@ -106,14 +91,8 @@ struct RowsS {
     int lane;
     float* tg;
     SNK_HD float& tgt(int j) const { return tg[j]; }
-#if SNK_PREB
-    SNK_HD void st_b(int k, float4 b0, float4 b1, float4 b2) const { s->B[0][k][lane] = b0; s->B[1][k][lane] = b1; s->B[2][k][lane] = b2; }
-    SNK_HD void ld_n(int k, float4& x0, float4& b0, float& idn) const { x0 = s->X[0][k][lane]; b0 = s->B[0][k][lane]; idn = s->B[1][k][lane].w; }
-    SNK_HD void ld_b12(int k, float4& b1, float4& b2) const { b1 = s->B[1][k][lane]; b2 = s->B[2][k][lane]; }
-#else
-    SNK_HD void st_n2(int k, float a, float b) const { s->N2[k][lane] = make_float2(a, b); }
-    SNK_HD void ld_n(int k, float4& x0, float2& n2) const { x0 = s->X[0][k][lane]; n2 = s->N2[k][lane]; }
-#endif
+    SNK_HD void st_n1(int k, float a) const { s->N1[k][lane] = a; }
+    SNK_HD void ld_n(int k, float4& x0, float& n1) const { x0 = s->X[0][k][lane]; n1 = s->N1[k][lane]; }
     SNK_HD void st16(int k, float4 x0, float4 x1, float4 x2, float4 x3) const {
         s->X[0][k][lane] = x0; s->X[1][k][lane] = x1; s->X[2][k][lane] = x2; s->X[3][k][lane] = x3;
     }
@@ -139,20 +118,11 @@ struct RowsT {
     int lane;
     float* tg;
     __device__ __forceinline__ float& tgt(int j) const { return tg[j]; }
-#if SNK_PREB
-    __device__ __forceinline__ void st_b(int k, float4 b0, float4 b1, float4 b2) const { s->B[0][k][lane] = b0; s->B[1][k][lane] = b1; s->B[2][k][lane] = b2; }
-    __device__ __forceinline__ void ld_b12(int k, float4& b1, float4& b2) const { b1 = s->B[1][k][lane]; b2 = s->B[2][k][lane]; }
-    __device__ __forceinline__ void ld_n(int k, float4& x0, float4& b0, float& idn) const {
+    __device__ __forceinline__ void st_n1(int k, float a) const { s->N1[k][lane] = a; }
+    __device__ __forceinline__ void ld_n(int k, float4& x0, float& n1) const {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(x0.x), "=f"(x0.y), "=f"(x0.z), "=f"(x0.w) : "r"(taddr + 16u * k) : "memory");
-        b0 = s->B[0][k][lane]; idn = s->B[1][k][lane].w;
+        n1 = s->N1[k][lane];
     }
-#else
-    __device__ __forceinline__ void st_n2(int k, float a, float b) const { s->N2[k][lane] = make_float2(a, b); }
-    __device__ __forceinline__ void ld_n(int k, float4& x0, float2& n2) const {
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(x0.x), "=f"(x0.y), "=f"(x0.z), "=f"(x0.w) : "r"(taddr + 16u * k) : "memory");
-        n2 = s->N2[k][lane];
-    }
-#endif
     __device__ __forceinline__ void st4(uint32_t col, float4 v) const {
         asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr + col), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
     }
@@ -471,6 +441,9 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
         const V3 uJ = mk(t0.x, t2.z, t2.w);
         const float dist = t0.w + p0z;
         const V3 r = mk(t0.y - hc.x, t0.z - hc.y, t0.w - hc.z);
+        // d2.y equals -d1.x up to round-off (A is symmetric): the record stores only d1.x and the solver reconstructs d2.y from
+        // it, while the effective mass and right-hand side here use the d2.y pass 1 computed (a 1e-7 relative difference; writing
+        // -d1.x here instead made the fma contractions of the row-storage instantiations differ, i.e. lost their bit-identity)
         const V3 d1 = mk(t1.x, t1.y, t1.z), d2 = mk(t1.w, t2.x, t2.y);
         // velocity of the contact point under the free rigid motion plus the new joint rates.  The rigid
         // field is (wf, velocity VC0 at C) with VC0 chosen so that the base origin gets v0 + dt a0:
@@ -490,13 +463,9 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
         const float D1 = dot(d1, d1) * invM + dot(r1, J1), D2 = dot(d2, d2) * invM + dot(r2, J2);
         const float iD1 = 1.f / D1, iD2 = 1.f / D2;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        R.st16(k, on ? make_float4(0.f, r.x, r.y, r.z) : z4, on ? make_float4(d1.x, d1.y, d1.z, d2.x) : z4,
-               on ? make_float4(d2.y, d2.z, -dot(d1, vp) * iD1, -dot(d2, vp) * iD2) : z4, on ? make_float4(iD1, iD2, 0.f, 0.f) : z4);
-#if SNK_PREB
-        R.st_b(k, on ? make_float4(Jn.x, Jn.y, Jn.z, rhsn) : z4, on ? make_float4(J1.x, J1.y, J1.z, iDn) : z4, on ? make_float4(J2.x, J2.y, J2.z, 0.f) : z4);
-#else
-        R.st_n2(k, on ? rhsn : 0.f, on ? iDn : 0.f);
-#endif
+        R.st16(k, on ? make_float4(0.f, r.x, r.y, iDn) : z4, on ? make_float4(r.z, d1.x, d1.y, d1.z) : z4,
+               on ? make_float4(d2.x, d2.z, -dot(d1, vp) * iD1, -dot(d2, vp) * iD2) : z4, on ? make_float4(iD1, iD2, 0.f, 0.f) : z4);
+        R.st_n1(k, on ? rhsn : 0.f);
     }
     R.fence_st();
 
@@ -511,79 +480,6 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
     const float sthr = sqrtf(P.resthr), mu = P.mu;
     bool frozen = !commit;
     int sweeps = 0;
-#if SNK_PREB
-    // A frozen lane re-selects its old impulse, so its impulse change is exactly zero and (dw, dV) stay put.
-#pragma unroll 1
-    for (int it = 0; it < P.iters; it++) {
-        if (ex_all(frozen)) break;
-        float viol = 0.f; // max over the rows of |d| - sqrt(thr) invD (in the row's scaled units)
-        {   // ---- normal rows; the record of row k+1 is fetched while row k is on the chain
-            float4 nx, nb; float nidn;
-            R.ld_n(0, nx, nb, nidn);
-#pragma unroll 4
-            for (int k = 0; k < NC; k++) {
-                R.fence4(nx);
-                const float4 x0 = nx, b0 = nb;  // (ln, rx, ry, rz), (Ji rn | rhs_n invD_n)
-                const float idn = nidn;
-                R.ld_n((k + 1) & (NC - 1), nx, nb, nidn);
-                const float ln = x0.x;
-                const float p = ln + b0.w;
-                float jd = fmaf(dw.x, x0.z, dV.z);
-                jd = fmaf(-dw.y, x0.y, jd);
-                const float sum = fmaxf(fmaf(-jd, idn, p), 0.f);
-                const float sel = frozen ? ln : sum;
-                const float dd = sel - ln;
-                R.st_ln(k, sel);
-                dw.x = fmaf(b0.x, dd, dw.x); dw.y = fmaf(b0.y, dd, dw.y); dw.z = fmaf(b0.z, dd, dw.z);
-                dV.z = fmaf(dd, invM, dV.z);
-                viol = fmaxf(viol, fmaf(-sthr, idn, fabsf(dd)));
-            }
-            R.fence4(nx);
-            R.fence_st();
-        }
-        {   // ---- friction pairs
-            float4 n0, n1, n2_, n3, nb1, nb2;
-            R.ld16(0, n0, n1, n2_, n3);
-            R.ld_b12(0, nb1, nb2);
-#pragma unroll 2
-            for (int k = 0; k < NC; k++) {
-                R.fence16(n0, n1, n2_, n3);
-                const float4 x0 = n0, x1 = n1, x2 = n2_, x3 = n3, b1 = nb1, b2 = nb2;
-                R.ld16((k + 1) & (NC - 1), n0, n1, n2_, n3);
-                R.ld_b12((k + 1) & (NC - 1), nb1, nb2);
-                const float rx = x0.y, ry = x0.z, rz = x0.w;
-                const float pa = x3.z + x2.z, pb = x3.w + x2.w, lim = mu * x0.x;
-                // u = dV + dw x r
-                const float ux = fmaf(-dw.z, ry, fmaf(dw.y, rz, dV.x));
-                const float uy = fmaf(-dw.x, rz, fmaf(dw.z, rx, dV.y));
-                const float uz = fmaf(-dw.y, rx, fmaf(dw.x, ry, dV.z));
-                const float g1 = fmaf(x1.z, uz, fmaf(x1.y, uy, x1.x * ux)), g2 = fmaf(x2.y, uz, fmaf(x2.x, uy, x1.w * ux));
-                float sa = fmaf(-g1, x3.x, pa), sb = fmaf(-g2, x3.y, pb);
-                if (CONE) { // implicit cone: radial projection onto the disc of radius mu * lambda_n,
-                            // s <- s min(1, lim / |s|)  (0/0 and lim/0 resolve to 1 through fminf)
-                    const float sc = fminf(1.f, lim * ex_rsqrt_fast(fmaf(sa, sa, sb * sb)));
-                    sa *= sc; sb *= sc;
-                } else {
-                    sa = fminf(fmaxf(sa, -lim), lim);
-                    sb = fminf(fmaxf(sb, -lim), lim);
-                }
-                sa = frozen ? x3.z : sa; sb = frozen ? x3.w : sb;
-                const float da = sa - x3.z, db = sb - x3.w;
-                R.st_lf(k, sa, sb);
-                const float fx = fmaf(x1.w, db, x1.x * da), fy = fmaf(x2.x, db, x1.y * da), fz = fmaf(x2.y, db, x1.z * da);
-                dV.x = fmaf(fx, invM, dV.x); dV.y = fmaf(fy, invM, dV.y); dV.z = fmaf(fz, invM, dV.z);
-                dw.x = fmaf(b1.x, da, fmaf(b2.x, db, dw.x));
-                dw.y = fmaf(b1.y, da, fmaf(b2.y, db, dw.y));
-                dw.z = fmaf(b1.z, da, fmaf(b2.z, db, dw.z));
-                // (da D1 + db D2)^2 <= thr  <=>  |da invD2 + db invD1| <= sqrt(thr) invD1 invD2
-                viol = fmaxf(viol, fmaf(-sthr * x3.x, x3.y, fabsf(fmaf(da, x3.y, db * x3.x))));
-            }
-            R.fence16(n0, n1, n2_, n3);
-            R.fence_st();
-        }
-        if (!frozen) { sweeps++; frozen = (viol <= 0.f); }
-    }
-#else
 #pragma unroll 1
     for (int it = 0; it < P.iters; it++) {
         if (ex_all(frozen)) break;
@@ -594,18 +490,18 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
         S3 Jg;
         Jg.xx = Ji.xx * gate; Jg.xy = Ji.xy * gate; Jg.xz = Ji.xz * gate; Jg.yy = Ji.yy * gate; Jg.yz = Ji.yz * gate; Jg.zz = Ji.zz * gate;
         {   // ---- normal rows; the record of row k+1 is fetched while row k is on the chain
-            float4 nx; float2 nn;
+            float4 nx; float nn;
             R.ld_n(0, nx, nn);
 #pragma unroll 4
             for (int k = 0; k < NC; k++) {
                 R.fence4(nx);
-                const float4 x0 = nx; const float2 n2 = nn;  // (ln, rx, ry, rz), (rhs_n invD_n, invD_n)
+                const float4 x0 = nx; const float n1 = nn;  // (ln, rx, ry, invD_n), rhs_n invD_n
                 R.ld_n((k + 1) & (NC - 1), nx, nn);
                 const float ln = x0.x;
-                const float p = ln + n2.x;
+                const float p = ln + n1;
                 float jd = fmaf(dw.x, x0.z, dV.z);
                 jd = fmaf(-dw.y, x0.y, jd);
-                const float sum = fmaxf(fmaf(-jd, n2.y, p), 0.f);
+                const float sum = fmaxf(fmaf(-jd, x0.w, p), 0.f);
                 const float dd = sum - ln;
                 R.st_ln(k, frozen ? ln : sum);
                 const float t1 = x0.z * dd, t2 = -x0.y * dd; // rn * dd
@@ -613,7 +509,7 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
                 dw.y = fmaf(Jg.xy, t1, fmaf(Jg.yy, t2, dw.y));
                 dw.z = fmaf(Jg.xz, t1, fmaf(Jg.yz, t2, dw.z));
                 dV.z = fmaf(dd, iM, dV.z);
-                viol = fmaxf(viol, fmaf(-sthr, n2.y, fabsf(dd)));
+                viol = fmaxf(viol, fmaf(-sthr, x0.w, fabsf(dd)));
             }
             R.fence4(nx);
             R.fence_st();
@@ -626,13 +522,14 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
                 R.fence16(n0, n1, n2_, n3);
                 const float4 x0 = n0, x1 = n1, x2 = n2_, x3 = n3;
                 R.ld16((k + 1) & (NC - 1), n0, n1, n2_, n3);
-                const float rx = x0.y, ry = x0.z, rz = x0.w;
+                const float rx = x0.y, ry = x0.z, rz = x1.x;
                 const float pa = x3.z + x2.z, pb = x3.w + x2.w, lim = mu * x0.x;
                 // u = dV + dw x r
                 const float ux = fmaf(-dw.z, ry, fmaf(dw.y, rz, dV.x));
                 const float uy = fmaf(-dw.x, rz, fmaf(dw.z, rx, dV.y));
                 const float uz = fmaf(-dw.y, rx, fmaf(dw.x, ry, dV.z));
-                const float g1 = fmaf(x1.z, uz, fmaf(x1.y, uy, x1.x * ux)), g2 = fmaf(x2.y, uz, fmaf(x2.x, uy, x1.w * ux));
+                // d1 = (x1.y, x1.z, x1.w), d2 = (x2.x, -x1.y, x2.y)
+                const float g1 = fmaf(x1.w, uz, fmaf(x1.z, uy, x1.y * ux)), g2 = fmaf(x2.y, uz, fmaf(-x1.y, uy, x2.x * ux));
                 float sa = fmaf(-g1, x3.x, pa), sb = fmaf(-g2, x3.y, pb);
                 if (CONE) { // implicit cone: radial projection onto the disc of radius mu * lambda_n,
                             // s <- s min(1, lim / |s|)  (0/0 and lim/0 resolve to 1 through fminf)
@@ -644,7 +541,7 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
                 }
                 const float da = sa - x3.z, db = sb - x3.w;
                 R.st_lf(k, frozen ? x3.z : sa, frozen ? x3.w : sb);
-                const float fx = fmaf(x1.w, db, x1.x * da), fy = fmaf(x2.x, db, x1.y * da), fz = fmaf(x2.y, db, x1.z * da);
+                const float fx = fmaf(x2.x, db, x1.y * da), fy = fmaf(-x1.y, db, x1.z * da), fz = fmaf(x2.y, db, x1.w * da);
                 const float tx = fmaf(ry, fz, -rz * fy), ty = fmaf(rz, fx, -rx * fz), tz = fmaf(rx, fy, -ry * fx); // r x f
                 dV.x = fmaf(fx, iM, dV.x); dV.y = fmaf(fy, iM, dV.y); dV.z = fmaf(fz, iM, dV.z);
                 dw.x = fmaf(Jg.xx, tx, fmaf(Jg.xy, ty, fmaf(Jg.xz, tz, dw.x)));
@@ -658,7 +555,6 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
         }
         if (!frozen) { sweeps++; frozen = (viol <= 0.f); }
     }
-#endif
     out->iterations = sweeps;
     out->contacts = ex_popc(act);
 
@@ -702,8 +598,10 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
                 float4 x0, x1, x2, x3;
                 R.ld16(k, x0, x1, x2, x3);
                 R.fence16(x0, x1, x2, x3);
-                V3 f = mk(x1.x * x3.z + x1.w * x3.w, x1.y * x3.z + x2.x * x3.w, x0.x + x1.z * x3.z + x2.y * x3.w) * inv_dt;
-                V3 r = mk(x0.y + hc.x, x0.z + hc.y, x0.w + hc.z); // back to the base origin
+                // contact force n ln + d1 la + d2 lb with d2 = (x2.x, -x1.y, x2.y); explicit fma so that every row-storage
+                // instantiation rounds alike
+                V3 f = mk(fmaf(x2.x, x3.w, x1.y * x3.z), fmaf(-x1.y, x3.w, x1.z * x3.z), fmaf(x2.y, x3.w, fmaf(x1.w, x3.z, x0.x))) * inv_dt;
+                V3 r = mk(x0.y + hc.x, x0.z + hc.y, x1.x + hc.z); // back to the base origin
                 SF = SF - f;
                 SN = SN - cross(r, f);
             }

@@ -151,8 +151,10 @@ def test_golden_scenarios_on_the_gpu(torch, golden):
                 break                                           # fp32 trajectories part ways after a discrete event
             agree += 1
             assert np.abs(ob[0, :16] - golden[name + "/obs"][t + 1][:16]).max() < 1e-5, (name, t)
-            if t < 3:   # ~90 ticks of fp32 vs fp64 contact dynamics
-                assert np.abs(ob[0, 48:51] - golden[name + "/obs"][t + 1][48:51]).max() < 5e-3, (name, t)
+            if t < 3:   # ~90 ticks of free-running fp32 vs fp64 contact dynamics: round-off grows about 3x per env-step (the same fp32
+                        # code on the CPU, tests/hostemu, lands anywhere between 1e-4 and 1e-2 by the third step depending on how the
+                        # arithmetic is associated), so this bounds the order of magnitude only
+                assert np.abs(ob[0, 48:51] - golden[name + "/obs"][t + 1][48:51]).max() < (2e-3 if t == 0 else 2e-2), (name, t)
                 assert abs(r[0] - golden[name + "/rew"][t]) < 2e-2, (name, t)
         assert agree >= min(len(acts), 8), (name, agree)
         env.close()
