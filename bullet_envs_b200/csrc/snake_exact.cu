@@ -5,20 +5,21 @@
 // snake_exact_core.cuh for the algorithm and oracle/snake_oracle.c:tick_exact for its CPU twin).
 //
 // One launch = one SubprocVecEnv.step(): clip + createAction, the data-dependent 0..41-tick loop,
-// observation, reward, termination, auto-reset.  The grid is persistent, one CTA of 6 warps per SM,
-// each lane owning one environment at a time (192 environments in flight per SM).  The per-environment
-// working set is the contact-row table (32 contacts x 18 words, re-read by every solver sweep), and what
+// observation, reward, termination, auto-reset.  The grid is persistent, one CTA of 4 + SW warps per SM (SW = 2 or 3,
+// picked per launch), each lane owning one environment at a time (192 / 224 environments in flight per SM).  The
+// per-environment working set is the contact-row table (32 contacts x 17 words, re-read by every solver sweep), and what
 // bounds the kernel is how many of those tables fit on chip.  Blackwell has two on-chip memories:
 //   warps 0-3  keep their rows in TENSOR MEMORY (tcgen05.ld/st 32x32b: TMEM lane = thread, the 512 columns
-//              of the warp's quadrant = 32 contacts x 16 words), plus 10 KB of shared memory each;
-//   warps 4-5  keep theirs in shared memory ([word][contact][lane] columns, conflict free), 74 KB each.
+//              of the warp's quadrant = 32 contacts x 16 words), plus 4 KB of shared memory each;
+//   warps 4-6  keep theirs in shared memory ([word][contact][lane] columns, conflict free), 68 KB each.
 // The lock-step unit of a warp is ONE PHYSICS TICK, not one env-step: a lane whose environment has
 // finished its tick loop writes its outputs and takes the next environment from a global counter while
 // the other lanes keep ticking, so the 0..41 spread of tick counts costs no idle lanes.
 //
 // Other data: base state and loop progress in registers, joint state in the environment's 256 B record
-// of the handle's [N][64] state array (L1 resident while the lane owns the environment), model tables in
-// constant memory at warp-uniform addresses.
+// of the handle's [N][64] state array and the joint targets in its 64 B row of the handle's target scratch
+// array (both L1/L2 resident while the lane owns the environment), model tables in constant memory at
+// warp-uniform addresses.
 //
 // Reference call sites replaced: SnakeGymEnv.py:33-50,82-103; snake.py:209-306,336-341;
 // ppo/multiprocessing_env.py:11-16; snake_gait_test.py:96-104 (raw ticks).

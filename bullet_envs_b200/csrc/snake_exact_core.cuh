@@ -17,7 +17,7 @@
 //   finish  base velocity/pose integration, joint-0 reaction force.
 //
 // Data placement: the 13 base-state floats, the chain cursor and the solver's
-// 6-vector live in registers; the contact-row table (32 contacts x 18 words, re-read by every sweep)
+// 6-vector live in registers; the contact-row table (32 contacts x 17 words, re-read by every sweep)
 // lives in tensor memory or shared memory behind a row-storage policy (RowsT / RowsS below); joint
 // angles/velocities/torques stay in the environment's 256 B record of the handle's [N][64] state
 // array (L1 resident while a lane owns the environment); model tables are read from constant memory
