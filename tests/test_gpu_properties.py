@@ -101,6 +101,29 @@ def test_row_storage_variants_agree(torch):
     assert sums[0] == sums[1]
 
 
+def test_warp_count_and_hand_out_policy_do_not_change_results(torch):
+    """The launcher picks 6 or 7 working warps per SM (two or three shared-memory warps) by batch size and hands the first wave
+    out warp-major, fastest warps first: none of that may change a bit of the results.  70 000 environments (above the switch
+    to 7 warps), forced to 6 / 7 / 4 warps and to the CTA-major and fully dynamic hand-outs, in subprocesses; checksums."""
+    import os, subprocess, sys
+    code = ("import torch, hashlib; from bullet_envs_b200 import SnakeVecEnv;"
+            "g=torch.Generator().manual_seed(4); a=(torch.rand((2,70000,8),generator=g)*2-1).cuda();"
+            "e=SnakeVecEnv(num_envs=70000,device=0); e.reset(as_torch=True);"
+            "h=hashlib.sha256();\n"
+            "for t in range(2):\n"
+            "    o,r,d,_=e.step(a[t]); h.update(o.cpu().numpy().tobytes()); h.update(r.cpu().numpy().tobytes()); h.update(e.last_ticks.cpu().numpy().tobytes())\n"
+            "print('SUM', h.hexdigest())")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sums = []
+    for extra in ({}, {"SNK_EXACT_WARPS": "6"}, {"SNK_EXACT_WARPS": "7"}, {"SNK_EXACT_WARPS": "4"}, {"SNK_EXACT_SPREAD": "0"}, {"SNK_EXACT_SPREAD": "2"},
+                  {"SNK_EXACT_ORDER": "index"}):
+        env = dict(os.environ, PYTHONPATH=root, **extra)
+        out = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        sums.append([l for l in out.stdout.splitlines() if l.startswith("SUM")][0])
+    assert len(set(sums)) == 1, sums
+
+
 def test_checkpoint_resume_is_bit_exact(torch):
     from bullet_envs_b200 import SnakeVecEnv
     n = 300
