@@ -12,7 +12,8 @@ import os
 from .urdf_model import CModel  # noqa: F401  (re-exported)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsnake_b200.so")
+# SNK_B200_LIB points at another build of the same library (compile-variant A/B runs); the default is the in-tree build
+LIB_PATH = os.environ.get("SNK_B200_LIB") or os.path.join(_HERE, "csrc", "libsnake_b200.so")
 
 
 class CParams(ctypes.Structure):

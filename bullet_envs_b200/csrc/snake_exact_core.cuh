@@ -39,6 +39,16 @@
 
 #define EB 32 // environments (= lanes) per warp
 
+// unroll factors of the solver's row loops (normal rows / friction pairs)
+#ifndef SNK_UNROLL_N
+#define SNK_UNROLL_N 4
+#endif
+#ifndef SNK_UNROLL_F
+#define SNK_UNROLL_F 2
+#endif
+#define SNK_PRAGMA_(x) _Pragma(#x)
+#define SNK_UNROLL(n) SNK_PRAGMA_(unroll n)
+
 // Model tables for the exact kernel (fp32; constant memory on the device).
 struct ExTables {
     float jR0[NJ][9];
@@ -492,7 +502,7 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
         {   // ---- normal rows; the record of row k+1 is fetched while row k is on the chain
             float4 nx; float nn;
             R.ld_n(0, nx, nn);
-#pragma unroll 4
+SNK_UNROLL(SNK_UNROLL_N)
             for (int k = 0; k < NC; k++) {
                 R.fence4(nx);
                 const float4 x0 = nx; const float n1 = nn;  // (ln, rx, ry, invD_n), rhs_n invD_n
@@ -517,7 +527,7 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
         {   // ---- friction pairs
             float4 n0, n1, n2_, n3;
             R.ld16(0, n0, n1, n2_, n3);
-#pragma unroll 2
+SNK_UNROLL(SNK_UNROLL_F)
             for (int k = 0; k < NC; k++) {
                 R.fence16(n0, n1, n2_, n3);
                 const float4 x0 = n0, x1 = n1, x2 = n2_, x3 = n3;
