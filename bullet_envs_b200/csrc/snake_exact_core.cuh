@@ -46,6 +46,24 @@
 #ifndef SNK_UNROLL_F
 #define SNK_UNROLL_F 2
 #endif
+// operation-order variants of the friction pair.  They change rounding in the last bit and, through ptxas' register allocation,
+// the number of register-bank conflicts in the solver loops (one lost issue cycle each): screened by counting conflicts in the
+// SASS, then measured (profiles/README.md).  Defaults = the fastest measured combination (G = 1, DW = 1).
+#ifndef SNK_VAR_U
+#define SNK_VAR_U 0
+#endif
+#ifndef SNK_VAR_G
+#define SNK_VAR_G 1
+#endif
+#ifndef SNK_VAR_DW
+#define SNK_VAR_DW 1
+#endif
+#ifndef SNK_VAR_F
+#define SNK_VAR_F 0
+#endif
+#ifndef SNK_VAR_SEL
+#define SNK_VAR_SEL 0
+#endif
 #define SNK_PRAGMA_(x) _Pragma(#x)
 #define SNK_UNROLL(n) SNK_PRAGMA_(unroll n)
 
@@ -77,8 +95,10 @@ struct ExTables {
 //   words 5-9    friction directions d1.xyz, d2.x, d2.z (anisotropic, not normalised).  d2.y is not stored: the directions are
 //                columns of the symmetric matrix A = Rl diag(aniso) Rl^T (d1 = -A e_y, d2 = A e_x), so d2.y = -d1.x
 //   words 10-11  rhs_1 invD_1, rhs_2 invD_2
-//   words 12-13  invD_1, invD_2
-//   words 14-15  friction impulses                   (solver state)
+//   words 12-13  friction impulses                   (solver state)
+//   words 14-15  invD_1, invD_2
+//                (the impulses sit 2 words after rhs invD so that the two operands of  impulse + rhs invD  come from different
+//                register banks when the 16 words arrive in 16 consecutive registers)
 //   N1           rhs_n invD_n                        (only the normal sweep reads it)
 // Words 0-15 live either in shared memory as [word/4][contact][lane] float4 columns (bank = lane) or in
 // TENSOR MEMORY: TMEM lane = thread, column = 16 * contact + word, moved with tcgen05.ld/st 32x32b
@@ -111,7 +131,7 @@ struct RowsS {
         x0 = s->X[0][k][lane]; x1 = s->X[1][k][lane]; x2 = s->X[2][k][lane]; x3 = s->X[3][k][lane];
     }
     SNK_HD void st_ln(int k, float v) const { s->X[0][k][lane].x = v; }
-    SNK_HD void st_lf(int k, float a, float b) const { *reinterpret_cast<float2*>(&s->X[3][k][lane].z) = make_float2(a, b); }
+    SNK_HD void st_lf(int k, float a, float b) const { *reinterpret_cast<float2*>(&s->X[3][k][lane].x) = make_float2(a, b); }
     SNK_HD void fence4(float4&) const {}
     SNK_HD void fence16(float4&, float4&, float4&, float4&) const {}
     SNK_HD void fence_st() const {}
@@ -152,7 +172,7 @@ struct RowsT {
         asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr + 16u * k), "f"(v) : "memory");
     }
     __device__ __forceinline__ void st_lf(int k, float a, float b) const {
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr + 16u * k + 14u), "f"(a), "f"(b) : "memory");
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr + 16u * k + 12u), "f"(a), "f"(b) : "memory");
     }
     __device__ __forceinline__ void fence4(float4& x0) const {
         asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(x0.x), "+f"(x0.y), "+f"(x0.z), "+f"(x0.w)::"memory");
@@ -474,7 +494,7 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
         const float iD1 = 1.f / D1, iD2 = 1.f / D2;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         R.st16(k, on ? make_float4(0.f, r.x, r.y, iDn) : z4, on ? make_float4(r.z, d1.x, d1.y, d1.z) : z4,
-               on ? make_float4(d2.x, d2.z, -dot(d1, vp) * iD1, -dot(d2, vp) * iD2) : z4, on ? make_float4(iD1, iD2, 0.f, 0.f) : z4);
+               on ? make_float4(d2.x, d2.z, -dot(d1, vp) * iD1, -dot(d2, vp) * iD2) : z4, on ? make_float4(0.f, 0.f, iD1, iD2) : z4);
         R.st_n1(k, on ? rhsn : 0.f);
     }
     R.fence_st();
@@ -487,7 +507,7 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
     // (converged, or masked from the start) is `frozen`: it keeps executing the warp's loop but commits
     // nothing, so its result is the one of the sweep at which the oracle's loop exits.
     V3 dw = mk(0.f, 0.f, 0.f), dV = mk(0.f, 0.f, 0.f);
-    const float sthr = sqrtf(P.resthr), mu = P.mu;
+    const float sthr = P.sthr, mu = P.mu; // kernel parameters: constant-bank operands, no register reads
     bool frozen = !commit;
     int sweeps = 0;
 #pragma unroll 1
@@ -496,9 +516,16 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
         float viol = 0.f; // max over the rows of |d| - sqrt(thr) invD (in the row's scaled units)
         // a frozen lane applies its (discarded) impulse changes through a zero inverse inertia: dw and dV stay
         // bit-exact without any per-row select or branch
+#if SNK_VAR_SEL
+        // gating by selection: a frozen lane re-selects its old impulse, so its impulse change is exactly zero; the inverse
+        // inertia stays unscaled and the inverse mass is a constant-bank operand
+        const float iM = invM;
+        const S3 Jg = Ji;
+#else
         const float gate = frozen ? 0.f : 1.f, iM = invM * gate;
         S3 Jg;
         Jg.xx = Ji.xx * gate; Jg.xy = Ji.xy * gate; Jg.xz = Ji.xz * gate; Jg.yy = Ji.yy * gate; Jg.yz = Ji.yz * gate; Jg.zz = Ji.zz * gate;
+#endif
         {   // ---- normal rows; the record of row k+1 is fetched while row k is on the chain
             float4 nx; float nn;
             R.ld_n(0, nx, nn);
@@ -512,8 +539,14 @@ SNK_UNROLL(SNK_UNROLL_N)
                 float jd = fmaf(dw.x, x0.z, dV.z);
                 jd = fmaf(-dw.y, x0.y, jd);
                 const float sum = fmaxf(fmaf(-jd, x0.w, p), 0.f);
+#if SNK_VAR_SEL
+                const float sel = frozen ? ln : sum;
+                const float dd = sel - ln;
+                R.st_ln(k, sel);
+#else
                 const float dd = sum - ln;
                 R.st_ln(k, frozen ? ln : sum);
+#endif
                 const float t1 = x0.z * dd, t2 = -x0.y * dd; // rn * dd
                 dw.x = fmaf(Jg.xx, t1, fmaf(Jg.xy, t2, dw.x));
                 dw.y = fmaf(Jg.xy, t1, fmaf(Jg.yy, t2, dw.y));
@@ -533,14 +566,24 @@ SNK_UNROLL(SNK_UNROLL_F)
                 const float4 x0 = n0, x1 = n1, x2 = n2_, x3 = n3;
                 R.ld16((k + 1) & (NC - 1), n0, n1, n2_, n3);
                 const float rx = x0.y, ry = x0.z, rz = x1.x;
-                const float pa = x3.z + x2.z, pb = x3.w + x2.w, lim = mu * x0.x;
+                const float pa = x3.x + x2.z, pb = x3.y + x2.w, lim = mu * x0.x; // x3 = (la, lb, invD_1, invD_2)
                 // u = dV + dw x r
+#if SNK_VAR_U
+                const float ux = fmaf(dw.y, rz, fmaf(-dw.z, ry, dV.x));
+                const float uy = fmaf(dw.z, rx, fmaf(-dw.x, rz, dV.y));
+                const float uz = fmaf(dw.x, ry, fmaf(-dw.y, rx, dV.z));
+#else
                 const float ux = fmaf(-dw.z, ry, fmaf(dw.y, rz, dV.x));
                 const float uy = fmaf(-dw.x, rz, fmaf(dw.z, rx, dV.y));
                 const float uz = fmaf(-dw.y, rx, fmaf(dw.x, ry, dV.z));
+#endif
                 // d1 = (x1.y, x1.z, x1.w), d2 = (x2.x, -x1.y, x2.y)
+#if SNK_VAR_G
+                const float g1 = fmaf(x1.y, ux, fmaf(x1.z, uy, x1.w * uz)), g2 = fmaf(x2.x, ux, fmaf(-x1.y, uy, x2.y * uz));
+#else
                 const float g1 = fmaf(x1.w, uz, fmaf(x1.z, uy, x1.y * ux)), g2 = fmaf(x2.y, uz, fmaf(-x1.y, uy, x2.x * ux));
-                float sa = fmaf(-g1, x3.x, pa), sb = fmaf(-g2, x3.y, pb);
+#endif
+                float sa = fmaf(-g1, x3.z, pa), sb = fmaf(-g2, x3.w, pb);
                 if (CONE) { // implicit cone: radial projection onto the disc of radius mu * lambda_n,
                             // s <- s min(1, lim / |s|)  (0/0 and lim/0 resolve to 1 through fminf)
                     const float sc = fminf(1.f, lim * ex_rsqrt_fast(fmaf(sa, sa, sb * sb)));
@@ -549,16 +592,32 @@ SNK_UNROLL(SNK_UNROLL_F)
                     sa = fminf(fmaxf(sa, -lim), lim);
                     sb = fminf(fmaxf(sb, -lim), lim);
                 }
-                const float da = sa - x3.z, db = sb - x3.w;
-                R.st_lf(k, frozen ? x3.z : sa, frozen ? x3.w : sb);
+#if SNK_VAR_SEL
+                sa = frozen ? x3.x : sa; sb = frozen ? x3.y : sb;
+                const float da = sa - x3.x, db = sb - x3.y;
+                R.st_lf(k, sa, sb);
+#else
+                const float da = sa - x3.x, db = sb - x3.y;
+                R.st_lf(k, frozen ? x3.x : sa, frozen ? x3.y : sb);
+#endif
+#if SNK_VAR_F
+                const float fx = fmaf(x1.y, da, x2.x * db), fy = fmaf(x1.z, da, -x1.y * db), fz = fmaf(x1.w, da, x2.y * db);
+#else
                 const float fx = fmaf(x2.x, db, x1.y * da), fy = fmaf(-x1.y, db, x1.z * da), fz = fmaf(x2.y, db, x1.w * da);
+#endif
                 const float tx = fmaf(ry, fz, -rz * fy), ty = fmaf(rz, fx, -rx * fz), tz = fmaf(rx, fy, -ry * fx); // r x f
                 dV.x = fmaf(fx, iM, dV.x); dV.y = fmaf(fy, iM, dV.y); dV.z = fmaf(fz, iM, dV.z);
+#if SNK_VAR_DW
+                dw.x = fmaf(Jg.xz, tz, fmaf(Jg.xy, ty, fmaf(Jg.xx, tx, dw.x)));
+                dw.y = fmaf(Jg.yz, tz, fmaf(Jg.yy, ty, fmaf(Jg.xy, tx, dw.y)));
+                dw.z = fmaf(Jg.zz, tz, fmaf(Jg.yz, ty, fmaf(Jg.xz, tx, dw.z)));
+#else
                 dw.x = fmaf(Jg.xx, tx, fmaf(Jg.xy, ty, fmaf(Jg.xz, tz, dw.x)));
                 dw.y = fmaf(Jg.xy, tx, fmaf(Jg.yy, ty, fmaf(Jg.yz, tz, dw.y)));
                 dw.z = fmaf(Jg.xz, tx, fmaf(Jg.yz, ty, fmaf(Jg.zz, tz, dw.z)));
+#endif
                 // (da D1 + db D2)^2 <= thr  <=>  |da invD2 + db invD1| <= sqrt(thr) invD1 invD2
-                viol = fmaxf(viol, fmaf(-sthr * x3.x, x3.y, fabsf(fmaf(da, x3.y, db * x3.x))));
+                viol = fmaxf(viol, fmaf(-sthr * x3.z, x3.w, fabsf(fmaf(da, x3.w, db * x3.z))));
             }
             R.fence16(n0, n1, n2_, n3);
             R.fence_st();
@@ -610,7 +669,7 @@ SNK_UNROLL(SNK_UNROLL_F)
                 R.fence16(x0, x1, x2, x3);
                 // contact force n ln + d1 la + d2 lb with d2 = (x2.x, -x1.y, x2.y); explicit fma so that every row-storage
                 // instantiation rounds alike
-                V3 f = mk(fmaf(x2.x, x3.w, x1.y * x3.z), fmaf(-x1.y, x3.w, x1.z * x3.z), fmaf(x2.y, x3.w, fmaf(x1.w, x3.z, x0.x))) * inv_dt;
+                V3 f = mk(fmaf(x2.x, x3.y, x1.y * x3.x), fmaf(-x1.y, x3.y, x1.z * x3.x), fmaf(x2.y, x3.y, fmaf(x1.w, x3.x, x0.x))) * inv_dt;
                 V3 r = mk(x0.y + hc.x, x0.z + hc.y, x1.x + hc.z); // back to the base origin
                 SF = SF - f;
                 SN = SN - cross(r, f);

@@ -77,7 +77,7 @@ static inline void snk_to_kparams(const snk_params* p, KParams* P) {
     P->maximp = isinf(p->motor_max_force) ? INFINITY : (float)(p->motor_max_force * p->dt);
     P->sf = (float)p->scaling_factor; P->alpha = (float)p->alpha; P->beta = (float)p->beta; P->gamma = (float)p->gamma;
     P->edt = (float)p->energy_dt; P->mu = (float)p->friction; P->kl = (float)p->lin_damping; P->ka = (float)p->ang_damping;
-    P->erp2 = (float)p->erp2; P->slop = (float)p->linear_slop; P->resthr = (float)p->residual_threshold;
+    P->erp2 = (float)p->erp2; P->slop = (float)p->linear_slop; P->resthr = (float)p->residual_threshold; P->sthr = sqrtf(P->resthr);
     P->maxvel = (float)p->max_coord_vel; P->errthr = (float)p->err_threshold; P->hthr = (float)p->height_threshold;
     P->tang = (float)p->term_angle; P->donepen = (float)p->done_penalty; P->colf = (float)p->collision_force;
     P->colpen = (float)p->collision_penalty; P->iters = p->solver_iterations; P->maxticks = p->max_ticks;

@@ -33,7 +33,7 @@ struct DevTables {
 
 // Task/solver parameters in fp32, passed by value to the kernels.
 struct KParams {
-    float dt, inv_dt, g[3], kp, kd, maximp, sf, alpha, beta, gamma, edt, mu, aniso[3], kl, ka, erp2, slop, resthr,
+    float dt, inv_dt, g[3], kp, kd, maximp, sf, alpha, beta, gamma, edt, mu, aniso[3], kl, ka, erp2, slop, resthr, sthr /* sqrt(resthr), computed on the host so that the solver reads it from the constant bank */,
         maxvel, errthr, hthr, tang, donepen, colf, colpen;
     int iters, maxticks, gait, cone, tjoint, stale, altmotor, actdim, exact;
 };
