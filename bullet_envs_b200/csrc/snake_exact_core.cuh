@@ -46,24 +46,6 @@
 #ifndef SNK_UNROLL_F
 #define SNK_UNROLL_F 2
 #endif
-// operation-order variants of the friction pair.  They change rounding in the last bit and, through ptxas' register allocation,
-// the number of register-bank conflicts in the solver loops (one lost issue cycle each): screened by counting conflicts in the
-// SASS, then measured (profiles/README.md).  Defaults = the fastest measured combination (G = 1, DW = 1).
-#ifndef SNK_VAR_U
-#define SNK_VAR_U 0
-#endif
-#ifndef SNK_VAR_G
-#define SNK_VAR_G 1
-#endif
-#ifndef SNK_VAR_DW
-#define SNK_VAR_DW 1
-#endif
-#ifndef SNK_VAR_F
-#define SNK_VAR_F 0
-#endif
-#ifndef SNK_VAR_SEL
-#define SNK_VAR_SEL 0
-#endif
 #define SNK_PRAGMA_(x) _Pragma(#x)
 #define SNK_UNROLL(n) SNK_PRAGMA_(unroll n)
 
@@ -516,16 +498,9 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
         float viol = 0.f; // max over the rows of |d| - sqrt(thr) invD (in the row's scaled units)
         // a frozen lane applies its (discarded) impulse changes through a zero inverse inertia: dw and dV stay
         // bit-exact without any per-row select or branch
-#if SNK_VAR_SEL
-        // gating by selection: a frozen lane re-selects its old impulse, so its impulse change is exactly zero; the inverse
-        // inertia stays unscaled and the inverse mass is a constant-bank operand
-        const float iM = invM;
-        const S3 Jg = Ji;
-#else
         const float gate = frozen ? 0.f : 1.f, iM = invM * gate;
         S3 Jg;
         Jg.xx = Ji.xx * gate; Jg.xy = Ji.xy * gate; Jg.xz = Ji.xz * gate; Jg.yy = Ji.yy * gate; Jg.yz = Ji.yz * gate; Jg.zz = Ji.zz * gate;
-#endif
         {   // ---- normal rows; the record of row k+1 is fetched while row k is on the chain
             float4 nx; float nn;
             R.ld_n(0, nx, nn);
@@ -539,14 +514,8 @@ SNK_UNROLL(SNK_UNROLL_N)
                 float jd = fmaf(dw.x, x0.z, dV.z);
                 jd = fmaf(-dw.y, x0.y, jd);
                 const float sum = fmaxf(fmaf(-jd, x0.w, p), 0.f);
-#if SNK_VAR_SEL
-                const float sel = frozen ? ln : sum;
-                const float dd = sel - ln;
-                R.st_ln(k, sel);
-#else
                 const float dd = sum - ln;
                 R.st_ln(k, frozen ? ln : sum);
-#endif
                 const float t1 = x0.z * dd, t2 = -x0.y * dd; // rn * dd
                 dw.x = fmaf(Jg.xx, t1, fmaf(Jg.xy, t2, dw.x));
                 dw.y = fmaf(Jg.xy, t1, fmaf(Jg.yy, t2, dw.y));
@@ -568,21 +537,15 @@ SNK_UNROLL(SNK_UNROLL_F)
                 const float rx = x0.y, ry = x0.z, rz = x1.x;
                 const float pa = x3.x + x2.z, pb = x3.y + x2.w, lim = mu * x0.x; // x3 = (la, lb, invD_1, invD_2)
                 // u = dV + dw x r
-#if SNK_VAR_U
-                const float ux = fmaf(dw.y, rz, fmaf(-dw.z, ry, dV.x));
-                const float uy = fmaf(dw.z, rx, fmaf(-dw.x, rz, dV.y));
-                const float uz = fmaf(dw.x, ry, fmaf(-dw.y, rx, dV.z));
-#else
                 const float ux = fmaf(-dw.z, ry, fmaf(dw.y, rz, dV.x));
                 const float uy = fmaf(-dw.x, rz, fmaf(dw.z, rx, dV.y));
                 const float uz = fmaf(-dw.y, rx, fmaf(dw.x, ry, dV.z));
-#endif
                 // d1 = (x1.y, x1.z, x1.w), d2 = (x2.x, -x1.y, x2.y)
-#if SNK_VAR_G
+                // The order of the operations in g1/g2 and in the dw update below is not arbitrary: different orders make ptxas
+                // allocate registers differently, and every pair of source registers of one instruction that falls into the same
+                // register bank costs an issue cycle.  tools/sass_bank_conflicts.py counts them in the SASS; these orders have the
+                // fewest (12.9 per contact and sweep, against 17.7 for the first version) and measured fastest (profiles/README.md).
                 const float g1 = fmaf(x1.y, ux, fmaf(x1.z, uy, x1.w * uz)), g2 = fmaf(x2.x, ux, fmaf(-x1.y, uy, x2.y * uz));
-#else
-                const float g1 = fmaf(x1.w, uz, fmaf(x1.z, uy, x1.y * ux)), g2 = fmaf(x2.y, uz, fmaf(-x1.y, uy, x2.x * ux));
-#endif
                 float sa = fmaf(-g1, x3.z, pa), sb = fmaf(-g2, x3.w, pb);
                 if (CONE) { // implicit cone: radial projection onto the disc of radius mu * lambda_n,
                             // s <- s min(1, lim / |s|)  (0/0 and lim/0 resolve to 1 through fminf)
@@ -592,30 +555,14 @@ SNK_UNROLL(SNK_UNROLL_F)
                     sa = fminf(fmaxf(sa, -lim), lim);
                     sb = fminf(fmaxf(sb, -lim), lim);
                 }
-#if SNK_VAR_SEL
-                sa = frozen ? x3.x : sa; sb = frozen ? x3.y : sb;
-                const float da = sa - x3.x, db = sb - x3.y;
-                R.st_lf(k, sa, sb);
-#else
                 const float da = sa - x3.x, db = sb - x3.y;
                 R.st_lf(k, frozen ? x3.x : sa, frozen ? x3.y : sb);
-#endif
-#if SNK_VAR_F
-                const float fx = fmaf(x1.y, da, x2.x * db), fy = fmaf(x1.z, da, -x1.y * db), fz = fmaf(x1.w, da, x2.y * db);
-#else
                 const float fx = fmaf(x2.x, db, x1.y * da), fy = fmaf(-x1.y, db, x1.z * da), fz = fmaf(x2.y, db, x1.w * da);
-#endif
                 const float tx = fmaf(ry, fz, -rz * fy), ty = fmaf(rz, fx, -rx * fz), tz = fmaf(rx, fy, -ry * fx); // r x f
                 dV.x = fmaf(fx, iM, dV.x); dV.y = fmaf(fy, iM, dV.y); dV.z = fmaf(fz, iM, dV.z);
-#if SNK_VAR_DW
                 dw.x = fmaf(Jg.xz, tz, fmaf(Jg.xy, ty, fmaf(Jg.xx, tx, dw.x)));
                 dw.y = fmaf(Jg.yz, tz, fmaf(Jg.yy, ty, fmaf(Jg.xy, tx, dw.y)));
                 dw.z = fmaf(Jg.zz, tz, fmaf(Jg.yz, ty, fmaf(Jg.xz, tx, dw.z)));
-#else
-                dw.x = fmaf(Jg.xx, tx, fmaf(Jg.xy, ty, fmaf(Jg.xz, tz, dw.x)));
-                dw.y = fmaf(Jg.xy, tx, fmaf(Jg.yy, ty, fmaf(Jg.yz, tz, dw.y)));
-                dw.z = fmaf(Jg.xz, tx, fmaf(Jg.yz, ty, fmaf(Jg.zz, tz, dw.z)));
-#endif
                 // (da D1 + db D2)^2 <= thr  <=>  |da invD2 + db invD1| <= sqrt(thr) invD1 invD2
                 viol = fmaxf(viol, fmaf(-sthr * x3.z, x3.w, fabsf(fmaf(da, x3.w, db * x3.z))));
             }
