@@ -38,14 +38,14 @@ WORKLOAD = "1M-env throughput sweep (2^20 envs total, random U[-1,1] actions, 1/
 # read 45-float minimal state 180 + action 32; write state 180 + obs 224 + reward 4 + done 1
 BYTES_PER_ENV_STEP = 621
 # DRAM bytes per environment of one launch, from the ncu --set full capture of this command at 2^20 environments
-# (profiles/r01_v8_exact_full_raw_1m.csv: dram__bytes_read.sum 452.33 MB + dram__bytes_write.sum 591.30 MB per launch =
-# 995 B/env; in index order it was 768 B/env: with the longest-first hand-out neighbouring environments are no longer
+# (profiles/r01_v9_exact_full_raw_1m.csv: dram__bytes_read.sum 455.35 MB + dram__bytes_write.sum 592.10 MB per launch =
+# 999 B/env; in index order it was 768 B/env: with the longest-first hand-out neighbouring environments are no longer
 # processed at the same time, so lines they share (32 B action rows, 4 B reward/ticks, 1 B done) move more than once.
 # Either way 0.03 % of the DRAM peak.)
-NCU_DRAM_BYTES_PER_ENV = (452330496 + 591302400) / float(1 << 20)
-# warp-level instructions executed per environment-tick, same capture: smsp__inst_executed.sum = 1.69973e11 for
+NCU_DRAM_BYTES_PER_ENV = (455350272 + 592098816) / float(1 << 20)
+# warp-level instructions executed per environment-tick, same capture: smsp__inst_executed.sum = 1.70003e11 for
 # 2^20 env-steps of 30.03 ticks each (every lane slot counts: masked / converged lanes execute too)
-NCU_WARP_INST_PER_ENV_TICK = 169973129958.0 / ((1 << 20) * 30.0274)
+NCU_WARP_INST_PER_ENV_TICK = 170002985085.0 / ((1 << 20) * 30.0271)
 
 
 def _peaks():
@@ -268,8 +268,8 @@ def run_ours(args):
         sms = torch.cuda.get_device_properties(local).multi_processor_count
         tick_rate_per_gpu = (total / world) * ticks_per_step_env / (kernel_ms * 1e-3)
         issue = {"bound": "issue", "achieved": NCU_WARP_INST_PER_ENV_TICK * tick_rate_per_gpu, "peak": 4.0 * sms * sm_hz, "unit": "warp-inst/s",
-                 "smsp_issue_active_pct_ncu": 63.0, "fma_pipe_active_pct_ncu": 46.3, "lanes_per_instruction_ncu": 32.0,
-                 "source": "instructions per env-tick from profiles/r01_v8_exact_full_raw_1m.csv (ncu, same command) x the tick rate timed here"}
+                 "smsp_issue_active_pct_ncu": 65.6, "fma_pipe_active_pct_ncu": 48.2, "lanes_per_instruction_ncu": 32.0,
+                 "source": "instructions per env-tick from profiles/r01_v9_exact_full_raw_1m.csv (ncu, same command) x the tick rate timed here"}
         issue["frac"] = issue["achieved"] / issue["peak"]
         line = {
             "metric": "snake env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,

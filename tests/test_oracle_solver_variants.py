@@ -78,3 +78,23 @@ def test_contact_points_per_cylinder_sensitivity(model):
     a.reset(); b.reset()
     Ra = sum(a.step(acts[t])[1][0] for t in range(30)); Rb = sum(b.step(acts[t])[1][0] for t in range(30))
     assert abs(Ra - Rb) < 2e-3 * abs(Ra), (Ra, Rb)
+
+
+def test_free_running_trajectories_are_sensitive_to_1e_7(model, golden_test_mode):
+    """Why the free-running GPU-vs-golden comparisons carry centimetre tolerances after a few env-steps: the fp64 oracle itself,
+    started with joint angles perturbed by 1e-7 rad, ends the same serpenoid env-steps millimetres apart after one step and
+    centimetres apart after five (32 unilateral contacts with anisotropic Coulomb friction under an unconverged Gauss-Seidel), while
+    the joint trajectory and the tick counts -- functions of the motor law only -- stay identical."""
+    acts = golden_test_mode["serpenoid/actions"][:8]
+    n = 9
+    o = Oracle(n, default_params(), model); o.reset()
+    s = o.get_state()
+    s[1:, 13:29] += np.random.default_rng(0).normal(0, 1e-7, (n - 1, 16))
+    o.set_state(s)
+    spread = []
+    for a in acts:
+        ob, r, d, tk = o.step(np.repeat(a[None, :], n, 0), threads=8)
+        assert (tk == tk[0]).all() and np.abs(ob[1:, :16] - ob[0, :16]).max() < 1e-6
+        spread.append(np.abs(ob[1:, 48:51] - ob[0, 48:51]).max())
+    assert spread[0] > 1e-4            # eleven orders of magnitude... four of them within the first env-step
+    assert max(spread[3:]) > 5e-3      # centimetre level after a handful of env-steps
