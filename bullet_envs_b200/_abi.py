@@ -109,6 +109,7 @@ def load_library():
     lib.snk_reset_host.argtypes = [vp, vp, vp]
     lib.snk_tick.argtypes = [vp, vp, i32, vp]
     lib.snk_rollout_linear.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
+    lib.snk_gae.argtypes = [ctypes.c_int, vp, vp, vp, vp, ctypes.c_double, ctypes.c_double, vp, vp, i32, i64, vp]
     lib.snk_observe.argtypes = [vp, vp, vp]
     lib.snk_self_clearance.argtypes = [vp, vp, vp]
     lib.snk_get_state.argtypes = [vp, vp, vp]
@@ -117,6 +118,7 @@ def load_library():
     lib.snk_launch_count.argtypes = [vp]; lib.snk_launch_count.restype = i64
     lib.snk_last_error.restype = ctypes.c_char_p
     lib.snk_build_info.restype = ctypes.c_char_p
+    lib.snk_kernel_variant.restype = ctypes.c_char_p
     _lib = lib
     return lib
 

@@ -5,6 +5,7 @@
 // the caller.  No CPU fallback: every entry point either enqueues CUDA work or fails.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -25,6 +26,7 @@ cudaError_t snk_pgs_launch_tick(const DevTables* T, const KParams& P, float* sta
 // thread-per-env kernel with the motor rows eliminated (snake_exact.cu)
 cudaError_t snk_exact_configure(const ExTables* host_tables);
 void snk_exact_release();
+const char* snk_exact_variant();
 cudaError_t snk_exact_launch_step(const KParams& P, float* state, float* tgt_scratch, const float* actions, float* obs, float* rew, uint8_t* done,
                                   int32_t* ticks, unsigned long long* counters, uint8_t* bucket, int32_t* order, int64_t n, cudaStream_t st,
                                   int* launches);
@@ -35,6 +37,9 @@ cudaError_t snk_exact_launch_step_trace(const KParams& P, float* state, float* t
                                         int32_t* ticks, unsigned long long* counters, int64_t n, float* tick_obs, float* tick_links, cudaStream_t st);
 cudaError_t snk_exact_launch_tick(const KParams& P, float* state, const float* targets, unsigned long long* counters, int64_t n,
                                   int n_ticks, cudaStream_t st);
+// generalised advantage estimation (snake_gae.cu)
+cudaError_t snk_launch_gae(const float* rewards, const uint8_t* dones, const float* values, const float* next_value, float gamma, float tau,
+                           float* returns, float* advantages, int T, int64_t n, cudaStream_t st);
 // self-collision clearance counter (snake_pgs.cu)
 cudaError_t snk_launch_self_clearance(const DevTables* T, const float* state, float* out, int64_t n, cudaStream_t st);
 // reset / observe (snake_pgs.cu)
@@ -92,6 +97,10 @@ static void wait_device_work(snk_handle* h) {
     if (h->ev_valid && h->hstream) cudaStreamWaitEvent(h->hstream, h->ev_dev, 0);
 }
 
+// the exact kernel moves action / observation / weight rows as 16-byte vectors (rows are 32, 64 and 224 bytes long, so an aligned
+// base pointer makes every row aligned): a misaligned pointer would fault inside the kernel and poison the context
+static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
 static cudaError_t launch_step(snk_handle* h, const float* act, float* obs, float* rew, uint8_t* done, int32_t* ticks, cudaStream_t st) {
     int launches = 1;
     cudaError_t e = h->exact ? snk_exact_launch_step(h->P, h->state, h->tgt, act, obs, rew, done, ticks, h->counters, h->bucket, h->order, h->n, st, &launches)
@@ -133,6 +142,8 @@ const char* snk_last_error(void) { return g_err; }
 const char* snk_build_info(void) {
     return "snake_b200 sm_100a; fused env-step kernels: thread-per-env (motor rows eliminated) and warp-per-env (Bullet-order PGS); built " __DATE__ " " __TIME__;
 }
+
+const char* snk_kernel_variant(void) { return snk_exact_variant(); }
 
 int snk_default_params(snk_params* p) {
     if (!p) return fail(SNK_E_ARG, "snk_default_params: null pointer%s");
@@ -245,11 +256,13 @@ int snk_observe(snk_handle* h, float* obs_dev, void* stream) {
     CU(cudaSetDevice(h->device));
     CU(snk_launch_reset(h->P, h->state, nullptr, obs_dev, h->n, 2, (cudaStream_t)stream));
     h->launches++;
+    mark_device_work(h, (cudaStream_t)stream); // a later *_host call must not overwrite the state under this read
     return 0;
 }
 
 int snk_step(snk_handle* h, const float* actions_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, int32_t* ticks_dev, void* stream) {
     if (!h || !actions_dev || !obs_dev || !rew_dev || !done_dev) return fail(SNK_E_ARG, "snk_step: null pointer%s");
+    if (!aligned16(actions_dev) || !aligned16(obs_dev)) return fail(SNK_E_ARG, "snk_step: actions and obs must be 16-byte aligned%s");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
@@ -261,6 +274,7 @@ int snk_step_trace(snk_handle* h, const float* actions_dev, float* obs_dev, floa
                    float* tick_obs_dev, float* tick_links_dev, void* stream) {
     if (!h || !actions_dev || !obs_dev || !rew_dev || !done_dev || !ticks_dev)
         return fail(SNK_E_ARG, "snk_step_trace: null pointer (ticks_dev is required: it says how many trace rows are valid)%s");
+    if (!aligned16(actions_dev) || !aligned16(obs_dev)) return fail(SNK_E_ARG, "snk_step_trace: actions and obs must be 16-byte aligned%s");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
@@ -277,6 +291,7 @@ int snk_rollout_linear(snk_handle* h, const float* weights_dev, const float* mea
                        int32_t n_steps, float* returns_dev, float* obs_trace_dev, void* stream) {
     if (!h || !weights_dev || !returns_dev || n_steps < 1) return fail(SNK_E_ARG, "snk_rollout_linear: bad argument%s");
     if (!h->exact) return fail(SNK_E_ARG, "snk_rollout_linear: only with the exact motor solver (motor force = inf, kd = 1)%s");
+    if (!aligned16(weights_dev)) return fail(SNK_E_ARG, "snk_rollout_linear: weights must be 16-byte aligned%s");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t qlen = (size_t)h->n * (size_t)(n_steps > 1 ? n_steps - 1 : 1);
@@ -293,6 +308,16 @@ int snk_rollout_linear(snk_handle* h, const float* weights_dev, const float* mea
                                 h->order, h->counters, h->n, st));
     h->launches++;
     mark_device_work(h, st);
+    return 0;
+}
+
+int snk_gae(int device, const float* rewards_dev, const uint8_t* dones_dev, const float* values_dev, const float* next_value_dev, double gamma,
+            double tau, float* returns_dev, float* advantages_dev, int32_t n_steps, int64_t n_envs, void* stream) {
+    if (!rewards_dev || !dones_dev || !values_dev || !next_value_dev || !returns_dev) return fail(SNK_E_ARG, "snk_gae: null pointer%s");
+    if (n_steps < 1 || n_envs < 1) return fail(SNK_E_ARG, "snk_gae: n_steps and n_envs must be positive%s");
+    CU(cudaSetDevice(device));
+    CU(snk_launch_gae(rewards_dev, dones_dev, values_dev, next_value_dev, (float)gamma, (float)tau, returns_dev, advantages_dev, n_steps, n_envs,
+                      (cudaStream_t)stream));
     return 0;
 }
 
@@ -356,7 +381,8 @@ int snk_step_host(snk_handle* h, const float* actions_host, float* obs_host, flo
     void *da = nullptr, *dob = nullptr, *dr = nullptr, *dd = nullptr, *dt = nullptr;
     const bool pa = is_pinned(actions_host, &da), po = is_pinned(obs_host, &dob), pr = is_pinned(rew_host, &dr), pd = is_pinned(done_host, &dd),
                pt = ticks_host && is_pinned(ticks_host, &dt);
-    if (zero_copy_enabled() && pa && po && pr && pd && (!ticks_host || pt) && da && dob && dr && dd && (!ticks_host || dt)) {
+    if (zero_copy_enabled() && pa && po && pr && pd && (!ticks_host || pt) && da && dob && dr && dd && (!ticks_host || dt) && aligned16(da) &&
+        aligned16(dob)) { // (a misaligned pinned buffer takes the staged path below)
         // Every caller buffer is page-locked and mapped: the kernel reads the 32 B action row of an environment straight from
         // host memory when a lane takes it and posts the observation row / reward / done / ticks straight back over PCIe when
         // the environment finishes, spread over the whole launch -- no copy before or after the kernel.
@@ -450,6 +476,7 @@ int snk_self_clearance(snk_handle* h, float* clearance_dev, void* stream) {
     CU(cudaSetDevice(h->device));
     CU(snk_launch_self_clearance(h->T, h->state, clearance_dev, h->n, (cudaStream_t)stream));
     h->launches++;
+    mark_device_work(h, (cudaStream_t)stream);
     return 0;
 }
 
@@ -457,6 +484,7 @@ int snk_get_state(snk_handle* h, float* state_dev, void* stream) {
     if (!h || !state_dev) return fail(SNK_E_ARG, "snk_get_state: null pointer%s");
     CU(cudaSetDevice(h->device));
     CU(cudaMemcpyAsync(state_dev, h->state, (size_t)h->n * SNK_STATE_STRIDE * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    mark_device_work(h, (cudaStream_t)stream);
     return 0;
 }
 

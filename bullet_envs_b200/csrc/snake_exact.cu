@@ -5,13 +5,17 @@
 // snake_exact_core.cuh for the algorithm and oracle/snake_oracle.c:tick_exact for its CPU twin).
 //
 // One launch = one SubprocVecEnv.step(): clip + createAction, the data-dependent 0..41-tick loop,
-// observation, reward, termination, auto-reset.  The grid is persistent, one CTA of 4 + SW warps per SM (SW = 2 or 3,
-// picked per launch), each lane owning one environment at a time (192 / 224 environments in flight per SM).  The
+// observation, reward, termination, auto-reset.  The grid is persistent, one CTA of EIGHT warps per SM, each lane
+// owning one environment at a time (256 environments in flight per SM, two warps on every scheduler).  The
 // per-environment working set is the contact-row table (32 contacts x 17 words, re-read by every solver sweep), and what
-// bounds the kernel is how many of those tables fit on chip.  Blackwell has two on-chip memories:
-//   warps 0-3  keep their rows in TENSOR MEMORY (tcgen05.ld/st 32x32b: TMEM lane = thread, the 512 columns
-//              of the warp's quadrant = 32 contacts x 16 words), plus 4 KB of shared memory each;
-//   warps 4-6  keep theirs in shared memory ([word][contact][lane] columns, conflict free), 68 KB each.
+// bounds the kernel is how many of those tables fit on chip.  snk_hyb_step_kernel spreads every table over the three
+// on-chip memories of a Blackwell SM (RowsH in snake_exact_core.cuh):
+//   8 words per contact in TENSOR MEMORY (tcgen05.ld/st 32x32b: TMEM lane = thread; warps w and w + 4 share lane quadrant
+//                       w and take 256 of its 512 columns each),
+//   7 words per contact in shared memory ([contact][lane] columns, conflict free, 28 KB per warp = 224 KB per CTA),
+//   2 words per contact in registers (64 of the thread's 255; the normal sweep that reads them is fully unrolled).
+// snk_exact_step_kernel<CONE, SW> is the previous layout (4 warps with 16 words in tensor memory + SW warps with the whole
+// record in shared memory, 7 warps per SM), kept for the ablation (SNK_EXACT_ROWS=split).
 // The lock-step unit of a warp is ONE PHYSICS TICK, not one env-step: a lane whose environment has
 // finished its tick loop writes its outputs and takes the next environment from a global counter while
 // the other lanes keep ticking, so the 0..41 spread of tick counts costs no idle lanes.
@@ -26,6 +30,8 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 #include <string.h>
+
+#include <mutex>
 
 #include "snake_exact_core.cuh"
 
@@ -390,6 +396,74 @@ snk_exact_step_kernel(const KParams P, float* __restrict__ state, float* __restr
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
 }
 
+// ---------------------------------------------------------------------------------------------
+// The benchmarked kernel: 8 warps per CTA, one CTA per SM, every warp's rows spread over tensor memory, shared memory
+// and registers (RowsH).  Warps w and w + 4 run on scheduler w and share TMEM lane quadrant w.
+// ---------------------------------------------------------------------------------------------
+#define HWARPS 8
+struct StepSmemH {
+    RowsHybStore w[HWARPS];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t hyb_tmem_alloc(StepSmemH& S, int warp) {
+    if (warp == 0) { // the whole tensor memory of the SM: 512 columns x 128 lanes
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S.tmem_base);
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    return S.tmem_base;
+}
+__device__ __forceinline__ void hyb_tmem_free(uint32_t tbase, int warp) {
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
+}
+__device__ __forceinline__ RowsH hyb_rows(StepSmemH& S, uint32_t tbase, int warp, int lane) {
+    RowsH R;
+    R.taddr = tbase + ((uint32_t)(32 * (warp & 3)) << 16) + 256u * (uint32_t)(warp >> 2);
+    R.s = &S.w[warp];
+    R.lane = lane;
+    R.tg = nullptr;
+    return R;
+}
+
+template <bool CONE>
+__global__ void __launch_bounds__(HWARPS * 32, 1)
+snk_hyb_step_kernel(const KParams P, float* __restrict__ state, float* __restrict__ tgt_scratch, const float* __restrict__ actions, float* __restrict__ obs,
+                    float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks, unsigned long long* __restrict__ counters,
+                    const int32_t* __restrict__ order, int64_t n, int active_warps, int spread) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StepSmemH& S = *reinterpret_cast<StepSmemH*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tbase = hyb_tmem_alloc(S, warp);
+    // first wave (SNK_EXACT_SPREAD): warp-major over the grid (default) -- a batch smaller than the grid's lanes puts one warp on every
+    // scheduler of every SM before any scheduler gets a second one (warps w and w + 4 share scheduler w); 0 = CTA-major; 2 = no static
+    // wave, everything from the global counter (ablations)
+    const int64_t first_base = (spread == 2) ? -1 : (spread ? ((int64_t)warp * gridDim.x + blockIdx.x) * 32 : ((int64_t)blockIdx.x * active_warps + warp) * 32);
+    const int64_t dyn_base = (spread == 2) ? 0 : min((int64_t)gridDim.x * active_warps * 32, n);
+    if (warp < active_warps) // SNK_EXACT_WARPS (ablation): the other warps take no environments
+        run_warp<CONE>(P, hyb_rows(S, tbase, warp, lane), state, tgt_scratch, actions, obs, rew, done, ticks, counters, order, n, first_base, dyn_base);
+    hyb_tmem_free(tbase, warp);
+}
+
+template <bool CONE>
+__global__ void __launch_bounds__(HWARPS * 32, 1)
+snk_hyb_rollout_kernel(const KParams P, float* __restrict__ state, float* __restrict__ tgt_scratch, const RolloutArgs A,
+                       unsigned long long* __restrict__ counters, int64_t n) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StepSmemH& S = *reinterpret_cast<StepSmemH*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tbase = hyb_tmem_alloc(S, warp);
+    const int64_t first_base = ((int64_t)warp * gridDim.x + blockIdx.x) * 32;
+    const int64_t dyn_base = min((int64_t)gridDim.x * HWARPS * 32, n);
+    run_rollout_warp<CONE>(P, hyb_rows(S, tbase, warp, lane), state, tgt_scratch, A, counters, n, first_base, dyn_base);
+    hyb_tmem_free(tbase, warp);
+}
+
 // the same loop with every warp's rows in shared memory: one warp per CTA, 3 CTAs per SM
 // (SNK_EXACT_ROWS=smem; kept for the ablation in DESIGN.md section 6)
 template <bool CONE>
@@ -519,25 +593,29 @@ __global__ void snk_exact_order_kernel(int64_t n, const uint8_t* __restrict__ bu
 // ---------------------------------------------------------------------------------------------
 // launch wrappers used by the C-ABI host code (snake_abi.cu)
 // ---------------------------------------------------------------------------------------------
-static int g_sms = 0, g_smem_ctas = 0;
-static bool g_rows_tmem = true; // SNK_EXACT_ROWS=smem selects the shared-memory-only variant
-static bool g_no_sort = false; // SNK_EXACT_ORDER=index disables the longest-first hand-out (ablation)
-static int g_spread = 3; // SNK_EXACT_SPREAD: first-wave hand-out policy (see snk_exact_step_kernel)
-static int g_active_warps = 0; // SNK_EXACT_WARPS=1..7 forces the number of working warps per SM (0: chosen per launch)
+enum { ROWS_HYBRID = 0, ROWS_SPLIT = 1, ROWS_SMEM = 2 };
+#define MAX_DEVICES 64
+// Process-wide configuration, written under g_mu by snk_exact_configure (i.e. by snk_create) and read by the launchers.
+// The per-device figures are indexed by the CUDA device ordinal; the ablation switches come from the environment once per create.
+static std::mutex g_mu;
+static int g_sms[MAX_DEVICES], g_smem_ctas[MAX_DEVICES];
+static int g_rows = ROWS_HYBRID; // SNK_EXACT_ROWS = split | smem selects one of the older row layouts (ablation)
+static bool g_no_sort = false;   // SNK_EXACT_ORDER=index disables the longest-first hand-out (ablation)
+static int g_spread = 3;         // SNK_EXACT_SPREAD: first-wave hand-out policy (see the step kernels)
+static int g_active_warps = 0;   // SNK_EXACT_WARPS=1..8 forces the number of working warps per SM (0: chosen per launch)
 
-// working warps per SM for a batch of n environments: 7 (three shared-memory warps) once the batch is about two waves of
-// the 7-warp grid, else 6 -- a single wave finishes sooner with fewer warps per scheduler.  Measured on B200 (env-steps/s,
-// 6 / 7 warps): 32 768 envs 3.10 M / 2.9 M, 65 536 3.90 M / 4.13 M, 131 072 4.05 M / 4.19 M, 262 144 4.13 M / 4.26 M,
-// 2^20 4.24 M / 4.50 M.
-static int warps_for(int64_t n) {
-    if (g_active_warps) return g_active_warps;
-    return (10 * n >= 18LL * g_sms * (TWARPS + SW_MAX) * 32) ? TWARPS + 3 : TWARPS + 2;
+// working warps per SM for a batch of n environments.  Hybrid rows: always 8.  Split rows: 7 (three shared-memory warps) once the
+// batch is about two waves of the 7-warp grid, else 6 -- a single wave finishes sooner with fewer warps per scheduler.
+static int warps_for(int64_t n, int dev) {
+    if (g_rows == ROWS_HYBRID) return (g_active_warps >= 1 && g_active_warps <= HWARPS) ? g_active_warps : HWARPS;
+    if (g_active_warps >= 1 && g_active_warps <= TWARPS + SW_MAX) return g_active_warps;
+    return (10 * n >= 18LL * g_sms[dev] * (TWARPS + SW_MAX) * 32) ? TWARPS + 3 : TWARPS + 2;
 }
 
-size_t snk_exact_smem_bytes() { return g_rows_tmem ? sizeof(StepSmemT<SW_MAX>) : sizeof(RowsSmemStore); }
-
 const char* snk_exact_variant() {
-    return g_rows_tmem ? "rows in TMEM (4 warps) + shared memory (2 or 3 warps per launch), 192 / 224 envs/SM" : "rows in shared memory, 3 x 32 envs/SM";
+    return g_rows == ROWS_HYBRID ? "8 warps/SM, rows in TMEM (8 words) + shared memory (7) + registers (2), 256 envs/SM"
+         : g_rows == ROWS_SPLIT  ? "rows in TMEM (4 warps) + shared memory (2 or 3 warps per launch), 192 / 224 envs/SM"
+                                 : "rows in shared memory, 3 x 32 envs/SM";
 }
 
 // The model tables live in one __constant__ symbol per device: all live handles of a process must share one
@@ -546,50 +624,68 @@ const char* snk_exact_variant() {
 static ExTables g_tables;
 static int g_live_handles = 0;
 
-void snk_exact_release() { if (g_live_handles > 0) g_live_handles--; }
+void snk_exact_release() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_live_handles > 0) g_live_handles--;
+}
+
+template <class K>
+static cudaError_t set_smem(K kernel, size_t bytes) { return cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }
 
 cudaError_t snk_exact_configure(const ExTables* host_tables) {
+    std::lock_guard<std::mutex> lk(g_mu);
     if (g_live_handles > 0 && memcmp(&g_tables, host_tables, sizeof(ExTables)) != 0) return cudaErrorInvalidValue;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= MAX_DEVICES) return cudaErrorInvalidDevice;
     memcpy(&g_tables, host_tables, sizeof(ExTables));
-    g_live_handles++;
     const char* v = getenv("SNK_EXACT_ROWS");
-    g_rows_tmem = !(v && v[0] == 's');
+    g_rows = (v && v[0] == 's' && v[1] == 'p') ? ROWS_SPLIT : (v && v[0] == 's') ? ROWS_SMEM : ROWS_HYBRID;
     const char* so = getenv("SNK_EXACT_ORDER");
     g_no_sort = so && so[0] == 'i';
     const char* sp = getenv("SNK_EXACT_SPREAD");
     g_spread = (sp && sp[0] >= '0' && sp[0] <= '3') ? sp[0] - '0' : 3;
     const char* w = getenv("SNK_EXACT_WARPS");
-    g_active_warps = (w && atoi(w) >= 1 && atoi(w) <= TWARPS + SW_MAX) ? atoi(w) : 0;
-    cudaError_t e = cudaMemcpyToSymbol(cT, host_tables, sizeof(ExTables));
-    const void* k1[6] = {(const void*)snk_exact_step_kernel_smem<true>, (const void*)snk_exact_step_kernel_smem<false>,
-                         (const void*)snk_exact_tick_kernel<true>, (const void*)snk_exact_tick_kernel<false>,
-                         (const void*)snk_exact_step_trace_kernel<true>, (const void*)snk_exact_step_trace_kernel<false>};
-    for (int i = 0; i < 6 && e == cudaSuccess; i++)
-        e = cudaFuncSetAttribute(k1[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowsSmemStore));
-    const void* k2[4] = {(const void*)snk_exact_step_kernel<true, 2>, (const void*)snk_exact_step_kernel<false, 2>,
-                         (const void*)snk_exact_rollout_kernel<true, 2>, (const void*)snk_exact_rollout_kernel<false, 2>};
-    for (int i = 0; i < 4 && e == cudaSuccess; i++)
-        e = cudaFuncSetAttribute(k2[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmemT<2>));
-    const void* k3[4] = {(const void*)snk_exact_step_kernel<true, 3>, (const void*)snk_exact_step_kernel<false, 3>,
-                         (const void*)snk_exact_rollout_kernel<true, 3>, (const void*)snk_exact_rollout_kernel<false, 3>};
-    for (int i = 0; i < 4 && e == cudaSuccess; i++)
-        e = cudaFuncSetAttribute(k3[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmemT<3>));
+    g_active_warps = (w && atoi(w) >= 1 && atoi(w) <= HWARPS) ? atoi(w) : 0;
+    e = cudaMemcpyToSymbol(cT, host_tables, sizeof(ExTables));
+    if (e == cudaSuccess) e = set_smem(snk_exact_step_kernel_smem<true>, sizeof(RowsSmemStore));
+    if (e == cudaSuccess) e = set_smem(snk_exact_step_kernel_smem<false>, sizeof(RowsSmemStore));
+    if (e == cudaSuccess) e = set_smem(snk_exact_tick_kernel<true>, sizeof(RowsSmemStore));
+    if (e == cudaSuccess) e = set_smem(snk_exact_tick_kernel<false>, sizeof(RowsSmemStore));
+    if (e == cudaSuccess) e = set_smem(snk_exact_step_trace_kernel<true>, sizeof(RowsSmemStore));
+    if (e == cudaSuccess) e = set_smem(snk_exact_step_trace_kernel<false>, sizeof(RowsSmemStore));
+    if (e == cudaSuccess) e = set_smem(snk_exact_step_kernel<true, 2>, sizeof(StepSmemT<2>));
+    if (e == cudaSuccess) e = set_smem(snk_exact_step_kernel<false, 2>, sizeof(StepSmemT<2>));
+    if (e == cudaSuccess) e = set_smem(snk_exact_step_kernel<true, 3>, sizeof(StepSmemT<3>));
+    if (e == cudaSuccess) e = set_smem(snk_exact_step_kernel<false, 3>, sizeof(StepSmemT<3>));
+    if (e == cudaSuccess) e = set_smem(snk_exact_rollout_kernel<true, 2>, sizeof(StepSmemT<2>));
+    if (e == cudaSuccess) e = set_smem(snk_exact_rollout_kernel<false, 2>, sizeof(StepSmemT<2>));
+    if (e == cudaSuccess) e = set_smem(snk_exact_rollout_kernel<true, 3>, sizeof(StepSmemT<3>));
+    if (e == cudaSuccess) e = set_smem(snk_exact_rollout_kernel<false, 3>, sizeof(StepSmemT<3>));
+    if (e == cudaSuccess) e = set_smem(snk_hyb_step_kernel<true>, sizeof(StepSmemH));
+    if (e == cudaSuccess) e = set_smem(snk_hyb_step_kernel<false>, sizeof(StepSmemH));
+    if (e == cudaSuccess) e = set_smem(snk_hyb_rollout_kernel<true>, sizeof(StepSmemH));
+    if (e == cudaSuccess) e = set_smem(snk_hyb_rollout_kernel<false>, sizeof(StepSmemH));
     if (e != cudaSuccess) return e;
-    int dev = 0, per_sm = 0;
-    e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    int per_sm = 0;
+    e = cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, snk_exact_step_kernel_smem<true>, EB, sizeof(RowsSmemStore));
-    if (e == cudaSuccess) g_smem_ctas = g_sms * (per_sm > 0 ? per_sm : 1);
+    if (e == cudaSuccess) g_smem_ctas[dev] = g_sms[dev] * (per_sm > 0 ? per_sm : 1);
+    if (e == cudaSuccess) g_live_handles++;
     return e;
 }
+
+static int cur_dev() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < MAX_DEVICES) ? d : 0; }
 
 // sched = {bucket[n] u8, order[n] i32} owned by the handle (null: hand out in index order); hist/cursor are the
 // 2 x 64 words after the 8 counters (zeroed with them)
 cudaError_t snk_exact_launch_step(const KParams& P, float* state, float* tgt_scratch, const float* actions, float* obs, float* rew, uint8_t* done,
                                   int32_t* ticks, unsigned long long* counters, uint8_t* bucket, int32_t* order, int64_t n, cudaStream_t st,
                                   int* launches) {
-    const int aw = warps_for(n);
-    const int lanes = g_rows_tmem ? g_sms * aw * 32 : g_smem_ctas * EB;
+    const int dev = cur_dev(), sms = g_sms[dev];
+    const int aw = warps_for(n, dev);
+    const int lanes = g_rows == ROWS_SMEM ? g_smem_ctas[dev] * EB : sms * aw * 32;
     const int32_t* use_order = nullptr;
     *launches = 1;
     if (bucket && order && n > lanes && !g_no_sort) {
@@ -601,19 +697,24 @@ cudaError_t snk_exact_launch_step(const KParams& P, float* state, float* tgt_scr
         use_order = order;
         *launches = 3;
     }
-    if (g_rows_tmem) {
+    if (g_rows == ROWS_HYBRID) {
         // a small batch gets one CTA per warp of environments: all SMs before a second warp per SM
+        const int64_t want = g_spread ? (n + EB - 1) / EB : (n + aw * 32 - 1) / (aw * 32);
+        dim3 grid((unsigned)(want < sms ? want : sms)), block(HWARPS * 32);
+        if (P.cone) snk_hyb_step_kernel<true><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n, aw, g_spread);
+        else snk_hyb_step_kernel<false><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n, aw, g_spread);
+    } else if (g_rows == ROWS_SPLIT) {
         const int sw = aw > TWARPS + 2 ? 3 : 2;
         const int per_cta = (TWARPS + sw) * 32, per_cta_active = aw * 32;
         const int64_t want = (g_spread == 1 || g_spread == 3) ? (n + EB - 1) / EB : (n + per_cta_active - 1) / per_cta_active;
-        dim3 grid((unsigned)(want < g_sms ? want : g_sms)), block(per_cta);
+        dim3 grid((unsigned)(want < sms ? want : sms)), block(per_cta);
 #define SNK_LAUNCH_STEP(C, S) snk_exact_step_kernel<C, S><<<grid, block, sizeof(StepSmemT<S>), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n, aw, g_spread)
         if (sw == 3) { if (P.cone) SNK_LAUNCH_STEP(true, 3); else SNK_LAUNCH_STEP(false, 3); }
         else { if (P.cone) SNK_LAUNCH_STEP(true, 2); else SNK_LAUNCH_STEP(false, 2); }
 #undef SNK_LAUNCH_STEP
     } else {
         const int64_t warps = (n + EB - 1) / EB;
-        dim3 grid((unsigned)(warps < g_smem_ctas ? warps : g_smem_ctas)), block(EB);
+        dim3 grid((unsigned)(warps < g_smem_ctas[dev] ? warps : g_smem_ctas[dev])), block(EB);
         if (P.cone) snk_exact_step_kernel_smem<true><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n);
         else snk_exact_step_kernel_smem<false><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n);
     }
@@ -622,31 +723,43 @@ cudaError_t snk_exact_launch_step(const KParams& P, float* state, float* tgt_scr
 
 cudaError_t snk_exact_launch_step_trace(const KParams& P, float* state, float* tgt_scratch, const float* actions, float* obs, float* rew, uint8_t* done,
                                         int32_t* ticks, unsigned long long* counters, int64_t n, float* tick_obs, float* tick_links, cudaStream_t st) {
+    const int dev = cur_dev();
     const int64_t warps = (n + EB - 1) / EB;
-    dim3 grid((unsigned)(warps < g_smem_ctas ? warps : g_smem_ctas)), block(EB);
+    dim3 grid((unsigned)(warps < g_smem_ctas[dev] ? warps : g_smem_ctas[dev])), block(EB);
     if (P.cone) snk_exact_step_trace_kernel<true><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, n, tick_obs, tick_links);
     else snk_exact_step_trace_kernel<false><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, n, tick_obs, tick_links);
     return cudaGetLastError();
 }
 
+// The rollout kernel's lanes wait for environments that other CTAs push onto the ready queue, so its whole grid must be
+// resident at once: it is launched COOPERATIVELY (one CTA per SM at most), which makes the driver either co-schedule every
+// CTA or refuse the launch (cudaErrorCooperativeLaunchTooLarge under an SM-limited context) -- it can never hang on a CTA
+// that did not get an SM.  Two rollouts on one device (two handles / streams) are serialised by the driver.
 cudaError_t snk_exact_launch_rollout(const KParams& P, float* state, float* tgt_scratch, const float* weights, const float* mean, const float* inv_std,
                                      const float* noise, int n_steps, float* returns, float* trace, int32_t* queue, int32_t* done_steps,
                                      unsigned long long* counters, int64_t n, cudaStream_t st) {
     RolloutArgs A;
     A.weights = weights; A.mean = mean; A.inv_std = inv_std; A.noise = noise; A.returns = returns; A.trace = trace; A.n_steps = n_steps;
     A.queue = queue; A.done_steps = done_steps;
-    const int sw = warps_for(n) > TWARPS + 2 ? 3 : 2;
-    const int per_cta = (TWARPS + sw) * 32;
+    const int dev = cur_dev(), sms = g_sms[dev];
     const int64_t want = (n + EB - 1) / EB;
-    dim3 grid((unsigned)(want < g_sms ? want : g_sms)), block(per_cta);
-    if (sw == 3) {
-        if (P.cone) snk_exact_rollout_kernel<true, 3><<<grid, block, sizeof(StepSmemT<3>), st>>>(P, state, tgt_scratch, A, counters, n);
-        else snk_exact_rollout_kernel<false, 3><<<grid, block, sizeof(StepSmemT<3>), st>>>(P, state, tgt_scratch, A, counters, n);
-    } else {
-        if (P.cone) snk_exact_rollout_kernel<true, 2><<<grid, block, sizeof(StepSmemT<2>), st>>>(P, state, tgt_scratch, A, counters, n);
-        else snk_exact_rollout_kernel<false, 2><<<grid, block, sizeof(StepSmemT<2>), st>>>(P, state, tgt_scratch, A, counters, n);
+    KParams Pc = P;
+    void* args[] = {(void*)&Pc, (void*)&state, (void*)&tgt_scratch, (void*)&A, (void*)&counters, (void*)&n};
+    if (g_rows == ROWS_HYBRID) {
+        int per_sm = 0;
+        const void* k = P.cone ? (const void*)snk_hyb_rollout_kernel<true> : (const void*)snk_hyb_rollout_kernel<false>;
+        cudaError_t e = P.cone ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, snk_hyb_rollout_kernel<true>, HWARPS * 32, sizeof(StepSmemH))
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, snk_hyb_rollout_kernel<false>, HWARPS * 32, sizeof(StepSmemH));
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorCooperativeLaunchTooLarge;
+        dim3 grid((unsigned)(want < sms ? want : sms)), block(HWARPS * 32);
+        return cudaLaunchCooperativeKernel(k, grid, block, args, sizeof(StepSmemH), st);
     }
-    return cudaGetLastError();
+    const int sw = warps_for(n, dev) > TWARPS + 2 ? 3 : 2;
+    dim3 grid((unsigned)(want < sms ? want : sms)), block((TWARPS + sw) * 32);
+    const void* k = sw == 3 ? (P.cone ? (const void*)snk_exact_rollout_kernel<true, 3> : (const void*)snk_exact_rollout_kernel<false, 3>)
+                            : (P.cone ? (const void*)snk_exact_rollout_kernel<true, 2> : (const void*)snk_exact_rollout_kernel<false, 2>);
+    return cudaLaunchCooperativeKernel(k, grid, block, args, sw == 3 ? sizeof(StepSmemT<3>) : sizeof(StepSmemT<2>), st);
 }
 
 cudaError_t snk_exact_launch_tick(const KParams& P, float* state, const float* targets, unsigned long long* counters, int64_t n,

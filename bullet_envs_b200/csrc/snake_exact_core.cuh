@@ -99,6 +99,7 @@ typedef RowsSmemStore ExSmem;
 // Both policies also carry `tg`, the 16 joint targets of the lane's current environment: a 64 B row of the handle's target
 // scratch array in global memory (written when the lane takes the environment, L1/L2 resident while it owns it).
 struct RowsS {
+    static constexpr bool REGN = false; // invD_n / rhs_n invD_n come from the record, not from registers
     RowsSmemStore* s;
     int lane;
     float* tg;
@@ -117,6 +118,13 @@ struct RowsS {
     SNK_HD void fence4(float4&) const {}
     SNK_HD void fence16(float4&, float4&, float4&, float4&) const {}
     SNK_HD void fence_st() const {}
+    // storage-neutral names used by ex_tick (the hybrid policy RowsH stores the same words elsewhere)
+    SNK_HD void st_tmp(int k, float4 t0, float4 t1, float4 t2) const { st12(k, t0, t1, t2); }
+    SNK_HD void ld_tmp(int k, float4& t0, float4& t1, float4& t2) const { t0 = s->X[0][k][lane]; t1 = s->X[1][k][lane]; t2 = s->X[2][k][lane]; }
+    SNK_HD void fence_tmp(float4&, float4&, float4&) const {}
+    SNK_HD void st_rec(int k, float4 x0, float4 x1, float4 x2, float4 x3, float n1) const { st16(k, x0, x1, x2, x3); st_n1(k, n1); }
+    SNK_HD void ld_regn(int, float&, float&) const {}
+    SNK_HD void clr_lf(int) const {}
 };
 
 #ifdef __CUDACC__
@@ -125,6 +133,7 @@ struct RowsS {
 // Loads are asynchronous: the destination registers may only be read after fence4/fence16, which wait for
 // the load AND tie the registers so that the compiler cannot move a use above the wait.
 struct RowsT {
+    static constexpr bool REGN = false;
     uint32_t taddr;  // TMEM address of this warp's quadrant: base + (32 * (warp % 4) << 16)
     RowsTmemAux* s;
     int lane;
@@ -163,6 +172,97 @@ struct RowsT {
         asm volatile("tcgen05.wait::ld.sync.aligned;"
                      : "+f"(x0.x), "+f"(x0.y), "+f"(x0.z), "+f"(x0.w), "+f"(x1.x), "+f"(x1.y), "+f"(x1.z), "+f"(x1.w), "+f"(x2.x), "+f"(x2.y), "+f"(x2.z),
                        "+f"(x2.w), "+f"(x3.x), "+f"(x3.y), "+f"(x3.z), "+f"(x3.w)::"memory");
+    }
+    __device__ __forceinline__ void fence_st() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+    __device__ __forceinline__ void st_tmp(int k, float4 t0, float4 t1, float4 t2) const { st12(k, t0, t1, t2); }
+    __device__ __forceinline__ void ld_tmp(int k, float4& t0, float4& t1, float4& t2) const { float4 t3; ld16(k, t0, t1, t2, t3); }
+    __device__ __forceinline__ void fence_tmp(float4& t0, float4& t1, float4& t2) const {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+f"(t0.x), "+f"(t0.y), "+f"(t0.z), "+f"(t0.w), "+f"(t1.x), "+f"(t1.y), "+f"(t1.z), "+f"(t1.w), "+f"(t2.x), "+f"(t2.y), "+f"(t2.z), "+f"(t2.w)::"memory");
+    }
+    __device__ __forceinline__ void st_rec(int k, float4 x0, float4 x1, float4 x2, float4 x3, float n1) const { st16(k, x0, x1, x2, x3); st_n1(k, n1); }
+    __device__ __forceinline__ void ld_regn(int, float&, float&) const {}
+    __device__ __forceinline__ void clr_lf(int) const {}
+};
+
+// HYBRID rows (the benchmarked kernel): every warp keeps 8 words of a record in tensor memory, 7 in shared memory and 2 in
+// registers, so that EIGHT warps fit on an SM (two per scheduler; two per TMEM lane quadrant, 256 columns each):
+//   tensor memory, column 8 k + w:  0 ln | 1 r.x | 2 r.y | 3 r.z | 4 la | 5 lb | 6 d1.x | 7 d1.y
+//                                   (the normal sweep reads words 0-3 with one ld.x4, the friction sweep all 8 with one ld.x8;
+//                                    the solver state ln / la, lb is written back with st.x1 / st.x2)
+//   shared memory, per contact [A | B | C][lane]: A = (d1.z, d2.x, d2.z, rhs_1 invD_1)   B = (rhs_2 invD_2, invD_1)   C = invD_2   (28 KB per warp)
+//   registers:                      invD_n and rhs_n invD_n of all 32 contacts (64 registers; only the normal sweep reads them, so only
+//                                   that loop is fully unrolled).  The rows phase, whose contact index is dynamic, parks the two values
+//                                   in the la / lb words (which start at zero); ld_regn / clr_lf move them into the registers and zero
+//                                   the words in an unrolled prologue of the solver.
+struct RowsHybStore { // 896 B per contact: the three loads of a record differ by constant offsets from one running address
+    struct { float4 A[EB]; float2 B[EB]; float C[EB]; } c[NC];
+};
+struct RowsH {
+    static constexpr bool REGN = true;
+    uint32_t taddr;  // TMEM address of this warp's 256 columns: base + (32 * (warp % 4) << 16) + 256 * (warp / 4)
+    RowsHybStore* s;
+    int lane;
+    float* tg;
+    __device__ __forceinline__ float& tgt(int j) const { return tg[j]; }
+    __device__ __forceinline__ void st8(uint32_t col, float a, float b, float c, float d, float e, float f, float g, float h) const {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr + col), "f"(a), "f"(b), "f"(c), "f"(d),
+                     "f"(e), "f"(f), "f"(g), "f"(h) : "memory");
+    }
+    __device__ __forceinline__ void ld8(uint32_t col, float& a, float& b, float& c, float& d, float& e, float& f, float& g, float& h) const {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=f"(a), "=f"(b), "=f"(c), "=f"(d), "=f"(e), "=f"(f), "=f"(g), "=f"(h) : "r"(taddr + col) : "memory");
+    }
+    // pass-1 temporaries: t0, t1 in tensor memory, t2 in shared memory
+    __device__ __forceinline__ void st_tmp(int k, float4 t0, float4 t1, float4 t2) const {
+        st8(8u * k, t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w);
+        s->c[k].A[lane] = t2;
+    }
+    __device__ __forceinline__ void ld_tmp(int k, float4& t0, float4& t1, float4& t2) const {
+        ld8(8u * k, t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w);
+        t2 = s->c[k].A[lane];
+    }
+    __device__ __forceinline__ void fence_tmp(float4& t0, float4& t1, float4&) const {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(t0.x), "+f"(t0.y), "+f"(t0.z), "+f"(t0.w), "+f"(t1.x), "+f"(t1.y), "+f"(t1.z), "+f"(t1.w)::"memory");
+    }
+    // final record (logical layout of the other policies: x0 = ln rx ry invD_n | x1 = rz d1 | x2 = d2x d2z b1 b2 | x3 = la lb invD_1 invD_2)
+    __device__ __forceinline__ void st_rec(int k, float4 x0, float4 x1, float4 x2, float4 x3, float n1) const {
+        st8(8u * k, x0.x, x0.y, x0.z, x1.x, x0.w /* invD_n, parked */, n1 /* parked */, x1.y, x1.z);
+        s->c[k].A[lane] = make_float4(x1.w, x2.x, x2.y, x2.z);
+        s->c[k].B[lane] = make_float2(x2.w, x3.z);
+        s->c[k].C[lane] = x3.w;
+    }
+    __device__ __forceinline__ void ld_regn(int k, float& idn, float& n1) const {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=f"(idn), "=f"(n1) : "r"(taddr + 8u * k + 4u) : "memory");
+    }
+    __device__ __forceinline__ void clr_lf(int k) const { st_lf(k, 0.f, 0.f); }
+    __device__ __forceinline__ void ld_n(int k, float4& x0, float&) const { // (ln, rx, ry, rz)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(x0.x), "=f"(x0.y), "=f"(x0.z), "=f"(x0.w) : "r"(taddr + 8u * k) : "memory");
+    }
+    __device__ __forceinline__ void ld16(int k, float4& x0, float4& x1, float4& x2, float4& x3) const {
+        ld8(8u * k, x0.x, x0.y, x0.z, x1.x, x3.x, x3.y, x1.y, x1.z);
+        const float4 a = s->c[k].A[lane];
+        const float2 b = s->c[k].B[lane];
+        x3.w = s->c[k].C[lane];
+        x1.w = a.x; x2.x = a.y; x2.y = a.z; x2.z = a.w; x2.w = b.x; x3.z = b.y;
+        x0.w = 0.f; // invD_n is not part of the friction record
+    }
+    __device__ __forceinline__ void st_ln(int k, float v) const {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr + 8u * k), "f"(v) : "memory");
+    }
+    __device__ __forceinline__ void st_lf(int k, float a, float b) const {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr + 8u * k + 4u), "f"(a), "f"(b) : "memory");
+    }
+    __device__ __forceinline__ void fence4(float4& x0) const {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(x0.x), "+f"(x0.y), "+f"(x0.z), "+f"(x0.w)::"memory");
+    }
+    __device__ __forceinline__ void fence16(float4& x0, float4& x1, float4&, float4& x3) const { // the 8 words that come from tensor memory
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(x0.x), "+f"(x0.y), "+f"(x0.z), "+f"(x1.x), "+f"(x3.x), "+f"(x3.y), "+f"(x1.y), "+f"(x1.z)::"memory");
+    }
+    __device__ __forceinline__ void fence_regn8(float* a, float* b) const { // 8 contacts' worth of ld_regn destinations
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]), "+f"(b[0]), "+f"(b[1]), "+f"(b[2]),
+                       "+f"(b[3]), "+f"(b[4]), "+f"(b[5]), "+f"(b[6]), "+f"(b[7])::"memory");
     }
     __device__ __forceinline__ void fence_st() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 };
@@ -410,7 +510,7 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
             V3 d1 = mul(Rl, l1), d2 = mul(Rl, l2);
             V3 uJ = vJ + cross(wJ, pc - c.p);
             // pass-1 temporaries in the record: (uJ.x | pc), (d1 | d2.x), (d2.y d2.z | uJ.y uJ.z)
-            R.st12(k, make_float4(uJ.x, pc.x, pc.y, pc.z), make_float4(d1.x, d1.y, d1.z, d2.x), make_float4(d2.y, d2.z, uJ.y, uJ.z));
+            R.st_tmp(k, make_float4(uJ.x, pc.x, pc.y, pc.z), make_float4(d1.x, d1.y, d1.z, d2.x), make_float4(d2.y, d2.z, uJ.y, uJ.z));
         }
     }
     R.fence_st();
@@ -446,9 +546,9 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
     // ------------------------------------------------------------------ rows
 #pragma unroll 1
     for (int k = 0; k < NC; k++) {
-        float4 t0, t1, t2, t3;
-        R.ld16(k, t0, t1, t2, t3);
-        R.fence16(t0, t1, t2, t3);
+        float4 t0, t1, t2;
+        R.ld_tmp(k, t0, t1, t2);
+        R.fence_tmp(t0, t1, t2);
         const bool on = (act >> k) & 1u;
         const V3 uJ = mk(t0.x, t2.z, t2.w);
         const float dist = t0.w + p0z;
@@ -475,11 +575,21 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
         const float D1 = dot(d1, d1) * invM + dot(r1, J1), D2 = dot(d2, d2) * invM + dot(r2, J2);
         const float iD1 = 1.f / D1, iD2 = 1.f / D2;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        R.st16(k, on ? make_float4(0.f, r.x, r.y, iDn) : z4, on ? make_float4(r.z, d1.x, d1.y, d1.z) : z4,
-               on ? make_float4(d2.x, d2.z, -dot(d1, vp) * iD1, -dot(d2, vp) * iD2) : z4, on ? make_float4(0.f, 0.f, iD1, iD2) : z4);
-        R.st_n1(k, on ? rhsn : 0.f);
+        R.st_rec(k, on ? make_float4(0.f, r.x, r.y, iDn) : z4, on ? make_float4(r.z, d1.x, d1.y, d1.z) : z4,
+                 on ? make_float4(d2.x, d2.z, -dot(d1, vp) * iD1, -dot(d2, vp) * iD2) : z4, on ? make_float4(0.f, 0.f, iD1, iD2) : z4, on ? rhsn : 0.f);
     }
     R.fence_st();
+    // hybrid rows: invD_n and rhs_n invD_n of every contact move from their parking words into registers (static indices: unrolled)
+    float idn[Rows::REGN ? NC : 1], n1r[Rows::REGN ? NC : 1];
+    if constexpr (Rows::REGN) {
+#pragma unroll
+        for (int k = 0; k < NC; k++) R.ld_regn(k, idn[k], n1r[k]);
+#pragma unroll
+        for (int k = 0; k < NC; k += 8) R.fence_regn8(idn + k, n1r + k);
+#pragma unroll
+        for (int k = 0; k < NC; k++) R.clr_lf(k);
+        R.fence_st();
+    }
 
     // ------------------------------------------------------------------ projected Gauss-Seidel
     // The only serial dependence is the 6-vector (dw, dV); everything else of a row (loads, impulse
@@ -502,71 +612,102 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
         S3 Jg;
         Jg.xx = Ji.xx * gate; Jg.xy = Ji.xy * gate; Jg.xz = Ji.xz * gate; Jg.yy = Ji.yy * gate; Jg.yz = Ji.yz * gate; Jg.zz = Ji.zz * gate;
         {   // ---- normal rows; the record of row k+1 is fetched while row k is on the chain
-            float4 nx; float nn;
-            R.ld_n(0, nx, nn);
-SNK_UNROLL(SNK_UNROLL_N)
-            for (int k = 0; k < NC; k++) {
-                R.fence4(nx);
-                const float4 x0 = nx; const float n1 = nn;  // (ln, rx, ry, invD_n), rhs_n invD_n
-                R.ld_n((k + 1) & (NC - 1), nx, nn);
-                const float ln = x0.x;
-                const float p = ln + n1;
-                float jd = fmaf(dw.x, x0.z, dV.z);
-                jd = fmaf(-dw.y, x0.y, jd);
-                const float sum = fmaxf(fmaf(-jd, x0.w, p), 0.f);
-                const float dd = sum - ln;
-                R.st_ln(k, frozen ? ln : sum);
-                const float t1 = x0.z * dd, t2 = -x0.y * dd; // rn * dd
-                dw.x = fmaf(Jg.xx, t1, fmaf(Jg.xy, t2, dw.x));
-                dw.y = fmaf(Jg.xy, t1, fmaf(Jg.yy, t2, dw.y));
-                dw.z = fmaf(Jg.xz, t1, fmaf(Jg.yz, t2, dw.z));
-                dV.z = fmaf(dd, iM, dV.z);
-                viol = fmaxf(viol, fmaf(-sthr, x0.w, fabsf(dd)));
+            // one row: LN = normal impulse, RX / RY = lever arm, IDN = invD_n, N1 = rhs_n invD_n
+#define SNK_NORMAL_ROW(K, LN, RX, RY, IDN, N1)                                            \
+            {                                                                             \
+                const float ln = (LN);                                                    \
+                const float p = ln + (N1);                                                \
+                float jd = fmaf(dw.x, (RY), dV.z);                                        \
+                jd = fmaf(-dw.y, (RX), jd);                                               \
+                const float sum = fmaxf(fmaf(-jd, (IDN), p), 0.f);                        \
+                const float dd = sum - ln;                                                \
+                R.st_ln((K), frozen ? ln : sum);                                          \
+                const float t1 = (RY) * dd, t2 = -(RX) * dd; /* rn * dd */                \
+                dw.x = fmaf(Jg.xx, t1, fmaf(Jg.xy, t2, dw.x));                            \
+                dw.y = fmaf(Jg.xy, t1, fmaf(Jg.yy, t2, dw.y));                            \
+                dw.z = fmaf(Jg.xz, t1, fmaf(Jg.yz, t2, dw.z));                            \
+                dV.z = fmaf(dd, iM, dV.z);                                                \
+                viol = fmaxf(viol, fmaf(-sthr, (IDN), fabsf(dd)));                        \
             }
-            R.fence4(nx);
+            float4 nx; float nn = 0.f;
+            R.ld_n(0, nx, nn);
+            if constexpr (Rows::REGN) { // invD_n / rhs_n invD_n in registers: static contact index, fully unrolled
+#pragma unroll
+                for (int k = 0; k < NC; k++) {
+                    R.fence4(nx);
+                    const float4 x0 = nx;  // (ln, rx, ry, -)
+                    if (k + 1 < NC) R.ld_n(k + 1, nx, nn);
+                    SNK_NORMAL_ROW(k, x0.x, x0.y, x0.z, idn[k], n1r[k])
+                }
+            } else {
+SNK_UNROLL(SNK_UNROLL_N)
+                for (int k = 0; k < NC; k++) {
+                    R.fence4(nx);
+                    const float4 x0 = nx; const float n1 = nn;  // (ln, rx, ry, invD_n), rhs_n invD_n
+                    R.ld_n((k + 1) & (NC - 1), nx, nn);
+                    SNK_NORMAL_ROW(k, x0.x, x0.y, x0.z, x0.w, n1)
+                }
+                R.fence4(nx);
+            }
+#undef SNK_NORMAL_ROW
             R.fence_st();
         }
-        {   // ---- friction pairs
+        {   // ---- friction pairs; row k+1 is fetched while row k is on the chain (the last two rows are peeled so that the
+            // prefetch index never wraps: the addresses of a row's loads and stores are constant offsets from one running address)
+            // x3 = (la, lb, invD_1, invD_2); d1 = (x1.y, x1.z, x1.w), d2 = (x2.x, -x1.y, x2.y)
+            // The order of the operations in g1/g2 and in the dw update below is not arbitrary: different orders make ptxas
+            // allocate registers differently, and every pair of source registers of one instruction that falls into the same
+            // register bank costs an issue cycle.  tools/sass_bank_conflicts.py counts them in the SASS (profiles/README.md).
+#define SNK_FRICTION_ROW(K)                                                                                                   \
+            {                                                                                                                 \
+                const float rx = x0.y, ry = x0.z, rz = x1.x;                                                                  \
+                const float pa = x3.x + x2.z, pb = x3.y + x2.w, lim = mu * x0.x;                                              \
+                /* u = dV + dw x r */                                                                                         \
+                const float ux = fmaf(-dw.z, ry, fmaf(dw.y, rz, dV.x));                                                       \
+                const float uy = fmaf(-dw.x, rz, fmaf(dw.z, rx, dV.y));                                                       \
+                const float uz = fmaf(-dw.y, rx, fmaf(dw.x, ry, dV.z));                                                       \
+                const float g1 = fmaf(x1.y, ux, fmaf(x1.z, uy, x1.w * uz)), g2 = fmaf(x2.x, ux, fmaf(-x1.y, uy, x2.y * uz));  \
+                float sa = fmaf(-g1, x3.z, pa), sb = fmaf(-g2, x3.w, pb);                                                     \
+                if (CONE) { /* implicit cone: radial projection onto the disc of radius mu * lambda_n,                        \
+                               s <- s min(1, lim / |s|)  (0/0 and lim/0 resolve to 1 through fminf) */                        \
+                    const float sc = fminf(1.f, lim * ex_rsqrt_fast(fmaf(sa, sa, sb * sb)));                                  \
+                    sa *= sc; sb *= sc;                                                                                       \
+                } else {                                                                                                      \
+                    sa = fminf(fmaxf(sa, -lim), lim);                                                                         \
+                    sb = fminf(fmaxf(sb, -lim), lim);                                                                         \
+                }                                                                                                             \
+                const float da = sa - x3.x, db = sb - x3.y;                                                                   \
+                R.st_lf((K), frozen ? x3.x : sa, frozen ? x3.y : sb);                                                         \
+                const float fx = fmaf(x2.x, db, x1.y * da), fy = fmaf(-x1.y, db, x1.z * da), fz = fmaf(x2.y, db, x1.w * da);  \
+                const float tx = fmaf(ry, fz, -rz * fy), ty = fmaf(rz, fx, -rx * fz), tz = fmaf(rx, fy, -ry * fx); /* r x f */ \
+                dV.x = fmaf(fx, iM, dV.x); dV.y = fmaf(fy, iM, dV.y); dV.z = fmaf(fz, iM, dV.z);                              \
+                dw.x = fmaf(Jg.xz, tz, fmaf(Jg.xy, ty, fmaf(Jg.xx, tx, dw.x)));                                               \
+                dw.y = fmaf(Jg.yz, tz, fmaf(Jg.yy, ty, fmaf(Jg.xy, tx, dw.y)));                                               \
+                dw.z = fmaf(Jg.zz, tz, fmaf(Jg.yz, ty, fmaf(Jg.xz, tx, dw.z)));                                               \
+                /* (da D1 + db D2)^2 <= thr  <=>  |da invD2 + db invD1| <= sqrt(thr) invD1 invD2 */                           \
+                viol = fmaxf(viol, fmaf(-sthr * x3.z, x3.w, fabsf(fmaf(da, x3.w, db * x3.z))));                               \
+            }
             float4 n0, n1, n2_, n3;
             R.ld16(0, n0, n1, n2_, n3);
 SNK_UNROLL(SNK_UNROLL_F)
-            for (int k = 0; k < NC; k++) {
+            for (int k = 0; k < NC - 2; k++) {
                 R.fence16(n0, n1, n2_, n3);
                 const float4 x0 = n0, x1 = n1, x2 = n2_, x3 = n3;
-                R.ld16((k + 1) & (NC - 1), n0, n1, n2_, n3);
-                const float rx = x0.y, ry = x0.z, rz = x1.x;
-                const float pa = x3.x + x2.z, pb = x3.y + x2.w, lim = mu * x0.x; // x3 = (la, lb, invD_1, invD_2)
-                // u = dV + dw x r
-                const float ux = fmaf(-dw.z, ry, fmaf(dw.y, rz, dV.x));
-                const float uy = fmaf(-dw.x, rz, fmaf(dw.z, rx, dV.y));
-                const float uz = fmaf(-dw.y, rx, fmaf(dw.x, ry, dV.z));
-                // d1 = (x1.y, x1.z, x1.w), d2 = (x2.x, -x1.y, x2.y)
-                // The order of the operations in g1/g2 and in the dw update below is not arbitrary: different orders make ptxas
-                // allocate registers differently, and every pair of source registers of one instruction that falls into the same
-                // register bank costs an issue cycle.  tools/sass_bank_conflicts.py counts them in the SASS; these orders have the
-                // fewest (12.9 per contact and sweep, against 17.7 for the first version) and measured fastest (profiles/README.md).
-                const float g1 = fmaf(x1.y, ux, fmaf(x1.z, uy, x1.w * uz)), g2 = fmaf(x2.x, ux, fmaf(-x1.y, uy, x2.y * uz));
-                float sa = fmaf(-g1, x3.z, pa), sb = fmaf(-g2, x3.w, pb);
-                if (CONE) { // implicit cone: radial projection onto the disc of radius mu * lambda_n,
-                            // s <- s min(1, lim / |s|)  (0/0 and lim/0 resolve to 1 through fminf)
-                    const float sc = fminf(1.f, lim * ex_rsqrt_fast(fmaf(sa, sa, sb * sb)));
-                    sa *= sc; sb *= sc;
-                } else {
-                    sa = fminf(fmaxf(sa, -lim), lim);
-                    sb = fminf(fmaxf(sb, -lim), lim);
-                }
-                const float da = sa - x3.x, db = sb - x3.y;
-                R.st_lf(k, frozen ? x3.x : sa, frozen ? x3.y : sb);
-                const float fx = fmaf(x2.x, db, x1.y * da), fy = fmaf(-x1.y, db, x1.z * da), fz = fmaf(x2.y, db, x1.w * da);
-                const float tx = fmaf(ry, fz, -rz * fy), ty = fmaf(rz, fx, -rx * fz), tz = fmaf(rx, fy, -ry * fx); // r x f
-                dV.x = fmaf(fx, iM, dV.x); dV.y = fmaf(fy, iM, dV.y); dV.z = fmaf(fz, iM, dV.z);
-                dw.x = fmaf(Jg.xz, tz, fmaf(Jg.xy, ty, fmaf(Jg.xx, tx, dw.x)));
-                dw.y = fmaf(Jg.yz, tz, fmaf(Jg.yy, ty, fmaf(Jg.xy, tx, dw.y)));
-                dw.z = fmaf(Jg.zz, tz, fmaf(Jg.yz, ty, fmaf(Jg.xz, tx, dw.z)));
-                // (da D1 + db D2)^2 <= thr  <=>  |da invD2 + db invD1| <= sqrt(thr) invD1 invD2
-                viol = fmaxf(viol, fmaf(-sthr * x3.z, x3.w, fabsf(fmaf(da, x3.w, db * x3.z))));
+                R.ld16(k + 1, n0, n1, n2_, n3);
+                SNK_FRICTION_ROW(k)
             }
-            R.fence16(n0, n1, n2_, n3);
+            {
+                R.fence16(n0, n1, n2_, n3);
+                const float4 x0 = n0, x1 = n1, x2 = n2_, x3 = n3;
+                R.ld16(NC - 1, n0, n1, n2_, n3);
+                SNK_FRICTION_ROW(NC - 2)
+            }
+            {
+                R.fence16(n0, n1, n2_, n3);
+                const float4 x0 = n0, x1 = n1, x2 = n2_, x3 = n3;
+                SNK_FRICTION_ROW(NC - 1)
+            }
+#undef SNK_FRICTION_ROW
             R.fence_st();
         }
         if (!frozen) { sweeps++; frozen = (viol <= 0.f); }

@@ -87,3 +87,32 @@ def mean_scalar(x):
     y = x.clone()
     dist.all_reduce(y, op=dist.ReduceOp.SUM)
     return y / dist.get_world_size()
+
+
+def global_uniform(seed: int, step: int, lo: int, hi: int, width: int, device=None, total: int | None = None):
+    """U[-1, 1) numbers for the environments [lo, hi) of a sharded batch, keyed by the GLOBAL environment index: element
+    (env, k) of step `step` is a hash of (seed, step, env, k) only, so a rank's slice does not depend on how many ranks
+    there are (W = 1 and W = 8 see bit-identical actions / directions).  splitmix64 finaliser on a 64-bit
+    counter, evaluated with wrapping int64 tensor arithmetic on `device`; returns float32 [hi - lo, width]."""
+    import torch
+    env = torch.arange(lo, hi, dtype=torch.int64, device=device).unsqueeze(1)
+    k = torch.arange(width, dtype=torch.int64, device=device).unsqueeze(0)
+    wrap = lambda v: ((int(v) + (1 << 63)) % (1 << 64)) - (1 << 63)  # Python int -> two's-complement int64
+    x = (env * width + k) + wrap((int(step) + 1) * 0x632BE59BD9B4E019 + int(seed) * 0x2545F4914F6CDD1D)
+    # splitmix64 (Steele, Lea, Flood 2014); arithmetic shifts are masked to emulate logical shifts on signed int64
+    x = x + (-7046029254386353131)                                   # 0x9E3779B97F4A7C15
+    x = (x ^ ((x >> 30) & 0x3FFFFFFFF)) * (-4658895280553007687)     # 0xBF58476D1CE4E5B9
+    x = (x ^ ((x >> 27) & 0x1FFFFFFFFF)) * (-7723592293110705685)    # 0x94D049BB133111EB
+    x = x ^ ((x >> 31) & 0x1FFFFFFFF)
+    u = ((x >> 40) & 0xFFFFFF).to(torch.float32) * (1.0 / 8388608.0) - 1.0   # 24 bits -> [-1, 1)
+    return u
+
+
+def global_normal(seed: int, step: int, lo: int, hi: int, width: int, device=None):
+    """N(0, 1) numbers keyed by the global environment index (Box-Muller on two :func:`global_uniform` streams): the ARS
+    directions delta_i of environment i (``ars/train.py:208-219``) do not depend on the number of ranks."""
+    import math
+    import torch
+    u1 = 1.0 - (global_uniform(seed, 2 * step, lo, hi, width, device) + 1.0) * 0.5        # (0, 1]
+    u2 = (global_uniform(seed, 2 * step + 1, lo, hi, width, device) + 1.0) * 0.5          # [0, 1)
+    return torch.sqrt(-2.0 * torch.log(u1)) * torch.cos((2.0 * math.pi) * u2)

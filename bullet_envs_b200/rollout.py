@@ -35,6 +35,27 @@ class RolloutBuffer:
         """start the next rollout from the last observation (``state = next_state``, ``ppo/train.py:139``)"""
         self.obs[0].copy_(self.obs[self.T])
 
+    def gae(self, next_value, gamma=0.99, tau=0.95):
+        """``compute_gae`` (``ppo/agent.py:14-22``) over the whole buffer as ONE kernel launch (C-ABI ``snk_gae``) on the current
+        torch stream: returns ``(returns, advantages)``, both [T, N] (``advantage = returns - values``, ``ppo/train.py:178``).
+        ``next_value`` [N] = V of ``obs[T]`` (``ppo/train.py:170-171``).  CUDA buffers only -- there is no CPU fallback."""
+        import ctypes
+        import torch
+        from . import _abi
+        if not self.rewards.is_cuda:
+            raise RuntimeError("RolloutBuffer.gae runs the CUDA kernel snk_gae: the buffer must live on a CUDA device")
+        lib = _abi.load_library()
+        nv = next_value.detach().reshape(self.N).to(dtype=torch.float32).contiguous()
+        values = self.values.detach()
+        returns = torch.empty_like(self.rewards)
+        adv = torch.empty_like(self.rewards)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        dev = self.rewards.device
+        _abi.check(lib.snk_gae(dev.index if dev.index is not None else torch.cuda.current_device(), p(self.rewards), p(self.dones), p(values), p(nv),
+                               float(gamma), float(tau), p(returns), p(adv), self.T, self.N,
+                               ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), lib)
+        return returns, adv
+
     def flat(self):
         """[T*N, ...] views in the layout ``ppo_update`` consumes (``torch.cat(states)`` etc., ``ppo/train.py:174-180``)."""
         T, N = self.T, self.N
@@ -43,7 +64,8 @@ class RolloutBuffer:
 
 
 def compute_gae(next_value, rewards, masks, values, gamma=0.99, tau=0.95):
-    """Generalised advantage estimation, the recursion of ``ppo/agent.py:14-22`` on [T, N] tensors:
+    """Plain-tensor statement of the recursion (host logic; T small eager steps) -- the product path for a device-resident rollout is
+    :meth:`RolloutBuffer.gae`, one kernel.  Generalised advantage estimation, the recursion of ``ppo/agent.py:14-22`` on [T, N] tensors:
     delta_t = r_t + gamma V_{t+1} m_t - V_t ;  gae_t = delta_t + gamma tau m_t gae_{t+1} ;  return_t = gae_t + V_t.
     ``next_value`` [N] is V of the state after the last step.  Returns the [T, N] returns tensor."""
     import torch

@@ -17,6 +17,8 @@
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all work is
  *     enqueued on it, no hidden synchronisation except in the *_host entry points.
  *   - layouts are row-major fp32: actions [N, act_dim], obs [N, 56], reward [N], done [N] u8.
+ *   - actions, obs and weights pointers must be 16-byte aligned (rows move as 16-byte vectors); anything a device or
+ *     pinned allocator returns is.  A misaligned pointer is refused with SNK_E_ARG (snk_step_host stages it instead).
  *
  * Reference interfaces replaced (file:line under /root/reference):
  *   snk_create      <- SnakeGymEnv.__init__ (SnakeGymEnv.py:5-26), Snake.__init__/reset(hardReset=True)
@@ -99,7 +101,10 @@ typedef struct snk_model {
     int32_t height_body[SNK_NB];
 } snk_model;
 
-/* Task + solver parameters; defaults reproduce the reference. */
+/* Task + solver parameters.  The defaults are the reference's task settings and PyBullet's documented world defaults (DESIGN.md
+ * section 3).  The tick underneath is this project's restatement of Bullet, not Bullet itself -- one contact point per cylinder and
+ * no persistent manifold (D1), no joint-limit / self-collision rows (D3), and with motor_solver = 2 the motor rows imposed exactly
+ * instead of relaxed by 50 sweeps (D4); DESIGN.md section 4 measures each.  No PyBullet was available to pin it against. */
 typedef struct snk_params {
     double dt;                  /* 1/240: Snake.setTimeSteps is never called (snake.py:271-272) */
     double gravity[3];          /* (0,0,-9.8) snake.py:8,91                                     */
@@ -188,6 +193,14 @@ int snk_step_trace(snk_handle* h, const float* actions_dev, float* obs_dev, floa
 int snk_rollout_linear(snk_handle* h, const float* weights_dev, const float* mean_dev, const float* inv_std_dev,
                        const float* noise_dev, int32_t n_steps, float* returns_dev, float* obs_trace_dev, void* stream);
 
+/* Generalised advantage estimation over a device-resident rollout (PPO half): compute_gae of ppo/agent.py:14-22
+ * as one kernel.  rewards_dev / values_dev / returns_dev / advantages_dev are [T, N] fp32 row-major (time major, as RolloutBuffer
+ * stores what ppo/train.py:131-136 appends), dones_dev [T, N] u8 (mask = 1 - done, ppo/train.py:134), next_value_dev [N] = V of the
+ * state after the last step (ppo/train.py:170-171).  returns_dev receives gae + V (what compute_gae returns), advantages_dev (may be
+ * NULL) the gae itself (= returns - values, ppo/train.py:178).  Stateless: no handle; runs on `device`. */
+int snk_gae(int device, const float* rewards_dev, const uint8_t* dones_dev, const float* values_dev, const float* next_value_dev,
+            double gamma, double tau, float* returns_dev, float* advantages_dev, int32_t n_steps, int64_t n_envs, void* stream);
+
 /* Raw physics ticks with explicit joint targets [N,16] (gait script, snake_gait_test.py:96-104);
  * no task logic.  n_ticks ticks are run with the same targets. */
 int snk_tick(snk_handle* h, const float* targets_dev, int32_t n_ticks, void* stream);
@@ -216,6 +229,8 @@ int64_t snk_launch_count(const snk_handle* h);
 
 const char* snk_last_error(void);
 const char* snk_build_info(void);
+/* Row layout / warp configuration of the env-step kernel the library currently launches (set at snk_create from SNK_EXACT_ROWS). */
+const char* snk_kernel_variant(void);
 
 #ifdef __cplusplus
 }

@@ -140,9 +140,22 @@ def scenario_actions():
     t = np.arange(30)[:, None] * 0.3                                 # serpenoid on the odd joints (snake_gait_test.py:65-89)
     nn = (2 * np.arange(8) + 1)[None, :]
     sc["serpenoid"] = -np.sin(4 * nn + 2 * t)
-    big = np.zeros((25, 8)); big[:, 4] = np.where(np.arange(25) % 2 == 0, 1.0, -1.0)  # drives joint 9 past 0.5 -> done
+    # joint 9 (action index 4) is held at its limit target pi/6 = 0.5236 > 0.5 while the other yaw joints swing: the tick loop
+    # stops at |error|_2 <= 0.05, so joint 9 ends inside 0.5 when it carries the whole error (even steps: 0.476) and beyond it
+    # when the others carry most of it (odd steps) -> `abs(observation[9]) > 0.5` fires (SnakeGymEnv.py:100), -5, double reset
+    big = np.zeros((25, 8)); big[:, 4] = 1.0
+    big[1::2, 0:4] = np.where(np.arange(12)[:, None] % 2 == 0, 1.0, -1.0)
     sc["terminate_q9"] = big
+    # checkSnakeHeight (snake.py:237-245,299-301; SnakeGymEnv.py:99-103): the fake client's state is lifted before some steps
+    # (see INJECT): 0 = dropped from z = 0.2 -> height break after the first tick; 3 = thrown upwards at 3 m/s from the ground
+    # -> break in the middle of the tick loop; 5 = lifted with the action already reached -> zero ticks, done by checkTermination
+    lift = np.zeros((8, 8)); lift[0] = 0.5; lift[1] = -0.5; lift[2] = 0.5; lift[3] = -0.7; lift[4] = 0.3; lift[5] = 0.3; lift[6] = 0.8; lift[7] = -0.2
+    sc["lifted"] = lift
     return sc
+
+
+# state edits applied to the (fake) simulator before a step: step -> (delta z of the base, delta vz of the base)
+INJECT = {"lifted": {0: (0.2, 0.0), 3: (0.0, 3.0), 5: (0.2, 0.0)}}
 
 
 def main():
@@ -164,8 +177,12 @@ def main():
         env = ref_env.SnakeGymEnv(robot)
         obs0 = env.reset()                       # worker 'reset' command
         rec_obs, rec_rew, rec_done, rec_ticks, rec_act = [np.array(obs0)], [], [], [], []
-        for a in actions:
+        inj = np.zeros((len(actions), 2))
+        for t, a in enumerate(actions):
             a_in = np.array(a, dtype=np.float64)
+            if t in INJECT.get(name.split("/")[-1], {}):
+                inj[t] = INJECT[name.split("/")[-1]][t]
+                s = client.oracle.get_state(); s[0, 2] += inj[t, 0]; s[0, 9] += inj[t, 1]; client.oracle.set_state(s)
             t0 = client.ticks
             ob, r, d, info = env.step(a_in)      # may clip a_in in place
             if d:
@@ -178,6 +195,7 @@ def main():
         out[name + "/rew"] = np.asarray(rec_rew)
         out[name + "/done"] = np.asarray(rec_done)
         out[name + "/ticks"] = np.asarray(rec_ticks, np.int32)
+        out[name + "/inject"] = inj
         print("%-14s steps %3d  ticks/step %5.1f  dones %d  return %.4f  client calls %d" % (
             name, len(actions), np.mean(rec_ticks), int(np.sum(rec_done)), float(np.sum(rec_rew)), client.calls))
     out["meta/motor_list"] = np.asarray(robot.motorList)

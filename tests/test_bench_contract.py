@@ -18,6 +18,12 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert "workload" in line["config"]
+    # same config object and same tick as this repo's arm (the driver compares the two lines)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.workload_config(1 << 20, 1)
+    assert "same tick as the GPU arm" in line["cpu_baseline"]["sample"] and line["cpu_baseline"]["value_bullet_order_rows"] > 0
+    assert line["cpu_baseline"]["value"] > line["cpu_baseline"]["value_bullet_order_rows"]   # the relaxed-row tick is the slower one
 
 
 def test_non_zero_ranks_of_the_reference_arm_do_nothing():

@@ -65,3 +65,18 @@ def test_gather_and_welford_world2(total):
         assert p.exitcode == 0
     for rank, okg, okw, ms in res:
         assert okg and okw and ms == pytest.approx(0.5)
+
+
+def test_global_streams_do_not_depend_on_the_sharding():
+    """actions / directions keyed by the global environment index: a rank's slice is the slice of the full stream."""
+    import torch
+    from bullet_envs_b200.dist import global_normal, global_uniform, shard_range
+    total = 1003
+    full_u, full_n = global_uniform(3, 7, 0, total, 8), global_normal(3, 7, 0, total, 5)
+    for world in (2, 8):
+        parts_u = [global_uniform(3, 7, *shard_range(total, r, world), 8) for r in range(world)]
+        parts_n = [global_normal(3, 7, *shard_range(total, r, world), 5) for r in range(world)]
+        assert torch.equal(torch.cat(parts_u), full_u) and torch.equal(torch.cat(parts_n), full_n)
+    assert full_u.min() >= -1 and full_u.max() < 1 and abs(float(full_u.mean())) < 0.05 and abs(float(full_u.std()) - 3 ** -0.5) < 0.02
+    assert not torch.equal(global_uniform(3, 8, 0, total, 8), full_u) and not torch.equal(global_uniform(4, 7, 0, total, 8), full_u)
+    assert abs(float(full_n.mean())) < 0.1 and abs(float(full_n.std()) - 1) < 0.1

@@ -138,13 +138,16 @@ def test_free_running_statistics(torch):
 def test_golden_scenarios_on_the_gpu(torch, golden):
     """The reference-Python golden vectors (tests/golden, made by tests/golden/make_golden.py): tick counts, done
     flags and joint angles of every step; the contact-sensitive base pose over the first steps."""
-    for name in ("const_half", "random", "clipped", "serpenoid", "terminate_q9"):
+    for name in ("const_half", "random", "clipped", "serpenoid", "terminate_q9", "lifted"):
         acts = golden[name + "/actions"]
+        inj = golden[name + "/inject"]
         env = make_env(1)
         obs0 = env.reset()
         assert np.array_equal(obs0[0], golden[name + "/obs"][0])
         agree = 0
         for t, a in enumerate(acts):
+            if inj[t].any():                                    # the generator lifted / threw the snake before this step
+                s = env.get_state(); s[0, 2] += float(inj[t, 0]); s[0, 9] += float(inj[t, 1]); env.set_state(s)
             ob, r, d, _ = env.step(a[None, :])                  # numpy in -> numpy out (snk_step_host)
             tk = int(env.last_ticks[0])
             if tk != int(golden[name + "/ticks"][t]) or bool(d[0]) != bool(golden[name + "/done"][t]):
@@ -157,6 +160,10 @@ def test_golden_scenarios_on_the_gpu(torch, golden):
                 assert np.abs(ob[0, 48:51] - golden[name + "/obs"][t + 1][48:51]).max() < (2e-3 if t == 0 else 2e-2), (name, t)
                 assert abs(r[0] - golden[name + "/rew"][t]) < 2e-2, (name, t)
         assert agree >= min(len(acts), 8), (name, agree)
+        if name == "terminate_q9":
+            assert golden[name + "/done"][:agree].sum() >= 4    # the |q9| > 0.5 termination was really taken on the GPU
+        if name == "lifted":
+            assert agree == len(acts)                           # height break after tick 1, mid-loop break, zero-tick height termination
         env.close()
 
 

@@ -81,8 +81,9 @@ def test_shards_equal_the_unsharded_batch(torch):
 
 
 def test_row_storage_variants_agree(torch):
-    """SNK_EXACT_ROWS=smem (every warp's rows in shared memory) must give the same bits as the default
-    (rows of 4 warps in tensor memory): run the variant in a subprocess and compare a checksum."""
+    """The three row layouts -- hybrid (default: 8 warps, rows in tensor memory + shared memory + registers), split (4 tensor-memory
+    warps + 2/3 shared-memory warps) and smem (every warp's rows in shared memory) -- must give the same bits: run each in a
+    subprocess and compare a checksum."""
     import os, subprocess, sys
     code = ("import torch, hashlib; from bullet_envs_b200 import SnakeVecEnv;"
             "g=torch.Generator().manual_seed(9); a=(torch.rand((4,1536,8),generator=g)*2-1).cuda();"
@@ -93,18 +94,18 @@ def test_row_storage_variants_agree(torch):
             "print('SUM', h.hexdigest())")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sums = []
-    for rows in ("tmem", "smem"):
+    for rows in ("hybrid", "split", "smem"):
         env = dict(os.environ, SNK_EXACT_ROWS=rows, PYTHONPATH=root)
         out = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
         assert out.returncode == 0, out.stderr[-2000:]
         sums.append([l for l in out.stdout.splitlines() if l.startswith("SUM")][0])
-    assert sums[0] == sums[1]
+    assert sums[0] == sums[1] == sums[2], sums
 
 
 def test_warp_count_and_hand_out_policy_do_not_change_results(torch):
-    """The launcher picks 6 or 7 working warps per SM (two or three shared-memory warps) by batch size and hands the first wave
-    out warp-major, fastest warps first: none of that may change a bit of the results.  70 000 environments (above the switch
-    to 7 warps), forced to 6 / 7 / 4 warps and to the CTA-major and fully dynamic hand-outs, in subprocesses; checksums."""
+    """The number of working warps per SM and the hand-out policy (warp-major first wave, longest-first order) may not change a bit
+    of the results.  70 000 environments (about two waves of the grid), forced to 6 / 7 / 4 warps and to the CTA-major and fully
+    dynamic hand-outs and the index order, in subprocesses; checksums."""
     import os, subprocess, sys
     code = ("import torch, hashlib; from bullet_envs_b200 import SnakeVecEnv;"
             "g=torch.Generator().manual_seed(4); a=(torch.rand((2,70000,8),generator=g)*2-1).cuda();"

@@ -69,3 +69,29 @@ def test_rollout_argument_errors(torch):
     with pytest.raises(RuntimeError, match="exact motor solver"):
         env.rollout_linear(np.zeros((4, 8, 56), np.float32), 2)
     env.close()
+
+
+def test_gae_kernel_matches_the_reference_recursion(torch):
+    """snk_gae (one launch) against compute_gae of ppo/agent.py:14-22 restated on lists of [N,1] tensors, as ppo/train.py:170-173
+    calls it -- in fp32 on the same device (same operation order: bit-exact up to fma contraction, asserted to 1e-5) and in fp64."""
+    from bullet_envs_b200.rollout import RolloutBuffer
+    g = torch.Generator().manual_seed(0)
+    for T, N in ((20, 65536), (7, 1001), (1, 5)):
+        buf = RolloutBuffer(T, N, device="cuda")
+        buf.rewards.copy_(torch.randn((T, N), generator=g)); buf.values.copy_(torch.randn((T, N), generator=g))
+        buf.dones.copy_((torch.rand((T, N), generator=g) < 0.15).to(torch.uint8))
+        nxt = torch.randn((N,), generator=g).cuda()
+        ret, adv = buf.gae(nxt, gamma=0.99, tau=0.95)
+
+        def reference(dtype):   # ppo/agent.py:14-22
+            values = [v.to(dtype)[:, None] for v in buf.values] + [nxt.to(dtype)[:, None]]
+            rewards = [r.to(dtype)[:, None] for r in buf.rewards]; masks = [1 - d.to(dtype)[:, None] for d in buf.dones]
+            gae = 0; returns = []
+            for step in reversed(range(len(rewards))):
+                delta = rewards[step] + 0.99 * values[step + 1] * masks[step] - values[step]
+                gae = delta + 0.99 * 0.95 * masks[step] * gae
+                returns.insert(0, gae + values[step])
+            return torch.cat(returns, 1).T
+        assert (ret - reference(torch.float32)).abs().max() < 1e-5
+        assert (ret.double() - reference(torch.float64)).abs().max() < 1e-4
+        assert torch.equal(adv, ret - buf.values) or (adv - (ret - buf.values)).abs().max() < 1e-5

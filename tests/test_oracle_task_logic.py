@@ -6,7 +6,7 @@ import pytest
 from bullet_envs_b200 import default_params
 from oracle.oracle_py import Oracle
 
-SCENARIOS = ["const_half", "random", "clipped", "serpenoid", "terminate_q9"]
+SCENARIOS = ["const_half", "random", "clipped", "serpenoid", "terminate_q9", "lifted"]
 
 
 def test_golden_meta(golden, model):
@@ -24,7 +24,10 @@ def test_oracle_reproduces_reference_python(golden, model, name, solver):
     o = Oracle(1, default_params(motor_solver=0 if solver else 2), model)
     obs = o.reset()
     assert np.array_equal(obs[0], golden[name + "/obs"][0])
+    inj = golden[name + "/inject"]
     for t, a in enumerate(acts):
+        if inj[t].any():                                       # the state edit the generator applied to the fake simulator before this step
+            s = o.get_state(); s[0, 2] += inj[t, 0]; s[0, 9] += inj[t, 1]; o.set_state(s)
         ob, r, d, tk = o.step(a[None, :])
         assert tk[0] == golden[name + "/ticks"][t], (name, t)
         assert bool(d[0]) == bool(golden[name + "/done"][t]), (name, t)
@@ -36,6 +39,11 @@ def test_oracle_reproduces_reference_python(golden, model, name, solver):
 
 def test_golden_covers_the_branches(golden):
     assert golden["clipped/done"].sum() >= 1                 # -5 penalty + double reset path
+    assert golden["terminate_q9/done"].sum() >= 10           # |q9| > 0.5 (SnakeGymEnv.py:100)
+    assert np.abs(golden["terminate_q9/obs"][:, 9]).max() < 0.5   # ... and every returned observation is the post-reset / unterminated one
+    # checkSnakeHeight (snake.py:237-245): break after the first tick, break in the middle of the loop, zero-tick termination
+    lt, ld = golden["lifted/ticks"], golden["lifted/done"]
+    assert lt[0] == 1 and ld[0] and 1 < lt[3] < 15 and ld[3] and lt[5] == 0 and ld[5] and ld.sum() == 3
     assert (golden["const_half/ticks"] == 0).any()           # Q5 zero-tick step
     assert golden["random/ticks"].max() <= 41                # `counter > 40` cap
 

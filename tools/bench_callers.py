@@ -57,7 +57,7 @@ def ppo(args):
                 buf.actions[t] = a; buf.log_probs[t] = dist.log_prob(a); buf.values[t] = v.squeeze(-1)
                 env.step(a, out=buf.out(t))                      # the kernel writes obs[t+1], rewards[t], dones[t] in place
             _, next_value = net(buf.obs[T])
-            returns = compute_gae(next_value.squeeze(-1), buf.rewards, buf.masks(), buf.values)   # ppo/agent.py:14-22 on device
+            returns, adv = buf.gae(next_value.squeeze(-1))         # ppo/agent.py:14-22 as one kernel (snk_gae)
             buf.roll()
         return returns
 
