@@ -23,22 +23,34 @@ def sass(tmp_path_factory):
     return str(out)
 
 
-def test_step_kernel_uses_tensor_memory(sass):
+def test_hybrid_step_kernel_uses_tensor_memory_shared_memory_and_registers(sass):
+    """the benchmarked kernel (RowsH): 8 / 4 / 2 word tensor-memory loads, tensor-memory stores of the solver state, the three
+    shared-memory loads of the friction record, and a fully unrolled normal sweep (one 4-word load per contact)"""
+    txt = open(sass).read()
+    k = [p for p in txt.split("Function : ") if p.startswith("_Z19snk_hyb_step_kernelILb1EE")][0]
+    assert k.count("LDTM.x8") >= 3 and k.count("LDTM.x4") >= 32 and k.count("LDTM.x2") >= 32
+    assert k.count("STTM.x2") >= 3 and k.count("STTM.x8") >= 2
+    assert k.count("LDS.128") >= 3 and k.count("LDS.64") >= 3
+
+
+def test_split_step_kernel_uses_tensor_memory(sass):
     txt = open(sass).read()
     assert "snk_exact_step_kernelILb1ELi3EE" in txt and "snk_exact_step_kernelILb1ELi2EE" in txt    # both warp configurations
     k = [p for p in txt.split("Function : ") if p.startswith("_Z21snk_exact_step_kernelILb1ELi3EE")][0]
     assert k.count("LDTM.x16") >= 2 and k.count("LDTM.x4") >= 4 and "STTM" in k                     # tcgen05.ld / tcgen05.st
-    assert "UTCATOMSWS" in k or "TMEM" in k.upper() or "LDTM" in k                                  # allocation / access mnemonics
 
 
 def test_bank_conflict_counter_finds_the_solver_loops(sass):
+    """tools/sass_bank_conflicts.py on the hybrid kernel: the rolled friction loop (2 pairs per iteration, MUFU of the cone projection,
+    tensor-memory loads) is found, and its register-bank conflicts per pair stay below the first version's 17.7 per contact and sweep"""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import sass_bank_conflicts as sbc
-    rep = sbc.report(sass, "snk_exact_step_kernelILb1ELi3EE")
-    kinds = {}
-    for kind, n, conflicts, reuse, nfp in rep:
-        if (kind[1] == "F" and 120 <= n <= 140) or (kind[1] == "N" and 90 <= n <= 110):
-            kinds[kind] = conflicts / (2 if kind[1] == "F" else 4)
-    assert set(kinds) == {"TF", "TN", "SF", "SN"}, rep
-    # conflict cycles per contact and sweep of the committed code: well below the 17.7 of the first version
-    assert kinds["TF"] + kinds["TN"] < 16 and kinds["SF"] + kinds["SN"] < 16, kinds
+    k = sbc.kernels(sass)
+    name = [n for n in k if "snk_hyb_step_kernelILb1EE" in n][0]
+    found = []
+    for body in sbc.loops(sbc.ins_of(k[name])):
+        if 100 <= len(body) <= 200 and any("LDTM.x8" in t for _, t in body) and sum("MUFU.RSQ" in t for _, t in body) == 2:
+            found.append((len(body),) + sbc.metric(body))
+    assert len(found) == 1, found
+    n, conflicts, reuse, nfp = found[0]
+    assert n <= 150 and conflicts / 2 < 17.7, found
