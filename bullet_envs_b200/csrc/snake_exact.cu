@@ -431,11 +431,14 @@ __device__ __forceinline__ RowsH hyb_rows(StepSmemH& S, uint32_t tbase, int warp
     return R;
 }
 
-template <bool CONE>
+// TRACE = true: the same kernel with the mode='test' info stream (snk_step_trace) -- a separate instantiation, so the
+// benchmarked one carries no trace code, and the traced step returns bit for bit what the plain step returns.
+template <bool CONE, bool TRACE>
 __global__ void __launch_bounds__(HWARPS * 32, 1)
 snk_hyb_step_kernel(const KParams P, float* __restrict__ state, float* __restrict__ tgt_scratch, const float* __restrict__ actions, float* __restrict__ obs,
                     float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks, unsigned long long* __restrict__ counters,
-                    const int32_t* __restrict__ order, int64_t n, int active_warps, int spread) {
+                    const int32_t* __restrict__ order, int64_t n, int active_warps, int spread, float* __restrict__ tick_obs,
+                    float* __restrict__ tick_links) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StepSmemH& S = *reinterpret_cast<StepSmemH*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -446,7 +449,44 @@ snk_hyb_step_kernel(const KParams P, float* __restrict__ state, float* __restric
     const int64_t first_base = (spread == 2) ? -1 : (spread ? ((int64_t)warp * gridDim.x + blockIdx.x) * 32 : ((int64_t)blockIdx.x * active_warps + warp) * 32);
     const int64_t dyn_base = (spread == 2) ? 0 : min((int64_t)gridDim.x * active_warps * 32, n);
     if (warp < active_warps) // SNK_EXACT_WARPS (ablation): the other warps take no environments
-        run_warp<CONE>(P, hyb_rows(S, tbase, warp, lane), state, tgt_scratch, actions, obs, rew, done, ticks, counters, order, n, first_base, dyn_base);
+        run_warp<CONE, RowsH, TRACE>(P, hyb_rows(S, tbase, warp, lane), state, tgt_scratch, actions, obs, rew, done, ticks, counters, order, n, first_base,
+                                     dyn_base, tick_obs, tick_links);
+    hyb_tmem_free(tbase, warp);
+}
+
+// n_ticks raw ticks with explicit targets[N,16] (snk_tick; gait script): every environment runs the same number of ticks, so the
+// assignment is static (thread = environment), 256 environments per CTA
+template <bool CONE>
+__global__ void __launch_bounds__(HWARPS * 32, 1)
+snk_hyb_tick_kernel(const KParams P, float* __restrict__ state, const float* __restrict__ targets, unsigned long long* __restrict__ counters, int64_t n,
+                    int n_ticks) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StepSmemH& S = *reinterpret_cast<StepSmemH*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tbase = hyb_tmem_alloc(S, warp);
+    RowsH R = hyb_rows(S, tbase, warp, lane);
+    const int64_t env = (int64_t)blockIdx.x * (HWARPS * 32) + threadIdx.x;
+    const bool live = env < n;
+    ExEnv e;
+    e.st = state + (live ? env : 0) * SNK_STATE_STRIDE;
+    e.tid = lane;
+    R.tg = const_cast<float*>(targets) + (live ? env : 0) * NJ; // the caller's row itself (only read here)
+    ex_load_base(e);
+    int iters = 0;
+#pragma unroll 1
+    for (int t = 0; t < n_ticks; t++) {
+        bool ab;
+        ExTickOut to;
+        ex_tick<CONE>(cT, P, R, e, live, false, &ab, &to);
+        iters += to.iterations;
+    }
+    if (live) {
+        ex_store_base(e);
+        if (counters) {
+            atomicAdd(&counters[0], (unsigned long long)n_ticks);
+            atomicAdd(&counters[1], (unsigned long long)iters);
+        }
+    }
     hyb_tmem_free(tbase, warp);
 }
 
@@ -663,8 +703,12 @@ cudaError_t snk_exact_configure(const ExTables* host_tables) {
     if (e == cudaSuccess) e = set_smem(snk_exact_rollout_kernel<false, 2>, sizeof(StepSmemT<2>));
     if (e == cudaSuccess) e = set_smem(snk_exact_rollout_kernel<true, 3>, sizeof(StepSmemT<3>));
     if (e == cudaSuccess) e = set_smem(snk_exact_rollout_kernel<false, 3>, sizeof(StepSmemT<3>));
-    if (e == cudaSuccess) e = set_smem(snk_hyb_step_kernel<true>, sizeof(StepSmemH));
-    if (e == cudaSuccess) e = set_smem(snk_hyb_step_kernel<false>, sizeof(StepSmemH));
+    if (e == cudaSuccess) e = set_smem(snk_hyb_step_kernel<true, false>, sizeof(StepSmemH));
+    if (e == cudaSuccess) e = set_smem(snk_hyb_step_kernel<false, false>, sizeof(StepSmemH));
+    if (e == cudaSuccess) e = set_smem(snk_hyb_step_kernel<true, true>, sizeof(StepSmemH));
+    if (e == cudaSuccess) e = set_smem(snk_hyb_step_kernel<false, true>, sizeof(StepSmemH));
+    if (e == cudaSuccess) e = set_smem(snk_hyb_tick_kernel<true>, sizeof(StepSmemH));
+    if (e == cudaSuccess) e = set_smem(snk_hyb_tick_kernel<false>, sizeof(StepSmemH));
     if (e == cudaSuccess) e = set_smem(snk_hyb_rollout_kernel<true>, sizeof(StepSmemH));
     if (e == cudaSuccess) e = set_smem(snk_hyb_rollout_kernel<false>, sizeof(StepSmemH));
     if (e != cudaSuccess) return e;
@@ -701,8 +745,8 @@ cudaError_t snk_exact_launch_step(const KParams& P, float* state, float* tgt_scr
         // a small batch gets one CTA per warp of environments: all SMs before a second warp per SM
         const int64_t want = g_spread ? (n + EB - 1) / EB : (n + aw * 32 - 1) / (aw * 32);
         dim3 grid((unsigned)(want < sms ? want : sms)), block(HWARPS * 32);
-        if (P.cone) snk_hyb_step_kernel<true><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n, aw, g_spread);
-        else snk_hyb_step_kernel<false><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n, aw, g_spread);
+        if (P.cone) snk_hyb_step_kernel<true, false><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n, aw, g_spread, nullptr, nullptr);
+        else snk_hyb_step_kernel<false, false><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n, aw, g_spread, nullptr, nullptr);
     } else if (g_rows == ROWS_SPLIT) {
         const int sw = aw > TWARPS + 2 ? 3 : 2;
         const int per_cta = (TWARPS + sw) * 32, per_cta_active = aw * 32;
@@ -725,6 +769,12 @@ cudaError_t snk_exact_launch_step_trace(const KParams& P, float* state, float* t
                                         int32_t* ticks, unsigned long long* counters, int64_t n, float* tick_obs, float* tick_links, cudaStream_t st) {
     const int dev = cur_dev();
     const int64_t warps = (n + EB - 1) / EB;
+    if (g_rows == ROWS_HYBRID) { // the benchmarked kernel's TRACE instantiation: same arithmetic, same bits as snk_step
+        dim3 grid((unsigned)(warps < g_sms[dev] ? warps : g_sms[dev])), block(HWARPS * 32);
+        if (P.cone) snk_hyb_step_kernel<true, true><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, nullptr, n, HWARPS, 1, tick_obs, tick_links);
+        else snk_hyb_step_kernel<false, true><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, nullptr, n, HWARPS, 1, tick_obs, tick_links);
+        return cudaGetLastError();
+    }
     dim3 grid((unsigned)(warps < g_smem_ctas[dev] ? warps : g_smem_ctas[dev])), block(EB);
     if (P.cone) snk_exact_step_trace_kernel<true><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, n, tick_obs, tick_links);
     else snk_exact_step_trace_kernel<false><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, n, tick_obs, tick_links);
@@ -764,6 +814,12 @@ cudaError_t snk_exact_launch_rollout(const KParams& P, float* state, float* tgt_
 
 cudaError_t snk_exact_launch_tick(const KParams& P, float* state, const float* targets, unsigned long long* counters, int64_t n,
                                   int n_ticks, cudaStream_t st) {
+    if (g_rows == ROWS_HYBRID) {
+        dim3 grid((unsigned)((n + HWARPS * 32 - 1) / (HWARPS * 32))), block(HWARPS * 32);
+        if (P.cone) snk_hyb_tick_kernel<true><<<grid, block, sizeof(StepSmemH), st>>>(P, state, targets, counters, n, n_ticks);
+        else snk_hyb_tick_kernel<false><<<grid, block, sizeof(StepSmemH), st>>>(P, state, targets, counters, n, n_ticks);
+        return cudaGetLastError();
+    }
     dim3 grid((unsigned)((n + EB - 1) / EB)), block(EB);
     if (P.cone) snk_exact_tick_kernel<true><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, targets, counters, n, n_ticks);
     else snk_exact_tick_kernel<false><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, targets, counters, n, n_ticks);

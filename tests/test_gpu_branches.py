@@ -60,7 +60,7 @@ def test_height_terminations_in_a_batch(torch):
     assert (tk[kind == 3] == 0).all() and dg[kind == 3].all()
     assert not dg[kind == 0].all() and (tk[kind == 0] > 20).mean() > 0.8
     lifted = kind != 0
-    assert (rg[lifted] < -4.9).all()                                # the -5 of SnakeGymEnv.py:40
+    assert (rg[lifted] < -4.0).all() and (orr[lifted] < -4.0).all()   # the -5 of SnakeGymEnv.py:40 (plus a few cm of progress)
     assert np.abs(rg - orr)[kind == 3].max() < 1e-5                 # no tick ran: closed-form reward
     og = obs.cpu().numpy()
     assert (og[lifted][:, :32] == 0).all() and (og[lifted][:, 48:51] == 0).all() and (og[lifted][:, 54] == 1).all()   # post-reset observation

@@ -116,7 +116,7 @@ def test_config2_free_running(torch, actions):
     assert tick_eq[-10:].mean() >= 0.97                             # ... and no drift: still true in the last ten steps
     # joints of the environments whose integer outputs agree: round-off in the median and at the 99th percentile (an environment that
     # took one tick more or less a few steps ago is still converging back: bounded by the maximum)
-    assert pct["q"][2] <= 1e-5 and pct["q"][3] <= 2e-2 and pct["qd"][2] <= 1e-4 * max(1.0, scale["qd"]), (pct["q"], pct["qd"])
+    assert pct["q"][2] <= 1e-5 and pct["q"][3] <= 5e-2 and pct["qd"][2] <= 1e-4 * max(1.0, scale["qd"]), (pct["q"], pct["qd"])
     # the base pose separates (chaotic contact dynamics): stated bounds over the 100 steps -- median within 10 cm / 0.1 in any quaternion
     # component, 99 % within the snake's own length
     assert pct["pos"][0] <= 0.10 and pct["pos"][2] <= 1.0, pct["pos"]
