@@ -157,6 +157,26 @@ class Oracle:
         if f(self._h, ctypes.c_int(int(cpp))) != 0:
             raise ValueError("contact points per cylinder must be 1 or 2")
 
+    def set_manifold(self, on=True, warm=0.0):
+        """Oracle-only switch for SURVEY 8f rank 2: Bullet-style persistent contact manifolds (support vertex of the 32-gon hull, 4 cached
+        points per cylinder, Bullet's refresh / breaking rule) in the exact tick; ``warm`` = warm-start factor of the cached normal
+        impulses (Bullet's warmstartingFactor is 0.1; 0 = off).  Clears the caches."""
+        f = self._fn("set_manifold"); f.restype = ctypes.c_int; f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double]
+        if f(self._h, int(bool(on)), float(warm)) != 0:
+            raise RuntimeError("set_manifold failed")
+
+    def set_joint_limits(self, on=True, angle=1.57):
+        """Oracle-only switch: joint-limit rows (snake.urdf:833-840, +-1.57 rad) in the Bullet-order tick (motor_solver = 0)."""
+        f = self._fn("set_joint_limits"); f.restype = ctypes.c_int; f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double]
+        f(self._h, int(bool(on)), float(angle))
+
+    def row_stats(self):
+        """(mean cached contact points per tick, joint-limit row activations) of the optional rows."""
+        out = (ctypes.c_double * 2)()
+        f = self._fn("row_stats"); f.restype = ctypes.c_int
+        f(self._h, out)
+        return float(out[0]), int(out[1])
+
     def self_clearance(self):
         """Twin of ``snk_self_clearance``: lower bound [n] of the smallest distance between non-consecutive cylinders."""
         out = np.empty(self.n, self.dtype)
