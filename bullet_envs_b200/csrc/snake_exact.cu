@@ -630,6 +630,11 @@ __global__ void snk_exact_order_kernel(int64_t n, const uint8_t* __restrict__ bu
     if (env < n) order[base[b] + my] = (int32_t)env;
 }
 
+#ifdef SNK_SCREEN
+// tools/screen_variants.py compiles this file with -DSNK_SCREEN: only the benchmarked kernel, for a look at its SASS
+template __global__ void snk_hyb_step_kernel<true, false>(const KParams, float*, float*, const float*, float*, float*, uint8_t*, int32_t*, unsigned long long*,
+                                                           const int32_t*, int64_t, int, int, float*, float*);
+#else
 // ---------------------------------------------------------------------------------------------
 // launch wrappers used by the C-ABI host code (snake_abi.cu)
 // ---------------------------------------------------------------------------------------------
@@ -825,3 +830,4 @@ cudaError_t snk_exact_launch_tick(const KParams& P, float* state, const float* t
     else snk_exact_tick_kernel<false><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, targets, counters, n, n_ticks);
     return cudaGetLastError();
 }
+#endif // SNK_SCREEN

@@ -46,6 +46,27 @@
 #ifndef SNK_UNROLL_F
 #define SNK_UNROLL_F 2
 #endif
+// Operation orders of the solver rows (tools/screen_variants.py): the arithmetic is the same up to the association of the sums, but
+// ptxas allocates registers differently for each, and every pair of source registers of one instruction that shares a register bank
+// costs an issue cycle.  The defaults are the orders with the fewest conflicts in the SASS of the benchmarked kernel.
+#ifndef SNK_VAR_G
+#define SNK_VAR_G 1
+#endif
+#ifndef SNK_VAR_DW
+#define SNK_VAR_DW 1
+#endif
+#ifndef SNK_VAR_F
+#define SNK_VAR_F 0
+#endif
+#ifndef SNK_VAR_T
+#define SNK_VAR_T 1
+#endif
+#ifndef SNK_VAR_U
+#define SNK_VAR_U 1
+#endif
+#ifndef SNK_VAR_NDW
+#define SNK_VAR_NDW 0
+#endif
 #define SNK_PRAGMA_(x) _Pragma(#x)
 #define SNK_UNROLL(n) SNK_PRAGMA_(unroll n)
 
@@ -299,6 +320,20 @@ SNK_HD M3 mulBT(const M3& A, const M3& B) { // A B^T
 #pragma unroll
         for (int j = 0; j < 3; j++) o.m[3 * i + j] = A.m[3 * i] * B.m[3 * j] + A.m[3 * i + 1] * B.m[3 * j + 1] + A.m[3 * i + 2] * B.m[3 * j + 2];
     return o;
+}
+// c + a1 b1 + a2 b2 + a3 b3 as three chained fmas, innermost term selected by ORDER (0: term 1 innermost, 1: term 3, 2: term 3 then 1)
+template <int ORDER>
+SNK_HD float ex_sum3(float a1, float b1, float a2, float b2, float a3, float b3, float c) {
+    if (ORDER == 0) return fmaf(a3, b3, fmaf(a2, b2, fmaf(a1, b1, c)));
+    if (ORDER == 1) return fmaf(a1, b1, fmaf(a2, b2, fmaf(a3, b3, c)));
+    return fmaf(a2, b2, fmaf(a1, b1, fmaf(a3, b3, c)));
+}
+// a1 b1 + a2 b2 + a3 b3: a product and two fmas, the plain product selected by ORDER (0: term 3, 1: term 1, 2: term 3 with 1 and 2 swapped)
+template <int ORDER>
+SNK_HD float ex_dot3(float a1, float b1, float a2, float b2, float a3, float b3) {
+    if (ORDER == 0) return fmaf(a1, b1, fmaf(a2, b2, a3 * b3));
+    if (ORDER == 1) return fmaf(a3, b3, fmaf(a2, b2, a1 * b1));
+    return fmaf(a2, b2, fmaf(a1, b1, a3 * b3));
 }
 struct S3 { float xx, xy, xz, yy, yz, zz; }; // symmetric 3x3
 SNK_HD V3 mul(const S3& S, V3 v) {
@@ -602,15 +637,15 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
     const float sthr = P.sthr, mu = P.mu; // kernel parameters: constant-bank operands, no register reads
     bool frozen = !commit;
     int sweeps = 0;
+    // a frozen lane applies its (discarded) impulse changes through a ZERO inverse inertia: dw and dV stay bit-exact without any
+    // per-row select or branch.  Nothing after the solver needs J^-1 or 1/M, so the lane's own copies are zeroed when it freezes.
+    S3 Jg = Ji;
+    float iM = invM;
 #pragma unroll 1
     for (int it = 0; it < P.iters; it++) {
         if (ex_all(frozen)) break;
         float viol = 0.f; // max over the rows of |d| - sqrt(thr) invD (in the row's scaled units)
-        // a frozen lane applies its (discarded) impulse changes through a zero inverse inertia: dw and dV stay
-        // bit-exact without any per-row select or branch
-        const float gate = frozen ? 0.f : 1.f, iM = invM * gate;
-        S3 Jg;
-        Jg.xx = Ji.xx * gate; Jg.xy = Ji.xy * gate; Jg.xz = Ji.xz * gate; Jg.yy = Ji.yy * gate; Jg.yz = Ji.yz * gate; Jg.zz = Ji.zz * gate;
+        if (frozen) { Jg.xx = 0.f; Jg.xy = 0.f; Jg.xz = 0.f; Jg.yy = 0.f; Jg.yz = 0.f; Jg.zz = 0.f; iM = 0.f; }
         {   // ---- normal rows; the record of row k+1 is fetched while row k is on the chain
             // one row: LN = normal impulse, RX / RY = lever arm, IDN = invD_n, N1 = rhs_n invD_n
 #define SNK_NORMAL_ROW(K, LN, RX, RY, IDN, N1)                                            \
@@ -623,9 +658,15 @@ SNK_HD void ex_tick(const ExTables& T, const KParams& P, const Rows& R, ExEnv& e
                 const float dd = sum - ln;                                                \
                 R.st_ln((K), frozen ? ln : sum);                                          \
                 const float t1 = (RY) * dd, t2 = -(RX) * dd; /* rn * dd */                \
-                dw.x = fmaf(Jg.xx, t1, fmaf(Jg.xy, t2, dw.x));                            \
-                dw.y = fmaf(Jg.xy, t1, fmaf(Jg.yy, t2, dw.y));                            \
-                dw.z = fmaf(Jg.xz, t1, fmaf(Jg.yz, t2, dw.z));                            \
+                if (SNK_VAR_NDW == 0) {                                                   \
+                    dw.x = fmaf(Jg.xx, t1, fmaf(Jg.xy, t2, dw.x));                        \
+                    dw.y = fmaf(Jg.xy, t1, fmaf(Jg.yy, t2, dw.y));                        \
+                    dw.z = fmaf(Jg.xz, t1, fmaf(Jg.yz, t2, dw.z));                        \
+                } else {                                                                  \
+                    dw.x = fmaf(Jg.xy, t2, fmaf(Jg.xx, t1, dw.x));                        \
+                    dw.y = fmaf(Jg.yy, t2, fmaf(Jg.xy, t1, dw.y));                        \
+                    dw.z = fmaf(Jg.yz, t2, fmaf(Jg.xz, t1, dw.z));                        \
+                }                                                                         \
                 dV.z = fmaf(dd, iM, dV.z);                                                \
                 viol = fmaxf(viol, fmaf(-sthr, (IDN), fabsf(dd)));                        \
             }
@@ -663,10 +704,11 @@ SNK_UNROLL(SNK_UNROLL_N)
                 const float rx = x0.y, ry = x0.z, rz = x1.x;                                                                  \
                 const float pa = x3.x + x2.z, pb = x3.y + x2.w, lim = mu * x0.x;                                              \
                 /* u = dV + dw x r */                                                                                         \
-                const float ux = fmaf(-dw.z, ry, fmaf(dw.y, rz, dV.x));                                                       \
-                const float uy = fmaf(-dw.x, rz, fmaf(dw.z, rx, dV.y));                                                       \
-                const float uz = fmaf(-dw.y, rx, fmaf(dw.x, ry, dV.z));                                                       \
-                const float g1 = fmaf(x1.y, ux, fmaf(x1.z, uy, x1.w * uz)), g2 = fmaf(x2.x, ux, fmaf(-x1.y, uy, x2.y * uz));  \
+                const float ux = SNK_VAR_U ? fmaf(dw.y, rz, fmaf(-dw.z, ry, dV.x)) : fmaf(-dw.z, ry, fmaf(dw.y, rz, dV.x));   \
+                const float uy = SNK_VAR_U ? fmaf(dw.z, rx, fmaf(-dw.x, rz, dV.y)) : fmaf(-dw.x, rz, fmaf(dw.z, rx, dV.y));   \
+                const float uz = SNK_VAR_U ? fmaf(dw.x, ry, fmaf(-dw.y, rx, dV.z)) : fmaf(-dw.y, rx, fmaf(dw.x, ry, dV.z));   \
+                const float g1 = ex_dot3<SNK_VAR_G>(x1.y, ux, x1.z, uy, x1.w, uz);                                            \
+                const float g2 = ex_dot3<SNK_VAR_G>(x2.x, ux, -x1.y, uy, x2.y, uz);                                           \
                 float sa = fmaf(-g1, x3.z, pa), sb = fmaf(-g2, x3.w, pb);                                                     \
                 if (CONE) { /* implicit cone: radial projection onto the disc of radius mu * lambda_n,                        \
                                s <- s min(1, lim / |s|)  (0/0 and lim/0 resolve to 1 through fminf) */                        \
@@ -678,12 +720,17 @@ SNK_UNROLL(SNK_UNROLL_N)
                 }                                                                                                             \
                 const float da = sa - x3.x, db = sb - x3.y;                                                                   \
                 R.st_lf((K), frozen ? x3.x : sa, frozen ? x3.y : sb);                                                         \
-                const float fx = fmaf(x2.x, db, x1.y * da), fy = fmaf(-x1.y, db, x1.z * da), fz = fmaf(x2.y, db, x1.w * da);  \
-                const float tx = fmaf(ry, fz, -rz * fy), ty = fmaf(rz, fx, -rx * fz), tz = fmaf(rx, fy, -ry * fx); /* r x f */ \
+                const float fx = SNK_VAR_F ? fmaf(x1.y, da, x2.x * db) : fmaf(x2.x, db, x1.y * da);                           \
+                const float fy = SNK_VAR_F ? fmaf(x1.z, da, -x1.y * db) : fmaf(-x1.y, db, x1.z * da);                         \
+                const float fz = SNK_VAR_F ? fmaf(x1.w, da, x2.y * db) : fmaf(x2.y, db, x1.w * da);                           \
+                /* r x f */                                                                                                   \
+                const float tx = SNK_VAR_T ? fmaf(-rz, fy, ry * fz) : fmaf(ry, fz, -rz * fy);                                 \
+                const float ty = SNK_VAR_T ? fmaf(-rx, fz, rz * fx) : fmaf(rz, fx, -rx * fz);                                 \
+                const float tz = SNK_VAR_T ? fmaf(-ry, fx, rx * fy) : fmaf(rx, fy, -ry * fx);                                 \
                 dV.x = fmaf(fx, iM, dV.x); dV.y = fmaf(fy, iM, dV.y); dV.z = fmaf(fz, iM, dV.z);                              \
-                dw.x = fmaf(Jg.xz, tz, fmaf(Jg.xy, ty, fmaf(Jg.xx, tx, dw.x)));                                               \
-                dw.y = fmaf(Jg.yz, tz, fmaf(Jg.yy, ty, fmaf(Jg.xy, tx, dw.y)));                                               \
-                dw.z = fmaf(Jg.zz, tz, fmaf(Jg.yz, ty, fmaf(Jg.xz, tx, dw.z)));                                               \
+                dw.x = ex_sum3<SNK_VAR_DW>(Jg.xx, tx, Jg.xy, ty, Jg.xz, tz, dw.x);                                            \
+                dw.y = ex_sum3<SNK_VAR_DW>(Jg.xy, tx, Jg.yy, ty, Jg.yz, tz, dw.y);                                            \
+                dw.z = ex_sum3<SNK_VAR_DW>(Jg.xz, tx, Jg.yz, ty, Jg.zz, tz, dw.z);                                            \
                 /* (da D1 + db D2)^2 <= thr  <=>  |da invD2 + db invD1| <= sqrt(thr) invD1 invD2 */                           \
                 viol = fmaxf(viol, fmaf(-sthr * x3.z, x3.w, fabsf(fmaf(da, x3.w, db * x3.z))));                               \
             }
