@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 def main():
     import torch
     from bullet_envs_b200 import SnakeVecEnv
-    sizes = [int(x) for x in sys.argv[1:]] or [16, 256, 4096, 14208, 28416, 65536]
+    sizes = [int(x) for x in sys.argv[1:]] or [16, 4096, 18944, 37888, 65536, 131072, 262144]
     steps, warmup = 20, 5
     for n in sizes:
         env = SnakeVecEnv(num_envs=n, device=0)
