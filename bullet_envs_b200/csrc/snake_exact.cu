@@ -82,10 +82,13 @@ __device__ __forceinline__ void run_warp(const KParams& P, Rows R, float* __rest
                                          float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks,
                                          unsigned long long* __restrict__ counters, const int32_t* __restrict__ order, int64_t n,
                                          int64_t first_base, int64_t dyn_base, float* __restrict__ tick_obs = nullptr,
-                                         float* __restrict__ tick_links = nullptr) {
+                                         float* __restrict__ tick_links = nullptr, int pool = 0, int64_t n_long = -1, int64_t dyn_base_short = 0) {
     // Hand-out positions: the warp's first 32 are static, [first_base, first_base + 32), laid out warp-major over the
     // grid by the caller so that a batch smaller than the grid's lanes spreads over all SMs (one warp per scheduler
-    // before a second one anywhere); every later position comes from the global counter, which starts at dyn_base.
+    // before a second one anywhere); every later position comes from a global counter, which starts at dyn_base.
+    // TWO POOLS (HandOut below): positions [0, n_long) are the long pool, [n_long, n) the short pool; a warp draws from its own pool
+    // (counter [4] / [6]) and moves over to the other one when its own is exhausted.  n_long < 0: one pool.
+    if (n_long < 0) n_long = n;
     const int lane = R.lane;
     const unsigned lt_mask = (1u << lane) - 1u;
     ExEnv e; // a lane without an environment computes (masked) on record 0 in the rest pose
@@ -105,17 +108,18 @@ __device__ __forceinline__ void run_warp(const KParams& P, Rows R, float* __rest
 #pragma unroll 1
     for (;;) {
         // ---- lanes without an environment take the next ones (first: the static positions, then the global counter)
-        const unsigned need = __ballot_sync(FULL, !have);
-        if (need) {
+        unsigned need = __ballot_sync(FULL, !have);
+#pragma unroll 1
+        for (int attempt = 0; attempt < 2 && need; attempt++) { // second attempt: the other pool, once the warp's own is exhausted
             unsigned long long base = (unsigned long long)first_base;
             if (!first) {
-                if (lane == 0) base = (unsigned long long)dyn_base + atomicAdd(&counters[4], (unsigned long long)__popc(need));
+                if (lane == 0) base = (unsigned long long)(pool ? dyn_base_short : dyn_base) + atomicAdd(&counters[pool ? 6 : 4], (unsigned long long)__popc(need));
                 base = __shfl_sync(FULL, base, 0);
             }
             first = false;
             if (!have) {
                 const int64_t cand = (int64_t)base + __popc(need & lt_mask);
-                if (cand < n) {
+                if (cand < (pool ? n : n_long)) {
                     env = order ? (int64_t)order[cand] : cand; have = true; // longest-first order when the batch exceeds the lanes
                     e.st = state + env * SNK_STATE_STRIDE;
                     R.tg = tgt_scratch + env * NJ;
@@ -124,6 +128,9 @@ __device__ __forceinline__ void run_warp(const KParams& P, Rows R, float* __rest
                     ex_step_begin(P, R, e, &run);
                 }
             }
+            need = __ballot_sync(FULL, !have);
+            if (n_long == n) break;        // a single pool
+            if (need) pool ^= 1;           // positions beyond the pool's end were drawn: it is empty, go on with the other one
         }
         if (!__any_sync(FULL, have)) break;
         __syncwarp();
@@ -431,13 +438,18 @@ __device__ __forceinline__ RowsH hyb_rows(StepSmemH& S, uint32_t tbase, int warp
     return R;
 }
 
+struct HandOut {       // two-pool hand-out of a launch (see snk_hyb_step_kernel); short_warps = 0: one pool, plain longest-first
+    int64_t n_long;    // positions [0, n_long) of the longest-first order are the long pool, [n_long, n) the short pool
+    int short_warps;   // warps (in warp-major order over the grid) that draw from the short pool
+};
+
 // TRACE = true: the same kernel with the mode='test' info stream (snk_step_trace) -- a separate instantiation, so the
 // benchmarked one carries no trace code, and the traced step returns bit for bit what the plain step returns.
 template <bool CONE, bool TRACE>
 __global__ void __launch_bounds__(HWARPS * 32, 1)
 snk_hyb_step_kernel(const KParams P, float* __restrict__ state, float* __restrict__ tgt_scratch, const float* __restrict__ actions, float* __restrict__ obs,
                     float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks, unsigned long long* __restrict__ counters,
-                    const int32_t* __restrict__ order, int64_t n, int active_warps, int spread, float* __restrict__ tick_obs,
+                    const int32_t* __restrict__ order, int64_t n, int active_warps, int spread, const HandOut H, float* __restrict__ tick_obs,
                     float* __restrict__ tick_links) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StepSmemH& S = *reinterpret_cast<StepSmemH*>(smem_raw);
@@ -446,11 +458,27 @@ snk_hyb_step_kernel(const KParams P, float* __restrict__ state, float* __restric
     // first wave (SNK_EXACT_SPREAD): warp-major over the grid (default) -- a batch smaller than the grid's lanes puts one warp on every
     // scheduler of every SM before any scheduler gets a second one (warps w and w + 4 share scheduler w); 0 = CTA-major; 2 = no static
     // wave, everything from the global counter (ablations)
-    const int64_t first_base = (spread == 2) ? -1 : (spread ? ((int64_t)warp * gridDim.x + blockIdx.x) * 32 : ((int64_t)blockIdx.x * active_warps + warp) * 32);
-    const int64_t dyn_base = (spread == 2) ? 0 : min((int64_t)gridDim.x * active_warps * 32, n);
+    int64_t first_base = (spread == 2) ? -1 : (spread ? ((int64_t)warp * gridDim.x + blockIdx.x) * 32 : ((int64_t)blockIdx.x * active_warps + warp) * 32);
+    int64_t dyn_base = (spread == 2) ? 0 : min((int64_t)gridDim.x * active_warps * 32, n);
+    // Balanced hand-out (HandOut, computed by the launcher): with n = k L + r environments on L lanes, r lanes run k + 1 env-steps and
+    // the others k.  The `short` warps -- the first ones in warp-major order, i.e. one per scheduler on every SM before a second one
+    // anywhere -- run the k + 1 and draw them from the SHORTEST (k + 1) r environments of the longest-first order, the other warps draw
+    // their k from the longest ones: every lane then carries about the same number of ticks, and the launch ends with the short warps
+    // alone on their schedulers instead of with every warp half empty.
+    int pool = 0;
+    int64_t dyn_short = 0;
+    if (H.short_warps > 0) {
+        const int64_t gw = (int64_t)warp * gridDim.x + blockIdx.x;
+        const int64_t long_warps = (int64_t)gridDim.x * active_warps - H.short_warps;
+        if (gw < H.short_warps) { pool = 1; first_base = H.n_long + gw * 32; }
+        else first_base = (gw - H.short_warps) * 32;
+        dyn_base = min(long_warps * 32, H.n_long);
+        dyn_short = H.n_long + min((int64_t)H.short_warps * 32, n - H.n_long);
+        if (first_base >= (pool ? n : H.n_long)) first_base = n; // nothing static for this warp: it starts with the counters
+    }
     if (warp < active_warps) // SNK_EXACT_WARPS (ablation): the other warps take no environments
         run_warp<CONE, RowsH, TRACE>(P, hyb_rows(S, tbase, warp, lane), state, tgt_scratch, actions, obs, rew, done, ticks, counters, order, n, first_base,
-                                     dyn_base, tick_obs, tick_links);
+                                     dyn_base, tick_obs, tick_links, pool, H.short_warps > 0 ? H.n_long : -1, dyn_short);
     hyb_tmem_free(tbase, warp);
 }
 
@@ -633,7 +661,7 @@ __global__ void snk_exact_order_kernel(int64_t n, const uint8_t* __restrict__ bu
 #ifdef SNK_SCREEN
 // tools/screen_variants.py compiles this file with -DSNK_SCREEN: only the benchmarked kernel, for a look at its SASS
 template __global__ void snk_hyb_step_kernel<true, false>(const KParams, float*, float*, const float*, float*, float*, uint8_t*, int32_t*, unsigned long long*,
-                                                           const int32_t*, int64_t, int, int, float*, float*);
+                                                           const int32_t*, int64_t, int, int, const HandOut, float*, float*);
 #else
 // ---------------------------------------------------------------------------------------------
 // launch wrappers used by the C-ABI host code (snake_abi.cu)
@@ -648,6 +676,7 @@ static int g_rows = ROWS_HYBRID; // SNK_EXACT_ROWS = split | smem selects one of
 static bool g_no_sort = false;   // SNK_EXACT_ORDER=index disables the longest-first hand-out (ablation)
 static int g_spread = 3;         // SNK_EXACT_SPREAD: first-wave hand-out policy (see the step kernels)
 static int g_active_warps = 0;   // SNK_EXACT_WARPS=1..8 forces the number of working warps per SM (0: chosen per launch)
+static bool g_balance = true;    // SNK_EXACT_BALANCE=0 disables the two-pool (balanced) hand-out (ablation)
 
 // working warps per SM for a batch of n environments.  Hybrid rows: always 8.  Split rows: 7 (three shared-memory warps) once the
 // batch is about two waves of the 7-warp grid, else 6 -- a single wave finishes sooner with fewer warps per scheduler.
@@ -691,6 +720,8 @@ cudaError_t snk_exact_configure(const ExTables* host_tables) {
     g_no_sort = so && so[0] == 'i';
     const char* sp = getenv("SNK_EXACT_SPREAD");
     g_spread = (sp && sp[0] >= '0' && sp[0] <= '3') ? sp[0] - '0' : 3;
+    const char* bl = getenv("SNK_EXACT_BALANCE");
+    g_balance = !(bl && bl[0] == '0');
     const char* w = getenv("SNK_EXACT_WARPS");
     g_active_warps = (w && atoi(w) >= 1 && atoi(w) <= HWARPS) ? atoi(w) : 0;
     e = cudaMemcpyToSymbol(cT, host_tables, sizeof(ExTables));
@@ -750,8 +781,18 @@ cudaError_t snk_exact_launch_step(const KParams& P, float* state, float* tgt_scr
         // a small batch gets one CTA per warp of environments: all SMs before a second warp per SM
         const int64_t want = g_spread ? (n + EB - 1) / EB : (n + aw * 32 - 1) / (aw * 32);
         dim3 grid((unsigned)(want < sms ? want : sms)), block(HWARPS * 32);
-        if (P.cone) snk_hyb_step_kernel<true, false><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n, aw, g_spread, nullptr, nullptr);
-        else snk_hyb_step_kernel<false, false><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n, aw, g_spread, nullptr, nullptr);
+        HandOut H;
+        H.n_long = n; H.short_warps = 0;
+        if (use_order && g_balance && (g_spread == 1 || g_spread == 3)) { // n = k L + r: r lanes (whole warps) run k + 1 env-steps, taken from the shortest
+            const int64_t L = (int64_t)grid.x * aw * 32, k = n / L, r = n - k * L;
+            if (k >= 1 && r > 0) {
+                H.short_warps = (int)((r + 31) / 32);
+                const int64_t n_short = H.short_warps * 32LL * (k + 1);
+                H.n_long = n_short < n ? n - n_short : 0;
+            }
+        }
+        if (P.cone) snk_hyb_step_kernel<true, false><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n, aw, g_spread, H, nullptr, nullptr);
+        else snk_hyb_step_kernel<false, false><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n, aw, g_spread, H, nullptr, nullptr);
     } else if (g_rows == ROWS_SPLIT) {
         const int sw = aw > TWARPS + 2 ? 3 : 2;
         const int per_cta = (TWARPS + sw) * 32, per_cta_active = aw * 32;
@@ -776,8 +817,10 @@ cudaError_t snk_exact_launch_step_trace(const KParams& P, float* state, float* t
     const int64_t warps = (n + EB - 1) / EB;
     if (g_rows == ROWS_HYBRID) { // the benchmarked kernel's TRACE instantiation: same arithmetic, same bits as snk_step
         dim3 grid((unsigned)(warps < g_sms[dev] ? warps : g_sms[dev])), block(HWARPS * 32);
-        if (P.cone) snk_hyb_step_kernel<true, true><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, nullptr, n, HWARPS, 1, tick_obs, tick_links);
-        else snk_hyb_step_kernel<false, true><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, nullptr, n, HWARPS, 1, tick_obs, tick_links);
+        HandOut H;
+        H.n_long = n; H.short_warps = 0;
+        if (P.cone) snk_hyb_step_kernel<true, true><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, nullptr, n, HWARPS, 1, H, tick_obs, tick_links);
+        else snk_hyb_step_kernel<false, true><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, nullptr, n, HWARPS, 1, H, tick_obs, tick_links);
         return cudaGetLastError();
     }
     dim3 grid((unsigned)(warps < g_smem_ctas[dev] ? warps : g_smem_ctas[dev])), block(EB);

@@ -293,6 +293,15 @@ def test_edge_cases(torch):
     # closed handle
     with pytest.raises(RuntimeError):
         env.step(a)
+    # action / observation rows move as 16-byte vectors: a misaligned device pointer is refused instead of faulting in the kernel,
+    # a misaligned host buffer is staged
+    env = make_env(8); env.reset()
+    flat = torch.zeros(8 * 8 + 1, device="cuda")
+    with pytest.raises(RuntimeError, match="16-byte aligned"):
+        env.step(flat[1:].view(8, 8))
+    ob1, _, _, _ = env.step(np.zeros(8 * 8 + 1, np.float32)[1:].reshape(8, 8))      # numpy view at a 4-byte offset: host path stages it
+    assert np.isfinite(ob1).all()
+    env.close()
 
 
 def test_single_env_facade_and_vec_surface(torch):

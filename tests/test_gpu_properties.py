@@ -127,7 +127,7 @@ def test_warp_count_and_hand_out_policy_do_not_change_results(torch):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sums = []
     for extra in ({}, {"SNK_EXACT_WARPS": "6"}, {"SNK_EXACT_WARPS": "7"}, {"SNK_EXACT_WARPS": "4"}, {"SNK_EXACT_SPREAD": "0"}, {"SNK_EXACT_SPREAD": "2"},
-                  {"SNK_EXACT_ORDER": "index"}):
+                  {"SNK_EXACT_ORDER": "index"}, {"SNK_EXACT_BALANCE": "0"}):
         env = dict(os.environ, PYTHONPATH=root, **extra)
         out = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
         assert out.returncode == 0, out.stderr[-2000:]
