@@ -11,8 +11,6 @@
 #include <string.h>
 
 #include <new>
-#include <thread>
-#include <vector>
 
 #include "snake_host.h"
 
@@ -110,30 +108,10 @@ static cudaError_t launch_step(snk_handle* h, const float* act, float* obs, floa
     return e;
 }
 
-// host-side worker threads of the float64 entry point (SNK_HOST_THREADS, default min(hardware threads, 16))
-static int host_threads() {
-    static int v = 0;
-    if (!v) {
-        const char* e = getenv("SNK_HOST_THREADS");
-        int hw = (int)std::thread::hardware_concurrency();
-        v = e ? atoi(e) : (hw > 16 ? 16 : hw);
-        if (v < 1) v = 1;
-    }
-    return v;
-}
+#include "snake_hostpool.h"
+
 template <class F>
-static void parallel_chunks(size_t n, F f) { // f(begin, end) over [0, n) on host_threads() threads
-    const int nt = (n < (size_t)1 << 16) ? 1 : host_threads();
-    if (nt == 1) { f((size_t)0, n); return; }
-    std::vector<std::thread> th;
-    const size_t per = (n + nt - 1) / nt;
-    for (int t = 0; t < nt; t++) {
-        const size_t b = (size_t)t * per, e = b + per < n ? b + per : n;
-        if (b >= e) break;
-        th.emplace_back([=] { f(b, e); });
-    }
-    for (auto& x : th) x.join();
-}
+static void parallel_chunks(size_t n, F f) { HostPool::get().run(n, std::function<void(size_t, size_t)>(f)); }
 
 extern "C" {
 

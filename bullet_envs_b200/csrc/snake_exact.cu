@@ -785,7 +785,12 @@ cudaError_t snk_exact_launch_step(const KParams& P, float* state, float* tgt_scr
         H.n_long = n; H.short_warps = 0;
         if (use_order && g_balance && (g_spread == 1 || g_spread == 3)) { // n = k L + r: r lanes (whole warps) run k + 1 env-steps, taken from the shortest
             const int64_t L = (int64_t)grid.x * aw * 32, k = n / L, r = n - k * L;
-            if (k >= 1 && r > 0) {
+            // Worth it when plain longest-first would end on a long, thinly populated last wave: L - r idle lanes for one env-step out
+            // of n / L per lane, i.e. a loss of about (L - r) / n.  Measured on B200 (ms per step, balanced / plain): 100 000 envs
+            // 22.6 / 23.0, 131 072 29.1 / 30.2, 200 000 42.0 / 44.8, 262 144 53.3 / 53.6 -- but 524 288 109.1 / 106.6: over many waves
+            // the lanes drift away from the k / k + 1 split and the pools only disturb the longest-first order, so it is used for
+            // (L - r) / n >= 3 % only.
+            if (k >= 1 && r > 0 && 100 * (L - r) >= 3 * n) {
                 H.short_warps = (int)((r + 31) / 32);
                 const int64_t n_short = H.short_warps * 32LL * (k + 1);
                 H.n_long = n_short < n ? n - n_short : 0;
