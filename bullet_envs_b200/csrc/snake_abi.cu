@@ -82,12 +82,19 @@ struct snk_handle {
     uint8_t *d_done, *d_mask;
     int32_t* d_ticks;
     bool staged;
+    cudaEvent_t ev_chunk[16];     // one per chunk of the pipelined float64 host path
+    int n_ev_chunk;
 };
 
 // Ordering between the caller's streams (device-path entry points, asynchronous) and the handle's own stream (host-path entry
 // points, synchronous): a device-path call records ev_dev behind its work, a host-path call waits for it before touching the state.
 static void mark_device_work(snk_handle* h, cudaStream_t st) {
     if (st == h->hstream && h->hstream) return;
+    // a caller capturing its stream into a CUDA graph (the device-path entry points are capturable: no allocation, no synchronisation):
+    // an event recorded inside a capture cannot be waited for outside of it, so nothing is recorded -- after replaying such a graph
+    // the caller synchronises before mixing in *_host calls
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) return;
     if (!h->ev_valid) { if (cudaEventCreateWithFlags(&h->ev_dev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return; } h->ev_valid = true; }
     cudaEventRecord(h->ev_dev, st);
 }
@@ -99,10 +106,15 @@ static void wait_device_work(snk_handle* h) {
 // base pointer makes every row aligned): a misaligned pointer would fault inside the kernel and poison the context
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
-static cudaError_t launch_step(snk_handle* h, const float* act, float* obs, float* rew, uint8_t* done, int32_t* ticks, cudaStream_t st) {
+// One env-step of the environments [off, off + cnt) (default: all).  act / obs / rew / done / ticks point at the rows of environment
+// `off`.  The per-launch scheduler words of `counters` must be zero; the statistics words [0..3] accumulate.
+static cudaError_t launch_step(snk_handle* h, const float* act, float* obs, float* rew, uint8_t* done, int32_t* ticks, cudaStream_t st, int64_t off = 0,
+                               int64_t cnt = -1) {
+    if (cnt < 0) cnt = h->n;
     int launches = 1;
-    cudaError_t e = h->exact ? snk_exact_launch_step(h->P, h->state, h->tgt, act, obs, rew, done, ticks, h->counters, h->bucket, h->order, h->n, st, &launches)
-                             : snk_pgs_launch_step(h->T, h->P, h->state, act, obs, rew, done, ticks, h->counters, h->n, st);
+    cudaError_t e = h->exact ? snk_exact_launch_step(h->P, h->state + off * SNK_STATE_STRIDE, h->tgt + off * NJ, act, obs, rew, done, ticks, h->counters,
+                                                     h->bucket + off, h->order + off, cnt, st, &launches)
+                             : snk_pgs_launch_step(h->T, h->P, h->state + off * SNK_STATE_STRIDE, act, obs, rew, done, ticks, h->counters, cnt, st);
     h->launches += launches;
     mark_device_work(h, st);
     return e;
@@ -209,6 +221,7 @@ int snk_destroy(snk_handle* h) {
         cudaStreamDestroy(h->hstream);
     }
     if (h->ev_valid) cudaEventDestroy(h->ev_dev);
+    for (int c = 0; c < h->n_ev_chunk; c++) cudaEventDestroy(h->ev_chunk[c]);
     if (h->exact) snk_exact_release();
     cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters); cudaFree(h->bucket); cudaFree(h->order); cudaFree(h->roll_queue); cudaFree(h->tgt);
     delete h;
@@ -404,28 +417,55 @@ int snk_step_host_f64(snk_handle* h, const double* actions_host, double* obs_hos
     int rc = ensure_staging(h);
     if (rc) return rc;
     wait_device_work(h);
-    const size_t n = (size_t)h->n, na = n * h->P.actdim;
-    float* ha = h->h_act;
-    parallel_chunks(na, [=](size_t b, size_t e) { for (size_t i = b; i < e; i++) ha[i] = (float)actions_host[i]; });
+    const size_t n = (size_t)h->n, ad = (size_t)h->P.actdim;
     cudaStream_t st = h->hstream;
+    // The batch goes through in a few chunks of environments, pipelined: while the GPU steps chunk c the host threads narrow the
+    // actions of chunk c + 1, and while it steps chunk c + 1 they widen the results of chunk c into the caller's arrays -- only the
+    // first narrowing and the last widening are not hidden behind the kernel (SNK_HOST_CHUNKS, default 4 from 2^18 environments).
+    static int cfg_chunks = -1;
+    if (cfg_chunks < 0) { const char* e = getenv("SNK_HOST_CHUNKS"); cfg_chunks = (e && atoi(e) >= 1 && atoi(e) <= 16) ? atoi(e) : 4; }
+    const int chunks = (n >= ((size_t)1 << 18)) ? cfg_chunks : 1;
+    if (h->n_ev_chunk < chunks) {
+        for (int c = h->n_ev_chunk; c < chunks; c++) CU(cudaEventCreateWithFlags(&h->ev_chunk[c], cudaEventDisableTiming));
+        h->n_ev_chunk = chunks;
+    }
+    const bool zc = zero_copy_enabled();
     CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
-    if (zero_copy_enabled()) {
-        CU(launch_step(h, h->h_act, h->h_obs, h->h_rew, h->h_done, h->h_ticks, st)); // cudaMallocHost memory is mapped (UVA)
-    } else {
-        CU(cudaMemcpyAsync(h->d_act, h->h_act, na * sizeof(float), cudaMemcpyHostToDevice, st));
-        CU(launch_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_ticks, st));
-        CU(cudaMemcpyAsync(h->h_obs, h->d_obs, n * SNK_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h->h_rew, h->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h->h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h->h_ticks, h->d_ticks, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    size_t lo[17]; // chunk boundaries, multiples of 32 environments (row pointers stay 16-byte aligned)
+    for (int c = 0; c <= chunks; c++) {
+        size_t x = (n * (size_t)c / (size_t)chunks + 31) / 32 * 32;
+        lo[c] = (c == chunks || x > n) ? n : x;
+    }
+    for (int c = 0; c < chunks; c++) {
+        const size_t b = lo[c], e = lo[c + 1];
+        if (e <= b) { CU(cudaEventRecord(h->ev_chunk[c], st)); continue; }
+        float* ha = h->h_act;
+        parallel_chunks((e - b) * ad, [=](size_t i0, size_t i1) { for (size_t i = b * ad + i0; i < b * ad + i1; i++) ha[i] = (float)actions_host[i]; });
+        if (c > 0) CU(cudaMemsetAsync(h->counters + 4, 0, (NCOUNTERS - 4) * sizeof(unsigned long long), st)); // the hand-out words are per launch
+        if (zc) {
+            CU(launch_step(h, h->h_act + b * ad, h->h_obs + b * SNK_OBS_DIM, h->h_rew + b, h->h_done + b, h->h_ticks + b, st, (int64_t)b, (int64_t)(e - b)));
+        } else {
+            CU(cudaMemcpyAsync(h->d_act + b * ad, h->h_act + b * ad, (e - b) * ad * sizeof(float), cudaMemcpyHostToDevice, st));
+            CU(launch_step(h, h->d_act + b * ad, h->d_obs + b * SNK_OBS_DIM, h->d_rew + b, h->d_done + b, h->d_ticks + b, st, (int64_t)b, (int64_t)(e - b)));
+            CU(cudaMemcpyAsync(h->h_obs + b * SNK_OBS_DIM, h->d_obs + b * SNK_OBS_DIM, (e - b) * SNK_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h->h_rew + b, h->d_rew + b, (e - b) * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h->h_done + b, h->d_done + b, e - b, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h->h_ticks + b, h->d_ticks + b, (e - b) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        }
+        CU(cudaEventRecord(h->ev_chunk[c], st));
+    }
+    for (int c = 0; c < chunks; c++) {
+        const size_t b = lo[c], e = lo[c + 1];
+        CU(cudaEventSynchronize(h->ev_chunk[c]));
+        if (e <= b) continue;
+        const float* ho = h->h_obs;
+        parallel_chunks((e - b) * SNK_OBS_DIM, [=](size_t i0, size_t i1) { for (size_t i = b * SNK_OBS_DIM + i0; i < b * SNK_OBS_DIM + i1; i++) obs_host[i] = (double)ho[i]; });
+        const float* hr = h->h_rew;
+        parallel_chunks(e - b, [=](size_t i0, size_t i1) { for (size_t i = b + i0; i < b + i1; i++) rew_host[i] = (double)hr[i]; });
+        memcpy(done_host + b, h->h_done + b, e - b);
+        if (ticks_host) memcpy(ticks_host + b, h->h_ticks + b, (e - b) * sizeof(int32_t));
     }
     CU(cudaStreamSynchronize(st));
-    const float* ho = h->h_obs;
-    parallel_chunks(n * SNK_OBS_DIM, [=](size_t b, size_t e) { for (size_t i = b; i < e; i++) obs_host[i] = (double)ho[i]; });
-    const float* hr = h->h_rew;
-    parallel_chunks(n, [=](size_t b, size_t e) { for (size_t i = b; i < e; i++) rew_host[i] = (double)hr[i]; });
-    memcpy(done_host, h->h_done, n);
-    if (ticks_host) memcpy(ticks_host, h->h_ticks, n * sizeof(int32_t));
     return 0;
 }
 

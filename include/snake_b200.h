@@ -15,7 +15,9 @@
  *     (torch allocates them); pointers named *_host are host pointers.  The handle owns only
  *     its internal state array and constant tables.  snk_step() allocates nothing.
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all work is
- *     enqueued on it, no hidden synchronisation except in the *_host entry points.
+ *     enqueued on it, no hidden synchronisation except in the *_host entry points.  snk_step, snk_reset, snk_tick and snk_gae
+ *     allocate nothing and never synchronise, so they may be captured into a CUDA graph (synchronise after replaying such a
+ *     graph before calling a *_host entry point on the same handle).
  *   - layouts are row-major fp32: actions [N, act_dim], obs [N, 56], reward [N], done [N] u8.
  *   - actions, obs and weights pointers must be 16-byte aligned (rows move as 16-byte vectors); anything a device or
  *     pinned allocator returns is.  A misaligned pointer is refused with SNK_E_ARG (snk_step_host stages it instead).

@@ -45,7 +45,7 @@ def ppo(args):
     assert sum(p.numel() for p in net.parameters()) == 165137
     n, T = args.envs, 20  # ppo/params.py:10
     env = SnakeVecEnv(num_envs=n, device=0)
-    from bullet_envs_b200.rollout import RolloutBuffer, compute_gae
+    from bullet_envs_b200.rollout import RolloutBuffer
     buf = RolloutBuffer(T, n, device=dev)
     rew, done = buf.rewards, buf.dones
 
@@ -64,14 +64,49 @@ def ppo(args):
     buf.obs[0] = env.reset(as_torch=True)
     rollout()  # warm-up
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.rollouts):
-        rollout()
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    print(json.dumps({"workload": "PPO rollout collection + GAE, ppo/train.py policy in torch, device-resident RolloutBuffer", "envs": n, "num_steps": T, "rollouts": args.rollouts,
-                      "env_steps_per_s": n * T * args.rollouts / (ms * 1e-3), "ms_per_rollout": ms / args.rollouts,
+    mode = "eager"
+    run = rollout
+    if args.graph:
+        # the whole rollout -- 20 x (policy forward + sample + env-step kernel) + GAE -- captured once as a CUDA graph and replayed:
+        # the ~25 small launches per step of the eager policy become one graph launch per rollout
+        mode = "cuda graph"
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            rollout()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            rollout()
+        run = g.replay
+        run(); torch.cuda.synchronize()
+
+    def timed(fn, reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms = timed(run, args.rollouts)
+    # breakdown (eager): the env-steps alone on the actions of the last rollout, and the policy alone
+    def env_only():
+        for t in range(T):
+            env.step(buf.actions[t], out=buf.out(t))
+
+    def policy_only():
+        with torch.no_grad():
+            for t in range(T):
+                dist, v = net(buf.obs[t]); a = dist.sample(); buf.log_probs[t] = dist.log_prob(a); buf.values[t] = v.squeeze(-1)
+            _, nv = net(buf.obs[T]); buf.gae(nv.squeeze(-1))
+
+    ms_env = timed(env_only, 2); ms_pol = timed(policy_only, 2)
+    print(json.dumps({"workload": "PPO rollout collection + GAE (snk_gae), ppo/train.py policy in torch, device-resident RolloutBuffer, " + mode, "envs": n, "num_steps": T,
+                      "rollouts": args.rollouts, "env_steps_per_s": n * T / (ms * 1e-3), "ms_per_rollout": ms,
+                      "ms_env_steps_only": ms_env, "env_steps_per_s_env_only": n * T / (ms_env * 1e-3), "ms_policy_and_gae_only": ms_pol,
+                      "ratio_to_env_only": ms_env / ms,
                       "mean_reward": float(rew.mean()), "done_rate": float(done.float().mean()), "n_gpus": 1}))
 
 
@@ -169,5 +204,6 @@ if __name__ == "__main__":
     ap.add_argument("--envs-per-gpu", type=int, default=32768)
     ap.add_argument("--rollouts", type=int, default=3)
     ap.add_argument("--fused", action="store_true", help="ars: run every rollout as one snk_rollout_linear launch")
+    ap.add_argument("--graph", action="store_true", help="ppo: capture the whole rollout as one CUDA graph")
     a = ap.parse_args()
     {"ppo": ppo, "ars": ars}[a.workload](a)
