@@ -25,6 +25,10 @@ def ppo(args):
 
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
+    # Normal(mu, sigma) validates its arguments with a device->host synchronisation on every construction (torch._is_all_true): with
+    # it the CPU stalls behind every env-step and the ~25 small launches of the policy are exposed; switched off (one line in the
+    # caller, ppo/model.py:40-45), the launches run ahead of the GPU and the rollout can be captured as a CUDA graph
+    torch.distributions.Distribution.set_default_validate_args(not args.no_validate)
 
     class ActorCritic(nn.Module):
         def __init__(self, ni=56, no=8, hs=(256, 256)):
@@ -70,6 +74,7 @@ def ppo(args):
         # the whole rollout -- 20 x (policy forward + sample + env-step kernel) + GAE -- captured once as a CUDA graph and replayed:
         # the ~25 small launches per step of the eager policy become one graph launch per rollout
         mode = "cuda graph"
+        torch.distributions.Distribution.set_default_validate_args(False)
         g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -205,5 +210,6 @@ if __name__ == "__main__":
     ap.add_argument("--rollouts", type=int, default=3)
     ap.add_argument("--fused", action="store_true", help="ars: run every rollout as one snk_rollout_linear launch")
     ap.add_argument("--graph", action="store_true", help="ppo: capture the whole rollout as one CUDA graph")
+    ap.add_argument("--no-validate", action="store_true", help="ppo: torch.distributions argument validation off (no per-step synchronisation)")
     a = ap.parse_args()
     {"ppo": ppo, "ars": ars}[a.workload](a)
