@@ -28,7 +28,8 @@ def ppo(args):
     # Normal(mu, sigma) validates its arguments with a device->host synchronisation on every construction (torch._is_all_true): with
     # it the CPU stalls behind every env-step and the ~25 small launches of the policy are exposed; switched off (one line in the
     # caller, ppo/model.py:40-45), the launches run ahead of the GPU and the rollout can be captured as a CUDA graph
-    torch.distributions.Distribution.set_default_validate_args(not args.no_validate)
+    fast = args.no_validate or args.graph
+    torch.distributions.Distribution.set_default_validate_args(not fast)
 
     class ActorCritic(nn.Module):
         def __init__(self, ni=56, no=8, hs=(256, 256)):
@@ -57,7 +58,9 @@ def ppo(args):
         with torch.no_grad():
             for t in range(T):
                 dist, v = net(buf.obs[t])
-                a = dist.sample()
+                # dist.sample() is torch.normal(mean, std), which checks std >= 0 with another device->host synchronisation;
+                # rsample() (mean + std * randn) draws from the same law without one
+                a = dist.rsample() if fast else dist.sample()
                 buf.actions[t] = a; buf.log_probs[t] = dist.log_prob(a); buf.values[t] = v.squeeze(-1)
                 env.step(a, out=buf.out(t))                      # the kernel writes obs[t+1], rewards[t], dones[t] in place
             _, next_value = net(buf.obs[T])
@@ -74,7 +77,6 @@ def ppo(args):
         # the whole rollout -- 20 x (policy forward + sample + env-step kernel) + GAE -- captured once as a CUDA graph and replayed:
         # the ~25 small launches per step of the eager policy become one graph launch per rollout
         mode = "cuda graph"
-        torch.distributions.Distribution.set_default_validate_args(False)
         g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -104,11 +106,11 @@ def ppo(args):
     def policy_only():
         with torch.no_grad():
             for t in range(T):
-                dist, v = net(buf.obs[t]); a = dist.sample(); buf.log_probs[t] = dist.log_prob(a); buf.values[t] = v.squeeze(-1)
+                dist, v = net(buf.obs[t]); a = dist.rsample() if fast else dist.sample(); buf.log_probs[t] = dist.log_prob(a); buf.values[t] = v.squeeze(-1)
             _, nv = net(buf.obs[T]); buf.gae(nv.squeeze(-1))
 
     ms_env = timed(env_only, 2); ms_pol = timed(policy_only, 2)
-    print(json.dumps({"workload": "PPO rollout collection + GAE (snk_gae), ppo/train.py policy in torch, device-resident RolloutBuffer, " + mode, "envs": n, "num_steps": T,
+    print(json.dumps({"workload": "PPO rollout collection + GAE (snk_gae), ppo/train.py policy in torch, device-resident RolloutBuffer, " + mode + (", no synchronising argument checks in the policy" if fast else ""), "envs": n, "num_steps": T,
                       "rollouts": args.rollouts, "env_steps_per_s": n * T / (ms * 1e-3), "ms_per_rollout": ms,
                       "ms_env_steps_only": ms_env, "env_steps_per_s_env_only": n * T / (ms_env * 1e-3), "ms_policy_and_gae_only": ms_pol,
                       "ratio_to_env_only": ms_env / ms,

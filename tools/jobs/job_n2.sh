@@ -1,0 +1,11 @@
+#!/bin/bash
+# 2-GPU job: W-invariance over NCCL, gloo host-logic check on GPUs, bench at N=2 (collective block + config 4)
+timeout 600 python -m pytest tests/test_gpu_world_invariance.py -m gpu -q -p no:cacheprovider 2>&1 | tail -3
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/b_n2.log 2> gpurun_out/b_n2.err
+python - <<'P'
+import json
+d=json.loads(open('gpurun_out/b_n2.log').read().strip().splitlines()[-1])
+print('N=2', round(d['value']), d['ms_per_step'], 'e2e', round(d['e2e']['value']), round(d['e2e']['value_pinned_f32']))
+print(d.get('collective')); print(d.get('config4_ars_sweep'))
+P
+tail -3 gpurun_out/b_n2.err
