@@ -29,6 +29,8 @@ def ppo(args):
     # it the CPU stalls behind every env-step and the ~25 small launches of the policy are exposed; switched off (one line in the
     # caller, ppo/model.py:40-45), the launches run ahead of the GPU and the rollout can be captured as a CUDA graph
     fast = args.no_validate or args.graph
+    if args.tf32:  # the caller's choice of matmul precision for its policy (PyTorch default is full fp32)
+        torch.backends.cuda.matmul.allow_tf32 = True
     torch.distributions.Distribution.set_default_validate_args(not fast)
 
     class ActorCritic(nn.Module):
@@ -110,7 +112,7 @@ def ppo(args):
             _, nv = net(buf.obs[T]); buf.gae(nv.squeeze(-1))
 
     ms_env = timed(env_only, 2); ms_pol = timed(policy_only, 2)
-    print(json.dumps({"workload": "PPO rollout collection + GAE (snk_gae), ppo/train.py policy in torch, device-resident RolloutBuffer, " + mode + (", no synchronising argument checks in the policy" if fast else ""), "envs": n, "num_steps": T,
+    print(json.dumps({"workload": "PPO rollout collection + GAE (snk_gae), ppo/train.py policy in torch, device-resident RolloutBuffer, " + mode + (", no synchronising argument checks in the policy" if fast else "") + (", tf32 matmul" if args.tf32 else ""), "envs": n, "num_steps": T,
                       "rollouts": args.rollouts, "env_steps_per_s": n * T / (ms * 1e-3), "ms_per_rollout": ms,
                       "ms_env_steps_only": ms_env, "env_steps_per_s_env_only": n * T / (ms_env * 1e-3), "ms_policy_and_gae_only": ms_pol,
                       "ratio_to_env_only": ms_env / ms,
@@ -212,6 +214,7 @@ if __name__ == "__main__":
     ap.add_argument("--rollouts", type=int, default=3)
     ap.add_argument("--fused", action="store_true", help="ars: run every rollout as one snk_rollout_linear launch")
     ap.add_argument("--graph", action="store_true", help="ppo: capture the whole rollout as one CUDA graph")
+    ap.add_argument("--tf32", action="store_true", help="ppo: TF32 tensor-core matmuls in the policy")
     ap.add_argument("--no-validate", action="store_true", help="ppo: torch.distributions argument validation off (no per-step synchronisation)")
     a = ap.parse_args()
     {"ppo": ppo, "ars": ars}[a.workload](a)
