@@ -236,7 +236,8 @@ __device__ __forceinline__ void run_rollout_warp(const KParams& P, Rows R, float
                                                  unsigned long long* __restrict__ counters, int64_t n, int64_t first_base, int64_t dyn_base) {
     const int lane = R.lane;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const long long total = (long long)n * A.n_steps;
+    const bool sticky = n <= (int64_t)gridDim.x * (int64_t)blockDim.x; // as many lanes as environments: no ready queue needed
+    const long long total = sticky ? (long long)n : (long long)n * A.n_steps; // tickets that will ever be served
     ExEnv e;
     e.st = state;
     e.tid = lane;
@@ -297,12 +298,20 @@ __device__ __forceinline__ void run_rollout_warp(const KParams& P, Rows R, float
             A.returns[env] = (t == 0) ? o.rew : A.returns[env] + o.rew;
             c_ticks += (unsigned long long)o.ticks; c_iters += (unsigned long long)o.iters; c_done += o.done; c_bad += o.bad;
             A.done_steps[env] = t + 1;
-            if (t + 1 < A.n_steps) {
-                __threadfence(); // release the record before the environment becomes visible to other lanes
-                const unsigned long long p = atomicAdd(&counters[5], 1ull);
-                *reinterpret_cast<volatile int32_t*>(A.queue + p) = (int32_t)env;
+            if (t + 1 < A.n_steps && sticky) {
+                // every environment has a lane of its own (n <= lanes of the grid): the lane keeps it for the whole rollout -- no
+                // hand-over latency, and its state record and weight rows stay in this SM's caches
+                t = t + 1;
+                policy_targets(P, R, e, A, env, n, t);
+                ex_step_begin(P, R, e, &run);
+            } else {
+                if (t + 1 < A.n_steps) {
+                    __threadfence(); // release the record before the environment becomes visible to other lanes
+                    const unsigned long long p = atomicAdd(&counters[5], 1ull);
+                    *reinterpret_cast<volatile int32_t*>(A.queue + p) = (int32_t)env;
+                }
+                have = false;
             }
-            have = false;
         }
         __syncwarp();
     }
