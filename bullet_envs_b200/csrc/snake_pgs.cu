@@ -14,14 +14,21 @@
 //   articulated inertias (backward pass)        : lane = element of the 6x6 matrices, 4 stages/joint
 //   constraint rows (J, M^-1 J^T, rhs)          : lane = collision cylinder (32 cylinders = 32 lanes);
 //       lanes 0..15 additionally own one motor row; each lane runs the O(n) impulse response of its rows
-//   projected Gauss-Seidel                      : lane = generalized-velocity DoF (22 of 32 lanes);
-//       J.dv by xor-shuffle butterfly, impulses kept in the owning lane's registers
+//   projected Gauss-Seidel                      : BLOCK form with exact in-block coupling (same iterates as the row-by-row
+//       sweep, see pgs_* below): lane = row of the current block of <= 32 rows (16 motor rows | 32 normal rows | 2 x 16 friction
+//       pairs); J.dv of all rows of the block at once (lane = row, no reduction), the rows then follow each other through the
+//       block's Delassus entries A = J M^-1 J^T (one broadcast shuffle per row on the serial chain instead of a five-level
+//       butterfly), the velocity update of the whole block at the end (lane = DoF)
 //
 // Reference call sites replaced: SnakeGymEnv.py:33-50,82-103; snake.py:209-306,336-341;
 // ppo/multiprocessing_env.py:11-16; physics per SURVEY.md Appendix A (see oracle/snake_oracle.c,
 // whose row order, clamping and residual rule this kernel reproduces).
 #include "snake_dev.cuh"
-#define WARPS_PER_CTA 4
+#define WARPS_PER_CTA 2
+#define CTAS_PER_SM 3
+#define JS 23
+#define APACK (1 + NC * (NC - 1) / 2 + 3)
+#define A_OFF(i) ((i) * NC - ((i) * ((i) + 1)) / 2)
 
 struct WarpMemPgs {
     float s[SNK_STATE_STRIDE];
@@ -43,11 +50,17 @@ struct WarpMemPgs {
     float nu[ND];
     float nuF[ND];
     float target[NJ];
-    float J[3 * NC][ND];
+    float J[3 * NC][JS];   // rows padded to JS words: lane = row reads are bank-conflict free
     float B[NROW][ND];
     float rhs[NROW];
     float invD[NROW];
     float Dg[NROW];
+    float dvs[32];         // the solver's velocity change (lane = DoF keeps it in a register; this is the copy the rows read)
+    float dl[32];          // impulse changes of the block just solved (lane = row), read by the velocity update
+    // in-block Delassus entries, packed upper triangles: entry (i, j > i) = J_j . B_i at A_OFF(i) + j - i (one pad word in front, so
+    // that the finished lanes j <= i of a step read inside the array); the motor block needs none (J = unit vector: B itself)
+    float An[APACK];
+    float Af[2][APACK];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -357,7 +370,7 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
     __syncwarp();
 
     // ---- constraint rows ----
-    float lam_m = 0.f, lam_n = 0.f, lam_a = 0.f, lam_b = 0.f; // impulses owned by this lane
+    float lam_m = 0.f, lam_n = 0.f; // motor / normal impulses owned by this lane (motor row = joint, normal row = cylinder)
     if (lane < NJ) { // motor row of joint lane+1 (A.4)
         const int j = lane;
         const float zero6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -389,6 +402,15 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
 #pragma unroll
         for (int k = 0; k < 9; k++) cfr[k] = __ldg(&T->cfr[c][k]);
         m3m3(W.Rw[b], cfr, Rl);
+        if (!active) { // a separated contact: all-zero rows are no-ops of the block solver below
+#pragma unroll 1
+            for (int f = 0; f < 3; f++) {
+                const int r = (f == 0) ? c : NC + 2 * c + (f - 1);
+#pragma unroll 1
+                for (int k = 0; k < ND; k++) { W.J[r][k] = 0.f; W.B[NJ + r][k] = 0.f; }
+                W.Dg[NJ + r] = 0.f; W.invD[NJ + r] = 0.f; W.rhs[NJ + r] = 0.f;
+            }
+        }
 #pragma unroll 1
         for (int f = 0; f < 3; f++) {
             if (!active) break;
@@ -438,68 +460,177 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
             W.Dg[NJ + r] = D; W.invD[NJ + r] = iD; W.rhs[NJ + r] = rh;
         }
     }
-    const unsigned act = __ballot_sync(FULL, active);
     __syncwarp();
 
-    // ---- projected Gauss-Seidel, lane = DoF ----
+    // ---- in-block Delassus entries A(i, j) = J_j . B_i for the rows j > i of the same block (lane = row j) ----
+    {
+        float Jr[ND];
+#pragma unroll
+        for (int k = 0; k < ND; k++) Jr[k] = W.J[lane][k];
+#pragma unroll 1
+        for (int i = 0; i < NC - 1; i++) {
+            const float* Bi = W.B[NJ + i];
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < ND; k += 2) { a0 = fmaf(Jr[k], Bi[k], a0); a1 = fmaf(Jr[k + 1], Bi[k + 1], a1); }
+            if (lane > i) W.An[A_OFF(i) + lane - i] = a0 + a1;
+        }
+#pragma unroll 1
+        for (int fb = 0; fb < 2; fb++) {
+#pragma unroll
+            for (int k = 0; k < ND; k++) Jr[k] = W.J[NC + 32 * fb + lane][k];
+#pragma unroll 1
+            for (int i = 0; i < NC - 1; i++) {
+                const float* Bi = W.B[NJ + NC + 32 * fb + i];
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int k = 0; k < ND; k += 2) { a0 = fmaf(Jr[k], Bi[k], a0); a1 = fmaf(Jr[k + 1], Bi[k + 1], a1); }
+                if (lane > i) W.Af[fb][A_OFF(i) + lane - i] = a0 + a1;
+            }
+        }
+    }
+
+    // ---- projected Gauss-Seidel in BLOCK form ----
+    // The sweep visits the rows in Bullet's order (motor rows, normal rows, friction pairs: oracle tick()), and every row sees the
+    // impulses of all rows before it -- but the rows of a block of <= 32 are handled together: (1) w = J dv for every row of the
+    // block at once, lane = row; (2) the rows in order: the lane of row i turns its w into the impulse change d_i, one shuffle
+    // broadcasts it, and the later rows j of the block add A(i, j) d_i to their w (what the velocity update of row i would have
+    // done to J_j dv); (3) dv += sum_i B_i d_i for the whole block, lane = DoF.  The serial chain per row is clamp + shuffle + fma
+    // instead of a shared-memory load, a five-level shuffle butterfly and the clamp; everything on it is branch free (a
+    // data-dependent branch would split the warp in front of the next shuffle).
     const bool dof = lane < ND;
     const int ld = dof ? lane : 0;
+    const int lm = lane & (NJ - 1);
     float dv = 0.f;
+    float lam_fa[2] = {0.f, 0.f}, lam_fb[2] = {0.f, 0.f}; // friction impulses of contact 16 fb + lane / 2 (both lanes of the pair hold both)
+    W.dvs[lane] = 0.f;
+    const float m_rhs = W.rhs[lm], m_iD = W.invD[lm], m_Dg = W.Dg[lm];
+    const float n_rhs = W.rhs[NJ + lane], n_iD = W.invD[NJ + lane], n_Dg = W.Dg[NJ + lane];
+    const int pa = lane & ~1; // the lane pair (pa, pa + 1) holds the two friction rows of one contact
+    float fa_rhs[2], fa_iD[2], fa_Dg[2], fb_rhs[2], fb_iD[2], fb_Dg[2];
+#pragma unroll
+    for (int fb = 0; fb < 2; fb++) {
+        const int r = NJ + NC + 32 * fb + pa;
+        fa_rhs[fb] = W.rhs[r]; fa_iD[fb] = W.invD[r]; fa_Dg[fb] = W.Dg[r];
+        fb_rhs[fb] = W.rhs[r + 1]; fb_iD[fb] = W.invD[r + 1]; fb_Dg[fb] = W.Dg[r + 1];
+    }
+    const float maximp = P.maximp, mu = P.mu;
+    const bool cone = P.cone != 0;
+    __syncwarp();
     int it = 0;
 #pragma unroll 1
     for (;; it++) {
         float res = 0.f;
-#pragma unroll 1
-        for (int jj = 0; jj < NJ; jj++) {
-            const int j = (P.altmotor && !(it & 1)) ? NJ - 1 - jj : jj;
-            float dvj = __shfl_sync(FULL, dv, 6 + j);
-            float lj = __shfl_sync(FULL, lam_m, j);
-            float d = W.rhs[j] - dvj * W.invD[j];
-            float sum = lj + d;
-            if (sum < -P.maximp) { d = -P.maximp - lj; sum = -P.maximp; }
-            else if (sum > P.maximp) { d = P.maximp - lj; sum = P.maximp; }
-            if (lane == j) lam_m = sum;
-            if (dof) dv += W.B[j][ld] * d;
-            float rr = d * W.Dg[j];
-            res = fmaxf(res, rr * rr);
-        }
-#pragma unroll 1
-        for (int c = 0; c < NC; c++) {
-            if (!((act >> c) & 1u)) continue;
-            const int r = NJ + c;
-            float jd = warp_sum(dof ? W.J[c][ld] * dv : 0.f);
-            float lc = __shfl_sync(FULL, lam_n, c);
-            float d = W.rhs[r] - jd * W.invD[r];
-            float sum = lc + d;
-            if (sum < 0.f) { d = -lc; sum = 0.f; }
-            if (lane == c) lam_n = sum;
-            if (dof) dv += W.B[r][ld] * d;
-            float rr = d * W.Dg[r];
-            res = fmaxf(res, rr * rr);
-        }
-#pragma unroll 1
-        for (int c = 0; c < NC; c++) {
-            if (!((act >> c) & 1u)) continue;
-            const int ja = NC + 2 * c, ra = NJ + ja, rb = ra + 1;
-            float xa = dof ? W.J[ja][ld] * dv : 0.f, xb = dof ? W.J[ja + 1][ld] * dv : 0.f;
+        {   // ---- motor rows (J = unit vector of joint j: w = dv[6 + j], A(i, j) = B_i[6 + j]) ----
+            const bool rev = P.altmotor && !(it & 1);
+            float w = W.dvs[6 + lm], lam = lam_m, dmine = 0.f;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { xa += __shfl_xor_sync(FULL, xa, o); xb += __shfl_xor_sync(FULL, xb, o); }
-            float lim = P.mu * __shfl_sync(FULL, lam_n, c);
-            float la = __shfl_sync(FULL, lam_a, c), lb = __shfl_sync(FULL, lam_b, c);
-            float sa = la + (W.rhs[ra] - xa * W.invD[ra]), sb = lb + (W.rhs[rb] - xb * W.invD[rb]);
-            if (P.cone) {
-                float n2 = sa * sa + sb * sb;
-                if (n2 > lim * lim) { float sc = lim * (1.f / sqrtf(n2)); sa *= sc; sb *= sc; }
-            } else {
-                sa = fminf(fmaxf(sa, -lim), lim);
-                sb = fminf(fmaxf(sb, -lim), lim);
+            for (int s = 0; s < NJ; s++) {
+                const int i = rev ? NJ - 1 - s : s;
+                const float d0 = m_rhs - w * m_iD;
+                const float sum0 = lam + d0;
+                const bool lo = sum0 < -maximp, hi = sum0 > maximp; // both false for a NaN: it passes through, as in the oracle
+                const float sum = lo ? -maximp : (hi ? maximp : sum0);
+                const float d = lo ? (-maximp - lam) : (hi ? (maximp - lam) : d0);
+                const float di = __shfl_sync(FULL, d, i);
+                const bool mine = lane == i;
+                lam = mine ? sum : lam; dmine = mine ? d : dmine;
+                w = fmaf(W.B[i][6 + lm], di, w);
             }
-            float da = sa - la, db = sb - lb;
-            if (lane == c) { lam_a = sa; lam_b = sb; }
-            if (dof) dv += W.B[ra][ld] * da + W.B[rb][ld] * db;
-            float rr = da * W.Dg[ra] + db * W.Dg[rb];
+            lam_m = lam;
+            W.dl[lane] = dmine;
+            __syncwarp();
+            if (dof) {
+#pragma unroll
+                for (int i = 0; i < NJ; i++) dv = fmaf(W.B[i][ld], W.dl[i], dv);
+                W.dvs[lane] = dv;
+            }
+            const float rr = dmine * m_Dg;
             res = fmaxf(res, rr * rr);
+            __syncwarp();
         }
+        {   // ---- normal rows, lane = contact ----
+            float w0 = 0.f, w1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < ND; k += 2) { w0 = fmaf(W.J[lane][k], W.dvs[k], w0); w1 = fmaf(W.J[lane][k + 1], W.dvs[k + 1], w1); }
+            float w = w0 + w1, lam = lam_n, dmine = 0.f;
+#pragma unroll
+            for (int i = 0; i < NC; i++) {
+                const float d0 = n_rhs - w * n_iD;
+                const float sum0 = lam + d0;
+                const bool neg = sum0 < 0.f;
+                const float sum = neg ? 0.f : sum0, d = neg ? -lam : d0;
+                const float di = __shfl_sync(FULL, d, i);
+                const bool mine = lane == i;
+                lam = mine ? sum : lam; dmine = mine ? d : dmine;
+                if (i < NC - 1) w = fmaf(W.An[A_OFF(i) + lane - i], di, w);
+            }
+            lam_n = lam;
+            W.dl[lane] = dmine;
+            __syncwarp();
+            if (dof) {
+                float x0 = 0.f, x1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < NC; i += 2) { x0 = fmaf(W.B[NJ + i][ld], W.dl[i], x0); x1 = fmaf(W.B[NJ + i + 1][ld], W.dl[i + 1], x1); }
+                dv += x0 + x1;
+                W.dvs[lane] = dv;
+            }
+            const float rr = dmine * n_Dg;
+            res = fmaxf(res, rr * rr);
+            __syncwarp();
+        }
+#pragma unroll
+        for (int fb = 0; fb < 2; fb++) { // ---- friction pairs of contacts 16 fb .. 16 fb + 15 ----
+            // lanes 2p and 2p + 1 both carry BOTH rows of contact 16 fb + p (w_a, w_b and the two impulses), so the cone projection
+            // needs no exchange between lanes: the only shuffles on the chain broadcast the pair's (da, db)
+            const float* Ja = W.J[NC + 32 * fb + pa];
+            const float* Jb = W.J[NC + 32 * fb + pa + 1];
+            float wa = 0.f, wb = 0.f;
+#pragma unroll
+            for (int k = 0; k < ND; k++) { const float x = W.dvs[k]; wa = fmaf(Ja[k], x, wa); wb = fmaf(Jb[k], x, wb); }
+            float la = lam_fa[fb], lb = lam_fb[fb], da_mine = 0.f, db_mine = 0.f;
+            const float lim = mu * __shfl_sync(FULL, lam_n, 16 * fb + (lane >> 1));
+            const float* Af = W.Af[fb];
+            const float a_rhs = fa_rhs[fb], a_iD = fa_iD[fb], b_rhs = fb_rhs[fb], b_iD = fb_iD[fb];
+#pragma unroll
+            for (int p = 0; p < NC / 2; p++) {
+                float sa = la + (a_rhs - wa * a_iD), sb = lb + (b_rhs - wb * b_iD);
+                if (cone) { // implicit cone: s <- s min(1, lim / |s|) (0/0 and lim/0 resolve to 1 through fminf, a NaN stays a NaN)
+                    float rs;
+                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(fmaf(sa, sa, sb * sb)));
+                    const float sc = fminf(1.f, lim * rs);
+                    sa *= sc; sb *= sc;
+                } else {
+                    sa = fminf(fmaxf(sa, -lim), lim);
+                    sb = fminf(fmaxf(sb, -lim), lim);
+                }
+                const float da0 = sa - la, db0 = sb - lb;
+                const float da = __shfl_sync(FULL, da0, 2 * p), db = __shfl_sync(FULL, db0, 2 * p);
+                const bool mine = (lane >> 1) == p;
+                la = mine ? sa : la; lb = mine ? sb : lb; da_mine = mine ? da0 : da_mine; db_mine = mine ? db0 : db_mine;
+                if (p < NC / 2 - 1) {
+                    const float* A0 = Af + A_OFF(2 * p) - 2 * p + pa;         // A(2p, pa), A(2p, pa + 1)
+                    const float* A1 = Af + A_OFF(2 * p + 1) - 2 * p - 1 + pa; // A(2p + 1, pa), A(2p + 1, pa + 1)
+                    wa = fmaf(A0[0], da, fmaf(A1[0], db, wa));
+                    wb = fmaf(A0[1], da, fmaf(A1[1], db, wb));
+                }
+            }
+            lam_fa[fb] = la; lam_fb[fb] = lb;
+            W.dl[lane] = (lane & 1) ? db_mine : da_mine;
+            __syncwarp();
+            if (dof) {
+                float x0 = 0.f, x1 = 0.f;
+                const int rb = NJ + NC + 32 * fb;
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) { x0 = fmaf(W.B[rb + i][ld], W.dl[i], x0); x1 = fmaf(W.B[rb + i + 1][ld], W.dl[i + 1], x1); }
+                dv += x0 + x1;
+                W.dvs[lane] = dv;
+            }
+            const float rr = fmaf(da_mine, fa_Dg[fb], db_mine * fb_Dg[fb]);
+            res = fmaxf(res, rr * rr);
+            __syncwarp();
+        }
+        res = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(res))); // res >= 0: the bit patterns order like the values
         if (res <= P.resthr || it >= P.iters - 1) break;
     }
 
@@ -680,15 +811,15 @@ cudaError_t snk_launch_self_clearance(const DevTables* T, const float* state, fl
 size_t snk_pgs_smem_bytes() { return sizeof(WarpMemPgs) * WARPS_PER_CTA; }
 
 cudaError_t snk_pgs_configure() {
-    cudaError_t e = cudaFuncSetAttribute(snk_env_kernel<WarpMemPgs, false, WARPS_PER_CTA, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)snk_pgs_smem_bytes());
+    cudaError_t e = cudaFuncSetAttribute(snk_env_kernel<WarpMemPgs, false, WARPS_PER_CTA, CTAS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)snk_pgs_smem_bytes());
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(snk_env_kernel<WarpMemPgs, true, WARPS_PER_CTA, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)snk_pgs_smem_bytes());
+    return cudaFuncSetAttribute(snk_env_kernel<WarpMemPgs, true, WARPS_PER_CTA, CTAS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)snk_pgs_smem_bytes());
 }
 
 cudaError_t snk_pgs_launch_step(const DevTables* T, const KParams& P, float* state, const float* actions, float* obs, float* rew, uint8_t* done,
                             int32_t* ticks, unsigned long long* counters, int64_t n, cudaStream_t st, float* tick_obs, float* tick_links) {
     dim3 grid((unsigned)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA)), block(WARPS_PER_CTA * 32);
-    snk_env_kernel<WarpMemPgs, false, WARPS_PER_CTA, 2><<<grid, block, snk_pgs_smem_bytes(), st>>>(T, P, state, actions, obs, rew, done, ticks, counters, n, 0,
+    snk_env_kernel<WarpMemPgs, false, WARPS_PER_CTA, CTAS_PER_SM><<<grid, block, snk_pgs_smem_bytes(), st>>>(T, P, state, actions, obs, rew, done, ticks, counters, n, 0,
                                                                                                     tick_obs, tick_links);
     return cudaGetLastError();
 }
@@ -696,7 +827,7 @@ cudaError_t snk_pgs_launch_step(const DevTables* T, const KParams& P, float* sta
 cudaError_t snk_pgs_launch_tick(const DevTables* T, const KParams& P, float* state, const float* targets, unsigned long long* counters, int64_t n,
                             int n_ticks, cudaStream_t st) {
     dim3 grid((unsigned)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA)), block(WARPS_PER_CTA * 32);
-    snk_env_kernel<WarpMemPgs, true, WARPS_PER_CTA, 2><<<grid, block, snk_pgs_smem_bytes(), st>>>(T, P, state, targets, nullptr, nullptr, nullptr, nullptr, counters, n, n_ticks);
+    snk_env_kernel<WarpMemPgs, true, WARPS_PER_CTA, CTAS_PER_SM><<<grid, block, snk_pgs_smem_bytes(), st>>>(T, P, state, targets, nullptr, nullptr, nullptr, nullptr, counters, n, n_ticks);
     return cudaGetLastError();
 }
 
