@@ -35,6 +35,11 @@ cudaError_t snk_exact_launch_step_trace(const KParams& P, float* state, float* t
                                         int32_t* ticks, unsigned long long* counters, int64_t n, float* tick_obs, float* tick_links, cudaStream_t st);
 cudaError_t snk_exact_launch_tick(const KParams& P, float* state, const float* targets, unsigned long long* counters, int64_t n,
                                   int n_ticks, cudaStream_t st);
+// persistent contact manifolds + warm starting (snake_manifold.cuh, compiled into snake_exact.cu)
+size_t snk_man_scratch_bytes();
+size_t snk_man_cache_floats();
+cudaError_t snk_man_launch_step(const KParams& P, float* state, float* tgt_scratch, float* cache, void* scratch, float warm, const float* actions, float* obs,
+                                float* rew, uint8_t* done, int32_t* ticks, unsigned long long* counters, int64_t n, cudaStream_t st);
 // generalised advantage estimation (snake_gae.cu)
 cudaError_t snk_launch_gae(const float* rewards, const uint8_t* dones, const float* values, const float* next_value, float gamma, float tau,
                            float* returns, float* advantages, int T, int64_t n, cudaStream_t st);
@@ -71,6 +76,11 @@ struct snk_handle {
     size_t roll_queue_len;
     unsigned long long* counters; // device [NCOUNTERS]: ticks, sweeps, dones, non-finite, work-queue head
     int64_t launches;
+    // persistent contact manifolds (snk_set_manifold): per-environment caches, the resident threads' row tables, warm-start factor
+    bool manifold;
+    float* man_cache;             // device [n][MAN_STRIDE]
+    void* man_scratch;            // device, snk_man_scratch_bytes()
+    float man_warm;
     // staging for the *_host entry points (allocated on first use)
     cudaEvent_t ev_dev;           // recorded after every state-touching launch on a caller stream; the *_host entry points
     bool ev_valid;                // make their own stream wait on it (a device-path call may still be in flight)
@@ -112,7 +122,10 @@ static cudaError_t launch_step(snk_handle* h, const float* act, float* obs, floa
                                int64_t cnt = -1) {
     if (cnt < 0) cnt = h->n;
     int launches = 1;
-    cudaError_t e = h->exact ? snk_exact_launch_step(h->P, h->state + off * SNK_STATE_STRIDE, h->tgt + off * NJ, act, obs, rew, done, ticks, h->counters,
+    cudaError_t e = h->manifold ? snk_man_launch_step(h->P, h->state + off * SNK_STATE_STRIDE, h->tgt + off * NJ,
+                                                      h->man_cache + off * (int64_t)snk_man_cache_floats(), h->man_scratch, h->man_warm, act, obs, rew, done,
+                                                      ticks, h->counters, cnt, st)
+                    : h->exact ? snk_exact_launch_step(h->P, h->state + off * SNK_STATE_STRIDE, h->tgt + off * NJ, act, obs, rew, done, ticks, h->counters,
                                                      h->bucket + off, h->order + off, cnt, st, &launches)
                              : snk_pgs_launch_step(h->T, h->P, h->state + off * SNK_STATE_STRIDE, act, obs, rew, done, ticks, h->counters, cnt, st);
     h->launches += launches;
@@ -200,7 +213,8 @@ int snk_create(const snk_model* model, const snk_params* params, int64_t n_envs,
     if (err == cudaSuccess) err = cudaDeviceSynchronize();
     if (err != cudaSuccess) {
         if (h->exact) snk_exact_release();
-        cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters); cudaFree(h->bucket); cudaFree(h->order); cudaFree(h->tgt);
+        cudaFree(h->man_cache); cudaFree(h->man_scratch);
+    cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters); cudaFree(h->bucket); cudaFree(h->order); cudaFree(h->tgt);
         delete h;
         return fail(SNK_E_CUDA, "snk_create: %s", cudaGetErrorString(err));
     }
@@ -266,6 +280,7 @@ int snk_step_trace(snk_handle* h, const float* actions_dev, float* obs_dev, floa
     if (!h || !actions_dev || !obs_dev || !rew_dev || !done_dev || !ticks_dev)
         return fail(SNK_E_ARG, "snk_step_trace: null pointer (ticks_dev is required: it says how many trace rows are valid)%s");
     if (!aligned16(actions_dev) || !aligned16(obs_dev)) return fail(SNK_E_ARG, "snk_step_trace: actions and obs must be 16-byte aligned%s");
+    if (h->manifold) return fail(SNK_E_ARG, "snk_step_trace: not available with persistent manifolds (snk_set_manifold); use snk_step%s");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
@@ -283,6 +298,7 @@ int snk_rollout_linear(snk_handle* h, const float* weights_dev, const float* mea
     if (!h || !weights_dev || !returns_dev || n_steps < 1) return fail(SNK_E_ARG, "snk_rollout_linear: bad argument%s");
     if (!h->exact) return fail(SNK_E_ARG, "snk_rollout_linear: only with the exact motor solver (motor force = inf, kd = 1)%s");
     if (!aligned16(weights_dev)) return fail(SNK_E_ARG, "snk_rollout_linear: weights must be 16-byte aligned%s");
+    if (h->manifold) return fail(SNK_E_ARG, "snk_rollout_linear: not available with persistent manifolds (snk_set_manifold); use snk_step%s");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t qlen = (size_t)h->n * (size_t)(n_steps > 1 ? n_steps - 1 : 1);
@@ -302,6 +318,32 @@ int snk_rollout_linear(snk_handle* h, const float* weights_dev, const float* mea
     return 0;
 }
 
+int snk_set_manifold(snk_handle* h, int on, double warm_start) {
+    if (!h) return fail(SNK_E_ARG, "snk_set_manifold: null handle%s");
+    if (on && !h->exact) return fail(SNK_E_ARG, "snk_set_manifold: only with the exact motor solver (motor force = inf, kd = 1)%s");
+    if (!(warm_start >= 0.0)) return fail(SNK_E_ARG, "snk_set_manifold: warm_start must be >= 0%s");
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize()); // the caches of a step in flight are about to be cleared or freed
+    if (!on) {
+        cudaFree(h->man_cache); cudaFree(h->man_scratch);
+        h->man_cache = nullptr; h->man_scratch = nullptr; h->manifold = false;
+        return 0;
+    }
+    const size_t cache_bytes = (size_t)h->n * snk_man_cache_floats() * sizeof(float);
+    if (!h->man_cache) {
+        if (cudaMalloc(&h->man_cache, cache_bytes) != cudaSuccess || cudaMalloc(&h->man_scratch, snk_man_scratch_bytes()) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(h->man_cache); cudaFree(h->man_scratch);
+            h->man_cache = nullptr; h->man_scratch = nullptr; h->manifold = false;
+            return fail(SNK_E_NOMEM, "snk_set_manifold: out of device memory (4 224 B per environment + 388 MB of row tables)%s");
+        }
+    }
+    CU(cudaMemset(h->man_cache, 0, cache_bytes)); // empty caches, like a freshly loaded world
+    h->man_warm = (float)warm_start;
+    h->manifold = true;
+    return 0;
+}
+
 int snk_gae(int device, const float* rewards_dev, const uint8_t* dones_dev, const float* values_dev, const float* next_value_dev, double gamma,
             double tau, float* returns_dev, float* advantages_dev, int32_t n_steps, int64_t n_envs, void* stream) {
     if (!rewards_dev || !dones_dev || !values_dev || !next_value_dev || !returns_dev) return fail(SNK_E_ARG, "snk_gae: null pointer%s");
@@ -314,6 +356,7 @@ int snk_gae(int device, const float* rewards_dev, const uint8_t* dones_dev, cons
 
 int snk_tick(snk_handle* h, const float* targets_dev, int32_t n_ticks, void* stream) {
     if (!h || !targets_dev || n_ticks < 0) return fail(SNK_E_ARG, "snk_tick: bad argument%s");
+    if (h->manifold) return fail(SNK_E_ARG, "snk_tick: not available with persistent manifolds (snk_set_manifold); use snk_step%s");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
@@ -521,6 +564,17 @@ int snk_last_counters(snk_handle* h, int64_t out[4]) {
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(tmp, h->counters, sizeof tmp, cudaMemcpyDeviceToHost));
     for (int k = 0; k < 4; k++) out[k] = (int64_t)tmp[k];
+    return 0;
+}
+
+int snk_manifold_stats(snk_handle* h, int64_t out[2]) {
+    if (!h || !out) return fail(SNK_E_ARG, "snk_manifold_stats: null pointer%s");
+    if (!h->manifold) return fail(SNK_E_ARG, "snk_manifold_stats: persistent manifolds are off (snk_set_manifold)%s");
+    CU(cudaSetDevice(h->device));
+    unsigned long long tmp[8];
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(tmp, h->counters, sizeof tmp, cudaMemcpyDeviceToHost));
+    out[0] = (int64_t)tmp[7]; out[1] = (int64_t)tmp[0];
     return 0;
 }
 

@@ -28,6 +28,7 @@
 // Reference call sites replaced: SnakeGymEnv.py:33-50,82-103; snake.py:209-306,336-341;
 // ppo/multiprocessing_env.py:11-16; snake_gait_test.py:96-104 (raw ticks).
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -667,6 +668,10 @@ __global__ void snk_exact_order_kernel(int64_t n, const uint8_t* __restrict__ bu
     if (env < n) order[base[b] + my] = (int32_t)env;
 }
 
+#ifndef SNK_SCREEN
+#include "snake_manifold.cuh"
+#endif
+
 #ifdef SNK_SCREEN
 // tools/screen_variants.py compiles this file with -DSNK_SCREEN: only the benchmarked kernel, for a look at its SASS
 template __global__ void snk_hyb_step_kernel<true, false>(const KParams, float*, float*, const float*, float*, float*, uint8_t*, int32_t*, unsigned long long*,
@@ -734,6 +739,12 @@ cudaError_t snk_exact_configure(const ExTables* host_tables) {
     const char* w = getenv("SNK_EXACT_WARPS");
     g_active_warps = (w && atoi(w) >= 1 && atoi(w) <= HWARPS) ? atoi(w) : 0;
     e = cudaMemcpyToSymbol(cT, host_tables, sizeof(ExTables));
+    if (e == cudaSuccess) { // Bullet's 32-gon cylinder hull (snake_manifold.cuh): vertex i at angle 2 pi i / 32 from the link's y axis
+        float hs[MAN_HULL], hcs[MAN_HULL];
+        for (int i = 0; i < MAN_HULL; i++) { const double th = 2.0 * 3.14159265358979323846 / MAN_HULL * i; hs[i] = (float)sin(th); hcs[i] = (float)cos(th); }
+        e = cudaMemcpyToSymbol(cHullS, hs, sizeof hs);
+        if (e == cudaSuccess) e = cudaMemcpyToSymbol(cHullC, hcs, sizeof hcs);
+    }
     if (e == cudaSuccess) e = set_smem(snk_exact_step_kernel_smem<true>, sizeof(RowsSmemStore));
     if (e == cudaSuccess) e = set_smem(snk_exact_step_kernel_smem<false>, sizeof(RowsSmemStore));
     if (e == cudaSuccess) e = set_smem(snk_exact_tick_kernel<true>, sizeof(RowsSmemStore));
@@ -822,6 +833,20 @@ cudaError_t snk_exact_launch_step(const KParams& P, float* state, float* tgt_scr
         if (P.cone) snk_exact_step_kernel_smem<true><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n);
         else snk_exact_step_kernel_smem<false><<<grid, block, sizeof(RowsSmemStore), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n);
     }
+    return cudaGetLastError();
+}
+
+// persistent manifolds (snake_manifold.cuh): grid and scratch size of a device, and the step launch
+static int man_grid(int dev) { return g_sms[dev] * MAN_MINB; }
+size_t snk_man_scratch_bytes() { return (size_t)man_grid(cur_dev()) * (MAN_THREADS / 32) * MAN_WARP_V4 * sizeof(float4); }
+size_t snk_man_cache_floats() { return MAN_STRIDE; }
+cudaError_t snk_man_launch_step(const KParams& P, float* state, float* tgt_scratch, float* cache, void* scratch, float warm, const float* actions, float* obs,
+                                float* rew, uint8_t* done, int32_t* ticks, unsigned long long* counters, int64_t n, cudaStream_t st) {
+    const int64_t want = (n + MAN_THREADS - 1) / MAN_THREADS;
+    const int full = man_grid(cur_dev());
+    dim3 grid((unsigned)(want < full ? want : full)), block(MAN_THREADS);
+    if (P.cone) snk_man_step_kernel<true><<<grid, block, 0, st>>>(P, state, tgt_scratch, cache, (float4*)scratch, warm, actions, obs, rew, done, ticks, counters, n);
+    else snk_man_step_kernel<false><<<grid, block, 0, st>>>(P, state, tgt_scratch, cache, (float4*)scratch, warm, actions, obs, rew, done, ticks, counters, n);
     return cudaGetLastError();
 }
 

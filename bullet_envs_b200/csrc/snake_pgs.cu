@@ -24,8 +24,8 @@
 // ppo/multiprocessing_env.py:11-16; physics per SURVEY.md Appendix A (see oracle/snake_oracle.c,
 // whose row order, clamping and residual rule this kernel reproduces).
 #include "snake_dev.cuh"
-#define WARPS_PER_CTA 2
-#define CTAS_PER_SM 3
+#define WARPS_PER_CTA 1
+#define CTAS_PER_SM 7
 #define JS 23
 #define APACK (1 + NC * (NC - 1) / 2 + 3)
 #define A_OFF(i) ((i) * NC - ((i) * ((i) + 1)) / 2)
@@ -35,17 +35,9 @@ struct WarpMemPgs {
     float Rw[NB][9];
     float pw[NB][3];
     float Rj[NB][9];
-    float v[NB][6];
-    float cb[NB][6];
-    float pA[NB][6];
-    float IA[NB][36];
     float U[NB][6];
     float Dinv[NB];
     float uu[NB];
-    float X[36];
-    float Ia[36];
-    float Tm[36];
-    float pa[6];
     float IA0inv[36];
     float nu[ND];
     float nuF[ND];
@@ -57,10 +49,22 @@ struct WarpMemPgs {
     float Dg[NROW];
     float dvs[32];         // the solver's velocity change (lane = DoF keeps it in a register; this is the copy the rows read)
     float dl[32];          // impulse changes of the block just solved (lane = row), read by the velocity update
-    // in-block Delassus entries, packed upper triangles: entry (i, j > i) = J_j . B_i at A_OFF(i) + j - i (one pad word in front, so
-    // that the finished lanes j <= i of a step read inside the array); the motor block needs none (J = unit vector: B itself)
-    float An[APACK];
-    float Af[2][APACK];
+    union {
+        struct {           // forward-dynamics workspace: dead once the unconstrained velocity nu and the articulated quantities U, Dinv,
+            float v[NB][6];    // uu, IA0inv exist, i.e. before the first constraint row is built
+            float cb[NB][6];
+            float pA[NB][6];
+            float IA[NB][36];
+            float X[36];
+            float Ia[36];
+            float Tm[36];
+            float pa[6];
+        };
+        struct {           // in-block Delassus entries (written after the rows), packed upper triangles: entry (i, j > i) = J_j . B_i at
+            float An[APACK];   // A_OFF(i) + j - i (one pad word in front, so that the finished lanes j <= i of a step read inside the
+            float Af[2][APACK]; // array); the motor block needs none (J = unit vector: B itself)
+        };
+    };
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -524,9 +528,13 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
         {   // ---- motor rows (J = unit vector of joint j: w = dv[6 + j], A(i, j) = B_i[6 + j]) ----
             const bool rev = P.altmotor && !(it & 1);
             float w = W.dvs[6 + lm], lam = lam_m, dmine = 0.f;
-#pragma unroll
+            float bn = W.B[rev ? NJ - 1 : 0][6 + lm]; // A(i, j) of the coming step, fetched one step ahead of the chain
+#pragma unroll 4
             for (int s = 0; s < NJ; s++) {
                 const int i = rev ? NJ - 1 - s : s;
+                const float a = bn;
+                const int inext = rev ? (i > 0 ? i - 1 : 0) : (i < NJ - 1 ? i + 1 : i);
+                bn = W.B[inext][6 + lm];
                 const float d0 = m_rhs - w * m_iD;
                 const float sum0 = lam + d0;
                 const bool lo = sum0 < -maximp, hi = sum0 > maximp; // both false for a NaN: it passes through, as in the oracle
@@ -535,7 +543,7 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
                 const float di = __shfl_sync(FULL, d, i);
                 const bool mine = lane == i;
                 lam = mine ? sum : lam; dmine = mine ? d : dmine;
-                w = fmaf(W.B[i][6 + lm], di, w);
+                w = fmaf(a, di, w);
             }
             lam_m = lam;
             W.dl[lane] = dmine;
@@ -554,8 +562,16 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
 #pragma unroll
             for (int k = 0; k < ND; k += 2) { w0 = fmaf(W.J[lane][k], W.dvs[k], w0); w1 = fmaf(W.J[lane][k + 1], W.dvs[k + 1], w1); }
             float w = w0 + w1, lam = lam_n, dmine = 0.f;
-#pragma unroll
+            // rolled (4 rows per trip: the whole sweep stays in the instruction caches); the Delassus entry of a row is fetched one row
+            // ahead of the chain; A(i, lane) sits at An[aoff + lane] with aoff = A_OFF(i) - i, which grows by NC - i - 2 per row
+            const float* Ap = W.An + lane;
+            int aoff = 0;
+            float an = Ap[0];
+#pragma unroll 4
             for (int i = 0; i < NC; i++) {
+                const float a = an;
+                aoff += NC - i - 2;
+                an = Ap[i < NC - 2 ? aoff : 0]; // rows NC - 2 and NC - 1 have nothing left to fetch
                 const float d0 = n_rhs - w * n_iD;
                 const float sum0 = lam + d0;
                 const bool neg = sum0 < 0.f;
@@ -563,7 +579,7 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
                 const float di = __shfl_sync(FULL, d, i);
                 const bool mine = lane == i;
                 lam = mine ? sum : lam; dmine = mine ? d : dmine;
-                if (i < NC - 1) w = fmaf(W.An[A_OFF(i) + lane - i], di, w);
+                w = fmaf(a, di, w); // the last row's entry is a dummy: no row is left to read w
             }
             lam_n = lam;
             W.dl[lane] = dmine;
@@ -592,8 +608,19 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
             const float lim = mu * __shfl_sync(FULL, lam_n, 16 * fb + (lane >> 1));
             const float* Af = W.Af[fb];
             const float a_rhs = fa_rhs[fb], a_iD = fa_iD[fb], b_rhs = fb_rhs[fb], b_iD = fb_iD[fb];
-#pragma unroll
+            // rolled, two contacts per trip; the four Delassus entries of a step are fetched one step ahead: A(2p, pa), A(2p, pa + 1) at
+            // Af[o0 + pa], Af[o0 + pa + 1] with o0 = A_OFF(2p) - 2p, and A(2p + 1, .) at o1 = A_OFF(2p + 1) - 2p - 1 = o0 + NC - 2p - 2
+            const float* Aq = Af + pa;
+            int o0 = 0;
+            float a00 = Aq[0], a01 = Aq[1], a10 = Aq[NC - 2], a11 = Aq[NC - 1];
+#pragma unroll 2
             for (int p = 0; p < NC / 2; p++) {
+                const float c00 = a00, c01 = a01, c10 = a10, c11 = a11;
+                o0 += 2 * NC - 4 * p - 5; // A_OFF(2p + 2) - (2p + 2) - (A_OFF(2p) - 2p)
+                {
+                    const int q0 = p < NC / 2 - 1 ? o0 : 0, q1 = p < NC / 2 - 1 ? o0 + NC - 2 * p - 4 : 0; // nothing left to fetch for the last pair
+                    a00 = Aq[q0]; a01 = Aq[q0 + 1]; a10 = Aq[q1]; a11 = Aq[q1 + 1];
+                }
                 float sa = la + (a_rhs - wa * a_iD), sb = lb + (b_rhs - wb * b_iD);
                 if (cone) { // implicit cone: s <- s min(1, lim / |s|) (0/0 and lim/0 resolve to 1 through fminf, a NaN stays a NaN)
                     float rs;
@@ -608,12 +635,8 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
                 const float da = __shfl_sync(FULL, da0, 2 * p), db = __shfl_sync(FULL, db0, 2 * p);
                 const bool mine = (lane >> 1) == p;
                 la = mine ? sa : la; lb = mine ? sb : lb; da_mine = mine ? da0 : da_mine; db_mine = mine ? db0 : db_mine;
-                if (p < NC / 2 - 1) {
-                    const float* A0 = Af + A_OFF(2 * p) - 2 * p + pa;         // A(2p, pa), A(2p, pa + 1)
-                    const float* A1 = Af + A_OFF(2 * p + 1) - 2 * p - 1 + pa; // A(2p + 1, pa), A(2p + 1, pa + 1)
-                    wa = fmaf(A0[0], da, fmaf(A1[0], db, wa));
-                    wb = fmaf(A0[1], da, fmaf(A1[1], db, wb));
-                }
+                wa = fmaf(c00, da, fmaf(c10, db, wa)); // after the last pair nothing reads wa / wb: its entries are dummies
+                wb = fmaf(c01, da, fmaf(c11, db, wb));
             }
             lam_fa[fb] = la; lam_fb[fb] = lb;
             W.dl[lane] = (lane & 1) ? db_mine : da_mine;

@@ -288,6 +288,18 @@ class SnakeVecEnv:
             raise ValueError("checkpoint was taken from a batch with another size or other parameters")
         self.set_state(sd["state"])
 
+    def set_manifold(self, on=True, warm=0.1):
+        """Bullet's persistent contact manifolds + contact warm starting (``snk_set_manifold``): 4 cached points
+        per cylinder fed by the hull's support vertex, normal impulses of the previous tick x ``warm``.  Clears the caches.  Mirrors
+        the oracle's ``Oracle.set_manifold``; the default (off) is the one-point-per-cylinder tick the benchmark runs."""
+        _abi.check(self._lib.snk_set_manifold(self._h, int(bool(on)), float(warm)), self._lib)
+
+    def manifold_stats(self):
+        """(cached contact points summed over the ticks of the last step launch, ticks) -- ``snk_manifold_stats``."""
+        out = (ctypes.c_int64 * 2)()
+        _abi.check(self._lib.snk_manifold_stats(self._h, out), self._lib)
+        return int(out[0]), int(out[1])
+
     def counters(self):
         """Device counters of the last step launch: ticks, PGS iterations, dones, non-finite resets."""
         out = (ctypes.c_int64 * 4)()

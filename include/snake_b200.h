@@ -39,6 +39,7 @@
  *   snk_step_trace  <- the same step in mode='test': Snake.step's per-tick step_internal_observations / link_positions
  *                      (snake.py:275-278,292-293,138-146) returned through info (SnakeGymEnv.py:43-44; read by ppo/test.py:93-105)
  *   snk_observe     <- Snake.getObservation (snake.py:209-217)
+ *   snk_set_manifold <- the contact model of pybullet.stepSimulation itself (persistent manifolds, warm starting): snake.py:92-93,286
  *   snk_rollout_linear <- ARS rollout with a linear policy per environment: ars/train.py:74-116 (test_envs)
  *                      with policy() = W x (ars/train.py:40-41), normalisation (ars/train.py:152-169, statistics
  *                      frozen for the rollout) and the state noise of ars/train.py:81,90 supplied by the caller
@@ -194,6 +195,19 @@ int snk_step_trace(snk_handle* h, const float* actions_dev, float* obs_dev, floa
  * Only with the exact motor solver (the reference configuration).  State persists as after n_steps snk_step calls. */
 int snk_rollout_linear(snk_handle* h, const float* weights_dev, const float* mean_dev, const float* inv_std_dev,
                        const float* noise_dev, int32_t n_steps, float* returns_dev, float* obs_trace_dev, void* stream);
+
+/* Bullet's persistent contact manifolds and contact warm starting (what
+ * pybullet.loadURDF + stepSimulation do for the snake's 32 collision cylinders, snake.py:92-93,286): on != 0 switches the
+ * handle's snk_step / snk_step_host* to the manifold kernel -- per cylinder the support vertex of the 32-gon hull feeds a
+ * 4-slot contact cache with Bullet's add / replace / refresh / breaking rules (up to 128 contact points per environment), and
+ * the cached normal impulses x warm_start (Bullet: 0.1; 0 = off) start the solver.  The call (re)allocates and CLEARS the caches
+ * (4 224 B per environment + 388 MB of row tables per device); they survive soft resets like Bullet's (Q10).  on == 0 returns to
+ * the default one-point-per-cylinder tick (deviation D1) and frees the memory.  Only with the exact motor solver; snk_step_trace,
+ * snk_tick and snk_rollout_linear are refused while it is on.  Synchronises the device. */
+int snk_set_manifold(snk_handle* h, int on, double warm_start);
+/* out[0] = cached contact points summed over the physics ticks of the last step launch, out[1] = those ticks (their ratio is the
+ * mean number of contact rows-triples per tick; the oracle's row_stats).  Synchronises the device. */
+int snk_manifold_stats(snk_handle* h, int64_t out[2]);
 
 /* Generalised advantage estimation over a device-resident rollout (PPO half): compute_gae of ppo/agent.py:14-22
  * as one kernel.  rewards_dev / values_dev / returns_dev / advantages_dev are [T, N] fp32 row-major (time major, as RolloutBuffer
