@@ -484,7 +484,10 @@ int snk_step_host_f64(snk_handle* h, const double* actions_host, double* obs_hos
         if (e <= b) { CU(cudaEventRecord(h->ev_chunk[c], st)); continue; }
         float* ha = h->h_act;
         parallel_chunks((e - b) * ad, [=](size_t i0, size_t i1) { for (size_t i = b * ad + i0; i < b * ad + i1; i++) ha[i] = (float)actions_host[i]; });
-        if (c > 0) CU(cudaMemsetAsync(h->counters + 4, 0, (NCOUNTERS - 4) * sizeof(unsigned long long), st)); // the hand-out words are per launch
+        if (c > 0) { // the hand-out words are per launch ([7] is a statistic of the manifold kernel: it accumulates like [0..3])
+            CU(cudaMemsetAsync(h->counters + 4, 0, 3 * sizeof(unsigned long long), st));
+            CU(cudaMemsetAsync(h->counters + 8, 0, (NCOUNTERS - 8) * sizeof(unsigned long long), st));
+        }
         if (zc) {
             CU(launch_step(h, h->h_act + b * ad, h->h_obs + b * SNK_OBS_DIM, h->h_rew + b, h->h_done + b, h->h_ticks + b, st, (int64_t)b, (int64_t)(e - b)));
         } else {

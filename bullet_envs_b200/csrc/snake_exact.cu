@@ -767,6 +767,8 @@ cudaError_t snk_exact_configure(const ExTables* host_tables) {
     if (e == cudaSuccess) e = set_smem(snk_hyb_tick_kernel<false>, sizeof(StepSmemH));
     if (e == cudaSuccess) e = set_smem(snk_hyb_rollout_kernel<true>, sizeof(StepSmemH));
     if (e == cudaSuccess) e = set_smem(snk_hyb_rollout_kernel<false>, sizeof(StepSmemH));
+    if (e == cudaSuccess) e = set_smem(snk_man_step_kernel<true>, MAN_RING_BYTES);
+    if (e == cudaSuccess) e = set_smem(snk_man_step_kernel<false>, MAN_RING_BYTES);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
     e = cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev);
@@ -845,8 +847,8 @@ cudaError_t snk_man_launch_step(const KParams& P, float* state, float* tgt_scrat
     const int64_t want = (n + MAN_THREADS - 1) / MAN_THREADS;
     const int full = man_grid(cur_dev());
     dim3 grid((unsigned)(want < full ? want : full)), block(MAN_THREADS);
-    if (P.cone) snk_man_step_kernel<true><<<grid, block, 0, st>>>(P, state, tgt_scratch, cache, (float4*)scratch, warm, actions, obs, rew, done, ticks, counters, n);
-    else snk_man_step_kernel<false><<<grid, block, 0, st>>>(P, state, tgt_scratch, cache, (float4*)scratch, warm, actions, obs, rew, done, ticks, counters, n);
+    if (P.cone) snk_man_step_kernel<true><<<grid, block, MAN_RING_BYTES, st>>>(P, state, tgt_scratch, cache, (float4*)scratch, warm, actions, obs, rew, done, ticks, counters, n);
+    else snk_man_step_kernel<false><<<grid, block, MAN_RING_BYTES, st>>>(P, state, tgt_scratch, cache, (float4*)scratch, warm, actions, obs, rew, done, ticks, counters, n);
     return cudaGetLastError();
 }
 

@@ -38,6 +38,21 @@ struct ManRows {
     __device__ __forceinline__ float4& at(int k, int v) const { return rows[(k * MAN_ROW_V4 + v) * 32]; }
 };
 
+// The solver sweeps stream the row table through a per-thread RING in shared memory filled by cp.async (LDGSTS, L2 -> shared memory
+// without a register round trip): MAN_RING rows are in flight per thread, which hides the L2 latency that a one-row-ahead register
+// prefetch cannot (the first version of this kernel spent 70 % of its time waiting for exactly these loads).  Ring word v of slot s of
+// thread t: ring[(s * MAN_ROW_V4 + v) * MAN_THREADS + t] -- consecutive threads on consecutive 16 B words, conflict free.
+#define MAN_THREADS 128
+#define MAN_MINB 2
+#define MAN_RING 8
+#define MAN_RING_BYTES (MAN_RING * MAN_ROW_V4 * MAN_THREADS * 16)
+__device__ __forceinline__ void man_cp16(float4* smem_dst, const float4* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void man_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void man_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // btPersistentManifold::sortCachedPoints: the slot a new point replaces in a full cache (oracle: man_sort_cached)
 __device__ __forceinline__ int man_sort_cached(const float* mc, V3 lp, float dist) {
     int deepest = -1;
@@ -120,7 +135,7 @@ __device__ __forceinline__ void man_update(const ExTables& T, int c, const M3& R
 // `cache` = this environment's MAN_STRIDE floats.  Returns like ex_tick; out->contacts = cached points of the tick.
 // -----------------------------------------------------------------------------------------------
 template <bool CONE>
-__device__ void man_tick(const ExTables& T, const KParams& P, const ManRows& R, float* __restrict__ cache, float warm, ExEnv& e, const float* __restrict__ tg,
+__device__ void man_tick(const ExTables& T, const KParams& P, const ManRows& R, float4* __restrict__ ring, float* __restrict__ cache, float warm, ExEnv& e, const float* __restrict__ tg,
                          bool abort_on_height, bool* aborted, ExTickOut* out) {
     const float dt = P.dt, inv_dt = P.inv_dt;
     const V3 p0 = ld3(e.pos);
@@ -187,12 +202,23 @@ __device__ void man_tick(const ExTables& T, const KParams& P, const ManRows& R, 
             float mc[MAN_CYL_W];
             float4* gc = reinterpret_cast<float4*>(cache + k * MAN_CYL_W);
             int n = (int)cache[NC * MAN_CYL_W + k];
+            const int n_old = n;
+            // only the occupied slots move: a sliding snake holds about one point per cylinder (32 B of the cylinder's 128 B)
 #pragma unroll
-            for (int q = 0; q < MAN_CYL_W / 4; q++) { const float4 v = gc[q]; mc[4 * q] = v.x; mc[4 * q + 1] = v.y; mc[4 * q + 2] = v.z; mc[4 * q + 3] = v.w; }
+            for (int q = 0; q < MAN_SLOTS; q++)
+                if (q < n_old) {
+                    const float4 u = gc[2 * q], v = gc[2 * q + 1];
+                    mc[8 * q] = u.x; mc[8 * q + 1] = u.y; mc[8 * q + 2] = u.z; mc[8 * q + 3] = u.w;
+                    mc[8 * q + 4] = v.x; mc[8 * q + 5] = v.y; mc[8 * q + 6] = v.z; mc[8 * q + 7] = v.w;
+                }
             man_update(T, k, c.R, c.p, p0, mc, n);
 #pragma unroll
-            for (int q = 0; q < MAN_CYL_W / 4; q++) gc[q] = make_float4(mc[4 * q], mc[4 * q + 1], mc[4 * q + 2], mc[4 * q + 3]);
-            cache[NC * MAN_CYL_W + k] = (float)n;
+            for (int q = 0; q < MAN_SLOTS; q++)
+                if (q < n) {
+                    gc[2 * q] = make_float4(mc[8 * q], mc[8 * q + 1], mc[8 * q + 2], mc[8 * q + 3]);
+                    gc[2 * q + 1] = make_float4(mc[8 * q + 4], mc[8 * q + 5], mc[8 * q + 6], mc[8 * q + 7]);
+                }
+            if (n != n_old) cache[NC * MAN_CYL_W + k] = (float)n;
             if (n == 0) continue;
             M3 cf, Rl;
 #pragma unroll
@@ -278,12 +304,23 @@ __device__ void man_tick(const ExTables& T, const KParams& P, const ManRows& R, 
 #pragma unroll 1
     for (int it = 0; it < P.iters; it++) {
         float viol = 0.f;
-        // the record of point k + 1 is fetched (L1 / L2) while point k is on the (dw, dV) chain
-        float4 n0 = R.at(0, 0), n1 = R.at(0, 1);
+        // normal rows: words v0, v1 of MAN_RING - 1 rows ahead are on their way into the ring while row k is on the (dw, dV) chain
+        __threadfence_block(); // the asynchronous copies below must see this thread's own stores of the previous phase (ln, la, lb)
+#pragma unroll
+        for (int k = 0; k < MAN_RING - 1; k++) {
+            if (k < np) { man_cp16(ring + (k * MAN_ROW_V4) * MAN_THREADS, &R.at(k, 0)); man_cp16(ring + (k * MAN_ROW_V4 + 1) * MAN_THREADS, &R.at(k, 1)); }
+            man_commit();
+        }
 #pragma unroll 1
         for (int k = 0; k < np; k++) {
-            const float4 x0 = n0, x1 = n1;
-            if (k + 1 < np) { n0 = R.at(k + 1, 0); n1 = R.at(k + 1, 1); }
+            {
+                const int kn = k + MAN_RING - 1, sn = kn & (MAN_RING - 1);
+                if (kn < np) { man_cp16(ring + (sn * MAN_ROW_V4) * MAN_THREADS, &R.at(kn, 0)); man_cp16(ring + (sn * MAN_ROW_V4 + 1) * MAN_THREADS, &R.at(kn, 1)); }
+                man_commit();
+                man_wait<MAN_RING - 1>();
+            }
+            const int sk = k & (MAN_RING - 1);
+            const float4 x0 = ring[(sk * MAN_ROW_V4) * MAN_THREADS], x1 = ring[(sk * MAN_ROW_V4 + 1) * MAN_THREADS];
             const float ln = x0.x, rx = x0.y, ry = x0.z, idn = x1.x;
             const float p = ln + x1.y;
             float jd = fmaf(dw.x, ry, dV.z);
@@ -298,11 +335,30 @@ __device__ void man_tick(const ExTables& T, const KParams& P, const ManRows& R, 
             dV.z = fmaf(dd, invM, dV.z);
             viol = fmaxf(viol, fmaf(-sthr, idn, fabsf(dd)));
         }
-        float4 f0 = R.at(0, 0), f1 = R.at(0, 1), f2 = R.at(0, 2), f3 = R.at(0, 3), f4 = R.at(0, 4);
+        man_wait<0>();
+        __threadfence_block();
+        // friction pairs: all five words of a row
+#pragma unroll
+        for (int k = 0; k < MAN_RING - 1; k++) {
+            if (k < np) {
+#pragma unroll
+                for (int v = 0; v < MAN_ROW_V4; v++) man_cp16(ring + (k * MAN_ROW_V4 + v) * MAN_THREADS, &R.at(k, v));
+            }
+            man_commit();
+        }
 #pragma unroll 1
         for (int k = 0; k < np; k++) {
-            const float4 x0 = f0, x1 = f1, x2 = f2, x3 = f3, x4 = f4;
-            if (k + 1 < np) { f0 = R.at(k + 1, 0); f1 = R.at(k + 1, 1); f2 = R.at(k + 1, 2); f3 = R.at(k + 1, 3); f4 = R.at(k + 1, 4); }
+            {
+                const int kn = k + MAN_RING - 1, sn = kn & (MAN_RING - 1);
+                if (kn < np) {
+#pragma unroll
+                    for (int v = 0; v < MAN_ROW_V4; v++) man_cp16(ring + (sn * MAN_ROW_V4 + v) * MAN_THREADS, &R.at(kn, v));
+                }
+                man_commit();
+                man_wait<MAN_RING - 1>();
+            }
+            const float4* rk = ring + ((k & (MAN_RING - 1)) * MAN_ROW_V4) * MAN_THREADS;
+            const float4 x0 = rk[0], x1 = rk[MAN_THREADS], x2 = rk[2 * MAN_THREADS], x3 = rk[3 * MAN_THREADS], x4 = rk[4 * MAN_THREADS];
             const float rx = x0.y, ry = x0.z, rz = x0.w, la = x1.z, lb = x1.w;
             const float pa = la + x4.x, pb = lb + x4.y, lim = mu * x0.x;
             const float ux = fmaf(dw.y, rz, fmaf(-dw.z, ry, dV.x));
@@ -328,6 +384,7 @@ __device__ void man_tick(const ExTables& T, const KParams& P, const ManRows& R, 
             dw.z = fmaf(Ji.xz, tx, fmaf(Ji.yz, ty, fmaf(Ji.zz, tz, dw.z)));
             viol = fmaxf(viol, fmaf(-sthr * x2.w, x3.w, fabsf(fmaf(da, x3.w, db * x2.w))));
         }
+        man_wait<0>();
         sweeps++;
         if (viol <= 0.f) break;
     }
@@ -437,8 +494,6 @@ __device__ void man_tick(const ExTables& T, const KParams& P, const ManRows& R, 
 // -----------------------------------------------------------------------------------------------
 // kernel: one SubprocVecEnv.step() of N environments with persistent manifolds; thread = environment, persistent grid
 // -----------------------------------------------------------------------------------------------
-#define MAN_THREADS 128
-#define MAN_MINB 2
 struct ManTgt { // the joint targets of the env-step in flight: the environment's 64 B row of the handle's target scratch array
     float* tg;
     __device__ __forceinline__ float& tgt(int j) const { return tg[j]; }
@@ -453,44 +508,64 @@ snk_man_step_kernel(const KParams P, float* __restrict__ state, float* __restric
     const int64_t gw = ((int64_t)blockIdx.x * MAN_THREADS + threadIdx.x) >> 5;
     ManRows R;
     R.rows = scratch + gw * MAN_WARP_V4 + lane;
+    extern __shared__ __align__(16) unsigned char man_smem[];
+    float4* ring = reinterpret_cast<float4*>(man_smem) + threadIdx.x;
     unsigned long long c_ticks = 0, c_iters = 0;
     unsigned c_done = 0, c_bad = 0;
     unsigned long long c_points = 0; // cached contact points summed over the ticks (counters[7]: snk_manifold_stats)
+    // The unit the lanes of a warp share is ONE PHYSICS TICK, as in the benchmarked kernel: a thread whose environment has finished its
+    // tick loop writes the outputs and takes the next environment (first its own index, then a global counter) while the other lanes
+    // keep ticking -- a plain `for env { for tick }` nest would make every warp wait for its longest env-step at the end of the inner loop.
+    const int64_t tid = (int64_t)blockIdx.x * MAN_THREADS + threadIdx.x, T0 = (int64_t)gridDim.x * MAN_THREADS;
+    ExEnv e;
+    e.st = state; e.tid = lane;
+    ManTgt G;
+    G.tg = tgt_scratch;
+    float* mc = cache;
+    ExRun run;
+    int64_t env = -1;
+    bool have = false, first = true;
 #pragma unroll 1
-    for (int64_t env = (int64_t)blockIdx.x * MAN_THREADS + threadIdx.x; env < n; env += (int64_t)gridDim.x * MAN_THREADS) {
-        ExEnv e;
-        e.st = state + env * SNK_STATE_STRIDE;
-        e.tid = lane;
-        ManTgt G;
-        G.tg = tgt_scratch + env * NJ;
-        float* mc = cache + env * MAN_STRIDE;
-        load_targets(P, G, actions + env * P.actdim);
-        ex_load_base(e);
-        ExRun run;
-        ex_step_begin(P, G, e, &run);
-#pragma unroll 1
-        for (;;) { // snake.py:284-304 (ex_step_advance without the warp lock-step)
-            if (!(sqrtf(run.e2) > P.errthr)) break;
+    for (;;) {
+        if (!have) {
+            const int64_t cand = first ? tid : T0 + (int64_t)atomicAdd(&counters[4], 1ull);
+            first = false;
+            if (cand >= n) break;
+            env = cand; have = true;
+            e.st = state + env * SNK_STATE_STRIDE;
+            G.tg = tgt_scratch + env * NJ;
+            mc = cache + env * MAN_STRIDE;
+            load_targets(P, G, actions + env * P.actdim);
+            ex_load_base(e);
+            ex_step_begin(P, G, e, &run);
+        }
+        bool fin = !(sqrtf(run.e2) > P.errthr); // checkFeedback (snake.py:228-235); true at once: a zero-tick step (Q5)
+        if (!fin) {
             bool aborted;
             ExTickOut to;
-            man_tick<CONE>(cT, P, R, mc, warm, e, G.tg, run.counter > 0, &aborted, &to);
-            if (aborted) { run.end_height = true; run.height = to.height; run.have_height = true; break; }
-            run.iters += to.iterations;
-            c_points += (unsigned long long)to.contacts;
-            run.counter++;
-            run.e2 = to.err2_next;
-            if (run.counter >= P.maxticks) break;
+            man_tick<CONE>(cT, P, R, ring, mc, warm, e, G.tg, run.counter > 0, &aborted, &to);
+            if (aborted) { run.end_height = true; run.height = to.height; run.have_height = true; fin = true; } // the previous tick lifted the snake
+            else {
+                run.iters += to.iterations;
+                c_points += (unsigned long long)to.contacts;
+                run.counter++;
+                run.e2 = to.err2_next;
+                fin = run.counter >= P.maxticks || !(sqrtf(run.e2) > P.errthr);
+            }
         }
-        ExStepOut o;
-        ex_step_end(cT, P, e, run, &o);
-        rew[env] = o.rew;
-        done[env] = (uint8_t)o.done;
-        if (ticks) ticks[env] = o.ticks;
-        float* go = obs + env * SNK_OBS_DIM;
+        if (fin) {
+            ExStepOut o;
+            ex_step_end(cT, P, e, run, &o);
+            rew[env] = o.rew;
+            done[env] = (uint8_t)o.done;
+            if (ticks) ticks[env] = o.ticks;
+            float* go = obs + env * SNK_OBS_DIM;
 #pragma unroll 1
-        for (int k = 0; k < SNK_OBS_DIM; k += 4)
-            *reinterpret_cast<float4*>(go + k) = make_float4(ex_obs_of(e, k), ex_obs_of(e, k + 1), ex_obs_of(e, k + 2), ex_obs_of(e, k + 3));
-        c_ticks += (unsigned long long)o.ticks; c_iters += (unsigned long long)o.iters; c_done += o.done; c_bad += o.bad;
+            for (int k = 0; k < SNK_OBS_DIM; k += 4)
+                *reinterpret_cast<float4*>(go + k) = make_float4(ex_obs_of(e, k), ex_obs_of(e, k + 1), ex_obs_of(e, k + 2), ex_obs_of(e, k + 3));
+            c_ticks += (unsigned long long)o.ticks; c_iters += (unsigned long long)o.iters; c_done += o.done; c_bad += o.bad;
+            have = false;
+        }
     }
     if (c_ticks) atomicAdd(&counters[0], c_ticks);
     if (c_iters) atomicAdd(&counters[1], c_iters);
