@@ -442,9 +442,28 @@ def run_ours(args):
             a.record(); eb.step(ab[1]); eb.step(ab[2]); b.record(); torch.cuda.synchronize()
             msb = a.elapsed_time(b) / 2
             line["bullet_order"] = {"envs": nb, "env_steps_per_s": nb / (msb * 1e-3), "ms_per_step": msb, "ticks_per_s": eb.counters()["ticks"] / (msb * 1e-3),
-                                    "kernel": "snk_env_kernel (warp per environment, 16 motor + 96 contact rows, Bullet's row order)",
+                                    "kernel": "snk_env_kernel (warp per environment, 16 motor + 96 contact rows, Bullet's row order, block Gauss-Seidel)",
                                     "ratio_to_value": nb / (msb * 1e-3) / value}
             eb.close()
+            # the cost of deviation D1: the same step with Bullet's persistent contact manifolds and warm starting (snk_set_manifold,
+            # csrc/snake_manifold.cuh), 262 144 environments from the reset pose
+            nm = 262144
+            em = SnakeVecEnv(num_envs=nm, device=local)
+            em.set_manifold(True, 0.1)
+            em.reset(as_torch=True)
+            am = acts[:5, :nm].contiguous()
+            em.step(am[0]); em.step(am[1])
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); em.step(am[2]); em.step(am[3]); em.step(am[4]); b.record(); torch.cuda.synchronize()
+            msm = a.elapsed_time(b) / 3
+            pts, tkm = em.manifold_stats()
+            line["manifold"] = {"envs": nm, "env_steps_per_s": nm / (msm * 1e-3), "ms_per_step": msm, "ticks_per_s": tkm / (msm * 1e-3),
+                                "contact_points_per_tick": pts / max(tkm, 1), "warm_start": 0.1,
+                                "kernel": "snk_man_step_kernel (thread per environment, 4-slot manifold per cylinder, rows in global memory streamed "
+                                          "through a cp.async ring)",
+                                "ratio_to_value": nm / (msm * 1e-3) / value}
+            em.close()
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             nb = 2048 * threads  # ~10 s of CPU work per leg

@@ -31,7 +31,8 @@
 __constant__ float cHullS[MAN_HULL], cHullC[MAN_HULL];   // sin / cos of 2 pi i / 32: Bullet's cylinder hull, first vertex at (0, r)
 
 // the scratch table of one thread: word v of point k at rows[(k * MAN_ROW_V4 + v) * 32]
-//   v0 = (ln, r.x, r.y, r.z)   v1 = (invD_n, rhs_n invD_n, la, lb)   v2 = (d1.xyz, invD_1)   v3 = (d2.xyz, invD_2)   v4 = (rhs_1 invD_1, rhs_2 invD_2, -, -)
+//   v0 = (ln, r.x, r.y, r.z)   v1 = (invD_n, rhs_n invD_n, -, -)   v2 = (d1.xyz, invD_1)   v3 = (d2.xyz, invD_2)   v4 = (la, lb, rhs_1 invD_1, rhs_2 invD_2)
+//   (the normal sweep reads v0, v1, the friction sweep v0, v2, v3, v4: 32 + 64 bytes per point and sweep)
 // (pass 1 parks its temporaries in v0..v2 exactly like ex_tick)
 struct ManRows {
     float4* rows;
@@ -292,7 +293,7 @@ __device__ void man_tick(const ExTables& T, const KParams& P, const ManRows& R, 
         R.at(k, 1) = make_float4(iDn, rhsn, 0.f, 0.f);
         R.at(k, 2) = make_float4(d1.x, d1.y, d1.z, iD1);
         R.at(k, 3) = make_float4(d2.x, d2.y, d2.z, iD2);
-        R.at(k, 4) = make_float4(-dot(d1, vp) * iD1, -dot(d2, vp) * iD2, 0.f, 0.f);
+        R.at(k, 4) = make_float4(0.f, 0.f, -dot(d1, vp) * iD1, -dot(d2, vp) * iD2);
         // warm start (A.5): the cached normal impulse x warm factor acts before the first sweep
         dw = dw + Jn * ln0;
         dV.z = fmaf(ln0, invM, dV.z);
@@ -342,7 +343,7 @@ __device__ void man_tick(const ExTables& T, const KParams& P, const ManRows& R, 
         for (int k = 0; k < MAN_RING - 1; k++) {
             if (k < np) {
 #pragma unroll
-                for (int v = 0; v < MAN_ROW_V4; v++) man_cp16(ring + (k * MAN_ROW_V4 + v) * MAN_THREADS, &R.at(k, v));
+                for (int v = 0; v < MAN_ROW_V4; v++) if (v != 1) man_cp16(ring + (k * MAN_ROW_V4 + v) * MAN_THREADS, &R.at(k, v));
             }
             man_commit();
         }
@@ -352,15 +353,15 @@ __device__ void man_tick(const ExTables& T, const KParams& P, const ManRows& R, 
                 const int kn = k + MAN_RING - 1, sn = kn & (MAN_RING - 1);
                 if (kn < np) {
 #pragma unroll
-                    for (int v = 0; v < MAN_ROW_V4; v++) man_cp16(ring + (sn * MAN_ROW_V4 + v) * MAN_THREADS, &R.at(kn, v));
+                    for (int v = 0; v < MAN_ROW_V4; v++) if (v != 1) man_cp16(ring + (sn * MAN_ROW_V4 + v) * MAN_THREADS, &R.at(kn, v));
                 }
                 man_commit();
                 man_wait<MAN_RING - 1>();
             }
             const float4* rk = ring + ((k & (MAN_RING - 1)) * MAN_ROW_V4) * MAN_THREADS;
-            const float4 x0 = rk[0], x1 = rk[MAN_THREADS], x2 = rk[2 * MAN_THREADS], x3 = rk[3 * MAN_THREADS], x4 = rk[4 * MAN_THREADS];
-            const float rx = x0.y, ry = x0.z, rz = x0.w, la = x1.z, lb = x1.w;
-            const float pa = la + x4.x, pb = lb + x4.y, lim = mu * x0.x;
+            const float4 x0 = rk[0], x2 = rk[2 * MAN_THREADS], x3 = rk[3 * MAN_THREADS], x4 = rk[4 * MAN_THREADS];
+            const float rx = x0.y, ry = x0.z, rz = x0.w, la = x4.x, lb = x4.y;
+            const float pa = la + x4.z, pb = lb + x4.w, lim = mu * x0.x;
             const float ux = fmaf(dw.y, rz, fmaf(-dw.z, ry, dV.x));
             const float uy = fmaf(dw.z, rx, fmaf(-dw.x, rz, dV.y));
             const float uz = fmaf(dw.x, ry, fmaf(-dw.y, rx, dV.z));
@@ -375,7 +376,7 @@ __device__ void man_tick(const ExTables& T, const KParams& P, const ManRows& R, 
                 sb = fminf(fmaxf(sb, -lim), lim);
             }
             const float da = sa - la, db = sb - lb;
-            *reinterpret_cast<float2*>(&R.at(k, 1).z) = make_float2(sa, sb);
+            *reinterpret_cast<float2*>(&R.at(k, 4).x) = make_float2(sa, sb);
             const float fx = fmaf(x3.x, db, x2.x * da), fy = fmaf(x3.y, db, x2.y * da), fz = fmaf(x3.z, db, x2.z * da);
             const float tx = fmaf(-rz, fy, ry * fz), ty = fmaf(-rx, fz, rz * fx), tz = fmaf(-ry, fx, rx * fy);
             dV.x = fmaf(fx, invM, dV.x); dV.y = fmaf(fy, invM, dV.y); dV.z = fmaf(fz, invM, dV.z);
@@ -439,8 +440,8 @@ __device__ void man_tick(const ExTables& T, const KParams& P, const ManRows& R, 
             SN = SN + cross(cc, F) + N;
 #pragma unroll 1
             for (int k = pbeg; k < pend; k++) {
-                const float4 x0 = R.at(k, 0), x1 = R.at(k, 1), x2 = R.at(k, 2), x3 = R.at(k, 3);
-                V3 f = mk(fmaf(x3.x, x1.w, x2.x * x1.z), fmaf(x3.y, x1.w, x2.y * x1.z), fmaf(x3.z, x1.w, fmaf(x2.z, x1.z, x0.x))) * inv_dt;
+                const float4 x0 = R.at(k, 0), x2 = R.at(k, 2), x3 = R.at(k, 3), x4 = R.at(k, 4);
+                V3 f = mk(fmaf(x3.x, x4.y, x2.x * x4.x), fmaf(x3.y, x4.y, x2.y * x4.x), fmaf(x3.z, x4.y, fmaf(x2.z, x4.x, x0.x))) * inv_dt;
                 V3 r = mk(x0.y + hc.x, x0.z + hc.y, x0.w + hc.z);
                 SF = SF - f;
                 SN = SN - cross(r, f);

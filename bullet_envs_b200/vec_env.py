@@ -113,6 +113,10 @@ class SnakeVecEnv:
             st[m] = 0.0
             st[m, 6] = 1.0  # SNK_S_QUAT + 3
             self.set_state(st)
+            if getattr(self, "_manifold", None):  # a rebuilt world has empty contact caches (they survive SOFT resets only, Q10)
+                if mask is not None and not bool(m.all()):
+                    raise NotImplementedError("hard reset of a subset of the environments while persistent manifolds are on")
+                self.set_manifold(*self._manifold)
         if as_torch or (mask is not None and torch.is_tensor(mask) and mask.is_cuda):
             obs = torch.empty((self.num_envs, OBS_DIM), dtype=torch.float32, device=self.device)
             m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
@@ -293,6 +297,7 @@ class SnakeVecEnv:
         per cylinder fed by the hull's support vertex, normal impulses of the previous tick x ``warm``.  Clears the caches.  Mirrors
         the oracle's ``Oracle.set_manifold``; the default (off) is the one-point-per-cylinder tick the benchmark runs."""
         _abi.check(self._lib.snk_set_manifold(self._h, int(bool(on)), float(warm)), self._lib)
+        self._manifold = (True, float(warm)) if on else None
 
     def manifold_stats(self):
         """(cached contact points summed over the ticks of the last step launch, ticks) -- ``snk_manifold_stats``."""

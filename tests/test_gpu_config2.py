@@ -40,11 +40,15 @@ def actions(torch):
     return (torch.rand((STEPS, N, 8), generator=g) * 2 - 1).numpy()   # float32 [100, 4096, 8], generated on the CPU
 
 
-def run_config2(torch, actions, resync):
+def run_config2(torch, actions, resync, manifold=None):
+    """manifold = warm-start factor: both sides run with Bullet's persistent contact manifolds (snk_set_manifold / Oracle.set_manifold)."""
     from bullet_envs_b200 import SnakeVecEnv
     p = default_params()
     env = SnakeVecEnv(num_envs=N, device=0, params=p)
     o = Oracle(N_ORACLE, p)
+    if manifold is not None:
+        assert not resync  # the contact caches are state without a set_state
+        env.set_manifold(True, manifold); o.set_manifold(True, manifold)
     env.reset(as_torch=True); o.reset()
     err = {k: [] for k, _ in FIELDS}
     scale = {k: 0.0 for k, _ in FIELDS}
@@ -125,6 +129,24 @@ def test_config2_free_running(torch, actions):
     # rewards: free-running trajectories of a contact-rich system separate, so the 100-step returns agree statistically -- the
     # event-free part of the reward (progress, drift, energy) in the batch mean, the rare -10 / -5 events as counts with a Poisson
     # allowance (tests/hostemu, the same fp32 arithmetic on the CPU, differs from the oracle by the same amounts)
+    assert abs(ev["free_g"] - ev["free_o"]) <= 0.05 * abs(ev["free_o"]) + 2e-3, ev
+    assert abs(ev["pen_g"] - ev["pen_o"]) <= 4 * np.sqrt(max(ev["pen_o"], 1)) + 5, ev
+    assert abs(ev["done_g"] - ev["done_o"]) <= 0.1 * ev["done_o"] + 5, ev
+    sigma = (10.0 * np.sqrt(ev["pen_g"] + ev["pen_o"] + 1) + 5.0 * np.sqrt(ev["done_g"] + ev["done_o"] + 1)) / N_ORACLE
+    assert abs(ret_g.mean() - ret_o.mean()) <= 0.01 * abs(ret_o.mean()) + 3 * sigma, (ret_g.mean(), ret_o.mean(), sigma)
+
+
+def test_config2_free_running_manifold(torch, actions):
+    """The same 4 096 x 100 free-running comparison with Bullet's persistent contact manifolds + warm starting (0.1) on both sides
+    (SURVEY.md 8f rank 2): the bounds of test_config2_free_running."""
+    pct, scale, tick_eq, done_eq, n_done, ret_g, ret_o, finite, ev = run_config2(torch, actions, resync=False, manifold=0.1)
+    assert finite
+    assert tick_eq.mean() >= 0.98 and done_eq.mean() >= 0.99, (tick_eq.mean(), done_eq.mean())
+    assert tick_eq[-10:].mean() >= 0.97
+    assert pct["q"][2] <= 1e-5 and pct["q"][3] <= 5e-2 and pct["qd"][2] <= 1e-4 * max(1.0, scale["qd"]), (pct["q"], pct["qd"])
+    assert pct["pos"][0] <= 0.15 and pct["pos"][2] <= 2.5, pct["pos"]
+    assert pct["quat"][0] <= 0.10, pct["quat"]
+    assert pct["rew"][0] <= 1e-2, pct["rew"]
     assert abs(ev["free_g"] - ev["free_o"]) <= 0.05 * abs(ev["free_o"]) + 2e-3, ev
     assert abs(ev["pen_g"] - ev["pen_o"]) <= 4 * np.sqrt(max(ev["pen_o"], 1)) + 5, ev
     assert abs(ev["done_g"] - ev["done_o"]) <= 0.1 * ev["done_o"] + 5, ev
