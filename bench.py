@@ -429,6 +429,12 @@ def run_ours(args):
             "clocks": clocks,
         }
         line.update(extra)
+        if world == 1:
+            # the kernels of the path for which HBM IS the roofline: observation epilogue, state copy, GAE scan
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_hbm_kernels
+            hb = bench_hbm_kernels.measure(env, iters=20, with_reset=False, peak=peak)
+            line["hbm_bound_kernels"] = {k["kernel"]: {"GB/s": k["GB/s"], "frac": k["frac_of_measured_hbm_peak"], "ms": k["ms"]} for k in hb["kernels"]}
         if world == 1 and not args.no_bullet_order:
             # the cost of deviation D4 being wrong: the same step with the motor rows relaxed inside the PGS in Bullet's order
             # (motor_solver = 0, warp-per-env kernel), 65 536 environments

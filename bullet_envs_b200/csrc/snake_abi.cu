@@ -249,6 +249,7 @@ int64_t snk_launch_count(const snk_handle* h) { return h ? h->launches : 0; }
 
 int snk_reset(snk_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
     if (!h) return fail(SNK_E_ARG, "snk_reset: null handle%s");
+    if (obs_dev && !aligned16(obs_dev)) return fail(SNK_E_ARG, "snk_reset: obs must be 16-byte aligned%s");
     CU(cudaSetDevice(h->device));
     CU(snk_launch_reset(h->P, h->state, mask_dev, obs_dev, h->n, 0, (cudaStream_t)stream));
     h->launches++;
@@ -258,6 +259,7 @@ int snk_reset(snk_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stre
 
 int snk_observe(snk_handle* h, float* obs_dev, void* stream) {
     if (!h || !obs_dev) return fail(SNK_E_ARG, "snk_observe: null pointer%s");
+    if (!aligned16(obs_dev)) return fail(SNK_E_ARG, "snk_observe: obs must be 16-byte aligned%s");
     CU(cudaSetDevice(h->device));
     CU(snk_launch_reset(h->P, h->state, nullptr, obs_dev, h->n, 2, (cudaStream_t)stream));
     h->launches++;

@@ -8,6 +8,7 @@
 // return 4 out).  The grid is a multiple of the SM count for large N.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 // UN consecutive time steps are loaded before they are consumed so that a thread has several independent loads in flight
 template <int UN>
@@ -54,6 +55,10 @@ cudaError_t snk_launch_gae(const float* rewards, const uint8_t* dones, const flo
     int64_t blocks = (n + 255) / 256;
     const int64_t cap = (int64_t)sms * 8; // 8 resident CTAs of 256 threads per SM
     if (blocks > cap) blocks = cap;
-    snk_gae_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(rewards, dones, values, next_value, gamma, tau, returns, advantages, T, n);
+    // loads in flight per thread: 10 time steps when the rollout length allows (num_steps = 20, ppo/params.py:10), else 4
+    const char* un = getenv("SNK_GAE_UN");
+    const bool deep = un ? atoi(un) >= 10 : (T % 10 == 0);
+    if (deep) snk_gae_kernel<10><<<(unsigned)blocks, 256, 0, st>>>(rewards, dones, values, next_value, gamma, tau, returns, advantages, T, n);
+    else snk_gae_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(rewards, dones, values, next_value, gamma, tau, returns, advantages, T, n);
     return cudaGetLastError();
 }

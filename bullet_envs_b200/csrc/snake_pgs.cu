@@ -710,25 +710,53 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
 // ---------------------------------------------------------------------------------------------
 #include "snake_task.cuh"
 
-// reset / observe: one thread per (env, state slot).  mode 0 = masked soft reset (+ optional obs of
-// every env), 1 = initialise everything, 2 = observe only.
-__global__ void snk_reset_kernel(const KParams P, float* __restrict__ state, const uint8_t* __restrict__ mask, float* __restrict__ obs,
-                                 int64_t n, int mode) {
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t env = idx >> 6;
-    int k = (int)(idx & 63);
+// reset / observe.  mode 0 = masked soft reset (+ optional obs of every env), 1 = initialise everything, 2 = observe only.
+// HBM bound (256 B record in, 224 B observation row out, the record of a reset environment written back), so the layout is chosen
+// for bytes in flight: SIXTEEN threads per environment, thread j < 14 owns the j-th 16-byte word of the observation row -- four
+// state slots in, one aligned float4 out, a warp writes 512 consecutive bytes -- and threads 14, 15 own the eight slots that are not
+// part of the observation in the slot map below; a reset environment's record is written as sixteen ALIGNED 16-byte words, one per
+// thread.  (One thread per slot, the first version, kept 4 B per thread in flight and reached 40 % of the copy bandwidth; writing the
+// record back as unaligned scalars, the second, 11 %.)  Observation index -> state slot (snake.py:209-217): q 0..15 <- 13..28,
+// qd 16..31 <- 29..44, applied torque 32..47 <- 45..60, base position 48..50 <- 0..2, quaternion 51..54 <- 3..6, Fz 55 <- 61.
+__device__ __forceinline__ int reset_slot_of(int j, int c) { // state slot of component c of 16-byte word j (j = 14, 15: the non-observed slots)
+    if (j < 12) return SNK_S_Q + 4 * j + c;
+    if (j == 12) return c;                                  // pos.xyz, quat.x
+    if (j == 13) return (c < 3) ? 4 + c : SNK_S_FZ;         // quat.yzw, Fz
+    if (j == 14) return SNK_S_VEL + c;                      // vel.xyz, omega.x
+    return (c < 2) ? SNK_S_OMEGA + 1 + c : SNK_S_RET + (c - 2); // omega.yz, return, length
+}
+__global__ void __launch_bounds__(256) snk_reset_kernel(const KParams P, float* __restrict__ state, const uint8_t* __restrict__ mask, float* __restrict__ obs,
+                                                        int64_t n, int mode) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t env = idx >> 4;
+    const int j = (int)(idx & 15);
     if (env >= n) return;
-    float* s = state + env * SNK_STATE_STRIDE;
-    float val = s[k];
     const bool hit = (mode == 1) || (mode == 0 && (!mask || mask[env]));
+    float* s = state + env * SNK_STATE_STRIDE;
+    const bool stale = P.stale && mode == 0; // Q9: the torque / Fz slots (45..61) survive a soft reset
+    // (a) the record of a reset environment: thread j writes its ALIGNED 16-byte word j (slots 4j..4j+3) -- a constant, except for the
+    //     words that hold surviving slots (44..63), which are read, cleared around them and written back
     if (hit) {
-        bool keep = (k >= SNK_S_TAU && k <= SNK_S_FZ) && P.stale && mode == 0;
-        if (!keep) { val = (k == SNK_S_QUAT + 3) ? 1.f : 0.f; s[k] = val; }
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j == 1) w.z = 1.f;                       // slot 6 = quat.w
+        if (stale && j >= 11) {
+            w = reinterpret_cast<const float4*>(s)[j];
+            if (j == 11) w.x = 0.f;                  // slot 44 = qd[15]
+            if (j == 15) { w.z = 0.f; w.w = 0.f; }   // slots 62, 63 = return, length
+        }
+        reinterpret_cast<float4*>(s)[j] = w;
     }
-    if (obs && k < SNK_S_RET) { // state slot -> observation index (snake.py:209-217)
-        int o = (k < SNK_S_QUAT) ? 48 + k : (k < SNK_S_VEL) ? 51 + (k - SNK_S_QUAT) : (k < SNK_S_Q) ? -1 : (k < SNK_S_QD) ? k - SNK_S_Q
-                : (k < SNK_S_TAU) ? 16 + (k - SNK_S_QD) : (k < SNK_S_FZ) ? 32 + (k - SNK_S_TAU) : 55;
-        if (o >= 0) obs[env * SNK_OBS_DIM + o] = val;
+    // (b) the observation row: thread j < 14 builds its 16-byte word from the PRE-reset record and the reset rule (thread (a) of a
+    //     surviving slot rewrites the value it read, so the two roles never disagree)
+    if (obs && j < 14) {
+        float v[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int k = reset_slot_of(j, c);
+            const bool keep = (k >= SNK_S_TAU && k <= SNK_S_FZ) && stale;
+            v[c] = (hit && !keep) ? ((k == SNK_S_QUAT + 3) ? 1.f : 0.f) : ((mode == 1) ? 0.f : s[k]);
+        }
+        *reinterpret_cast<float4*>(obs + env * SNK_OBS_DIM + 4 * j) = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
 
@@ -855,7 +883,7 @@ cudaError_t snk_pgs_launch_tick(const DevTables* T, const KParams& P, float* sta
 }
 
 cudaError_t snk_launch_reset(const KParams& P, float* state, const uint8_t* mask, float* obs, int64_t n, int mode, cudaStream_t st) {
-    int64_t total = n * 64;
+    int64_t total = n * 16;
     dim3 grid((unsigned)((total + 255) / 256)), block(256);
     snk_reset_kernel<<<grid, block, 0, st>>>(P, state, mask, obs, n, mode);
     return cudaGetLastError();

@@ -98,3 +98,22 @@ def test_manifold_switch_and_refusals(torch):
     with pytest.raises(RuntimeError):
         e0.set_manifold(True)
     e0.close()
+
+
+def test_manifold_host_path_equals_device_path(torch):
+    """SnakeVecEnv.step(numpy) goes through snk_step_host_f64 (the batch in pipelined chunks of environments, each chunk a launch at an
+    environment offset): with the manifolds on it must return what the device path returns, bit for bit -- the caches and the row
+    tables are indexed by environment and by resident thread, not by launch."""
+    n = 1000
+    g = torch.Generator().manual_seed(11)
+    acts = (torch.rand((3, n, 8), generator=g) * 2 - 1)
+    a = SnakeVecEnv(num_envs=n, device=0); b = SnakeVecEnv(num_envs=n, device=0)
+    a.set_manifold(True, 0.1); b.set_manifold(True, 0.1)
+    a.reset(); b.reset(as_torch=True)
+    for t in range(3):
+        oa, ra, da, _ = a.step(acts[t].numpy().astype(np.float64))
+        ob, rb, db, _ = b.step(acts[t].cuda())
+        assert np.array_equal(oa.astype(np.float32), ob.cpu().numpy())
+        assert np.array_equal(ra.astype(np.float32), rb.cpu().numpy())
+        assert np.array_equal(np.asarray(da, bool), db.cpu().numpy().astype(bool))
+    a.close(); b.close()
