@@ -25,7 +25,7 @@
 // whose row order, clamping and residual rule this kernel reproduces).
 #include "snake_dev.cuh"
 #define WARPS_PER_CTA 1
-#define CTAS_PER_SM 7
+#define CTAS_PER_SM 8
 #define JS 23
 #define APACK (1 + NC * (NC - 1) / 2 + 3)
 #define A_OFF(i) ((i) * NC - ((i) * ((i) + 1)) / 2)
@@ -42,7 +42,7 @@ struct WarpMemPgs {
     float nu[ND];
     float nuF[ND];
     float target[NJ];
-    float J[3 * NC][JS];   // rows padded to JS words: lane = row reads are bank-conflict free
+    float Jf[2 * NC][JS];  // Jacobians of the friction rows (2c, 2c + 1 of contact c), padded to JS words: lane = row reads are bank-conflict free
     float B[NROW][ND];
     float rhs[NROW];
     float invD[NROW];
@@ -60,6 +60,7 @@ struct WarpMemPgs {
             float Tm[36];
             float pa[6];
         };
+        float Jn[NC][JS];  // Jacobians of the normal rows while the rows are built; each lane then keeps its row in registers for the solver
         struct {           // in-block Delassus entries (written after the rows), packed upper triangles: entry (i, j > i) = J_j . B_i at
             float An[APACK];   // A_OFF(i) + j - i (one pad word in front, so that the finished lanes j <= i of a step read inside the
             float Af[2][APACK]; // array); the motor block needs none (J = unit vector: B itself)
@@ -410,8 +411,9 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
 #pragma unroll 1
             for (int f = 0; f < 3; f++) {
                 const int r = (f == 0) ? c : NC + 2 * c + (f - 1);
+                float* Jz = (f == 0) ? W.Jn[c] : W.Jf[2 * c + (f - 1)];
 #pragma unroll 1
-                for (int k = 0; k < ND; k++) { W.J[r][k] = 0.f; W.B[NJ + r][k] = 0.f; }
+                for (int k = 0; k < ND; k++) { Jz[k] = 0.f; W.B[NJ + r][k] = 0.f; }
                 W.Dg[NJ + r] = 0.f; W.invD[NJ + r] = 0.f; W.rhs[NJ + r] = 0.f;
             }
         }
@@ -425,8 +427,8 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
                 loc[0] *= P.aniso[0]; loc[1] *= P.aniso[1]; loc[2] *= P.aniso[2];
                 m3v(Rl, loc, d);
             }
-            const int r = (f == 0) ? c : NC + 2 * c + (f - 1); // index into J; B/rhs rows are NJ + r
-            float* Jr = W.J[r];
+            const int r = (f == 0) ? c : NC + 2 * c + (f - 1); // B / rhs rows are NJ + r
+            float* Jr = (f == 0) ? W.Jn[c] : W.Jf[2 * c + (f - 1)];
             float* Br = W.B[NJ + r];
             float rel[3] = {p[0] - W.pw[0][0], p[1] - W.pw[0][1], p[2] - W.pw[0][2]}, rxd[3], jb[6];
             cross3(rel, d, rxd);
@@ -467,10 +469,16 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
     __syncwarp();
 
     // ---- in-block Delassus entries A(i, j) = J_j . B_i for the rows j > i of the same block (lane = row j) ----
+    // the lane of contact c keeps the Jacobian of its normal row in registers from here on: the staging rows share their shared memory
+    // with the Delassus blocks written next
+    float Jn[ND];
+#pragma unroll
+    for (int k = 0; k < ND; k++) Jn[k] = W.Jn[lane][k];
+    __syncwarp();
     {
         float Jr[ND];
 #pragma unroll
-        for (int k = 0; k < ND; k++) Jr[k] = W.J[lane][k];
+        for (int k = 0; k < ND; k++) Jr[k] = Jn[k];
 #pragma unroll 1
         for (int i = 0; i < NC - 1; i++) {
             const float* Bi = W.B[NJ + i];
@@ -482,7 +490,7 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
 #pragma unroll 1
         for (int fb = 0; fb < 2; fb++) {
 #pragma unroll
-            for (int k = 0; k < ND; k++) Jr[k] = W.J[NC + 32 * fb + lane][k];
+            for (int k = 0; k < ND; k++) Jr[k] = W.Jf[32 * fb + lane][k];
 #pragma unroll 1
             for (int i = 0; i < NC - 1; i++) {
                 const float* Bi = W.B[NJ + NC + 32 * fb + i];
@@ -560,7 +568,7 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
         {   // ---- normal rows, lane = contact ----
             float w0 = 0.f, w1 = 0.f;
 #pragma unroll
-            for (int k = 0; k < ND; k += 2) { w0 = fmaf(W.J[lane][k], W.dvs[k], w0); w1 = fmaf(W.J[lane][k + 1], W.dvs[k + 1], w1); }
+            for (int k = 0; k < ND; k += 2) { w0 = fmaf(Jn[k], W.dvs[k], w0); w1 = fmaf(Jn[k + 1], W.dvs[k + 1], w1); }
             float w = w0 + w1, lam = lam_n, dmine = 0.f;
             // rolled (4 rows per trip: the whole sweep stays in the instruction caches); the Delassus entry of a row is fetched one row
             // ahead of the chain; A(i, lane) sits at An[aoff + lane] with aoff = A_OFF(i) - i, which grows by NC - i - 2 per row
@@ -599,8 +607,8 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
         for (int fb = 0; fb < 2; fb++) { // ---- friction pairs of contacts 16 fb .. 16 fb + 15 ----
             // lanes 2p and 2p + 1 both carry BOTH rows of contact 16 fb + p (w_a, w_b and the two impulses), so the cone projection
             // needs no exchange between lanes: the only shuffles on the chain broadcast the pair's (da, db)
-            const float* Ja = W.J[NC + 32 * fb + pa];
-            const float* Jb = W.J[NC + 32 * fb + pa + 1];
+            const float* Ja = W.Jf[32 * fb + pa];
+            const float* Jb = W.Jf[32 * fb + pa + 1];
             float wa = 0.f, wb = 0.f;
 #pragma unroll
             for (int k = 0; k < ND; k++) { const float x = W.dvs[k]; wa = fmaf(Ja[k], x, wa); wb = fmaf(Jb[k], x, wb); }
