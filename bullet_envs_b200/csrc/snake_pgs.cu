@@ -25,7 +25,7 @@
 // whose row order, clamping and residual rule this kernel reproduces).
 #include "snake_dev.cuh"
 #define WARPS_PER_CTA 1
-#define CTAS_PER_SM 8
+#define CTAS_PER_SM 9
 #define JS 23
 #define APACK (1 + NC * (NC - 1) / 2 + 3)
 #define A_OFF(i) ((i) * NC - ((i) * ((i) + 1)) / 2)
@@ -34,11 +34,6 @@ struct WarpMemPgs {
     float s[SNK_STATE_STRIDE];
     float Rw[NB][9];
     float pw[NB][3];
-    float Rj[NB][9];
-    float U[NB][6];
-    float Dinv[NB];
-    float uu[NB];
-    float IA0inv[36];
     float nu[ND];
     float nuF[ND];
     float target[NJ];
@@ -46,27 +41,40 @@ struct WarpMemPgs {
     float B[NROW][ND];
     float rhs[NROW];
     float invD[NROW];
-    float Dg[NROW];
     float dvs[32];         // the solver's velocity change (lane = DoF keeps it in a register; this is the copy the rows read)
     float dl[32];          // impulse changes of the block just solved (lane = row), read by the velocity update
+    // Three lifetimes share one region: what only the forward dynamics and the row set-up read (joint frames, articulated quantities;
+    // fk() rewrites Rj after every tick), inside it the forward-dynamics workspace and then the staging rows of the normal Jacobians,
+    // and finally -- once the rows exist and every lane holds its normal row in registers -- the Delassus blocks of the solver.
     union {
-        struct {           // forward-dynamics workspace: dead once the unconstrained velocity nu and the articulated quantities U, Dinv,
-            float v[NB][6];    // uu, IA0inv exist, i.e. before the first constraint row is built
-            float cb[NB][6];
-            float pA[NB][6];
-            float IA[NB][36];
-            float X[36];
-            float Ia[36];
-            float Tm[36];
-            float pa[6];
+        struct {
+            float Rj[NB][9];
+            float U[NB][6];
+            float Dinv[NB];
+            float uu[NB];
+            float IA0inv[36];
+            union {
+                struct {       // forward-dynamics workspace: dead once the unconstrained velocity nu and U, Dinv, uu, IA0inv exist
+                    float v[NB][6];
+                    float cb[NB][6];
+                    float pA[NB][6];
+                    float IA[NB][36];
+                    float X[36];
+                    float Ia[36];
+                    float Tm[36];
+                    float pa[6];
+                };
+                float Jn[NC][JS];  // Jacobians of the normal rows while the rows are built
+            };
         };
-        float Jn[NC][JS];  // Jacobians of the normal rows while the rows are built; each lane then keeps its row in registers for the solver
-        struct {           // in-block Delassus entries (written after the rows), packed upper triangles: entry (i, j > i) = J_j . B_i at
-            float An[APACK];   // A_OFF(i) + j - i (one pad word in front, so that the finished lanes j <= i of a step read inside the
-            float Af[2][APACK]; // array); the motor block needs none (J = unit vector: B itself)
+        struct {           // in-block Delassus entries, packed upper triangles: entry (i, j > i) = J_j . B_i at A_OFF(i) + j - i (one pad
+            float An[APACK];   // word in front, so that the finished lanes j <= i of a step read inside the array); the motor block
+            float Af[2][APACK]; // needs none (J = unit vector: B itself)
         };
     };
 };
+
+static_assert((sizeof(WarpMemPgs) * WARPS_PER_CTA + 1024) * CTAS_PER_SM <= 233472, "CTAS_PER_SM CTAs of the warp-per-env kernel must fit into the 228 KB of an SM");
 
 // ---------------------------------------------------------------------------------------------
 // response of the generalized velocity to a unit impulse (oracle: impulse_response): spatial impulse
@@ -383,7 +391,7 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
         float D = W.B[j][6 + j];
         float q = W.s[SNK_S_Q + j], qd = W.nu[6 + j];
         float vt = P.kp * (W.target[j] - q) * P.inv_dt + qd + P.kd * (0.f - qd);
-        W.Dg[j] = D; W.invD[j] = 1.f / D; W.rhs[j] = (vt - qd) / D;
+        W.invD[j] = 1.f / D; W.rhs[j] = (vt - qd) / D;
     }
     bool active;
     {
@@ -414,7 +422,7 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
                 float* Jz = (f == 0) ? W.Jn[c] : W.Jf[2 * c + (f - 1)];
 #pragma unroll 1
                 for (int k = 0; k < ND; k++) { Jz[k] = 0.f; W.B[NJ + r][k] = 0.f; }
-                W.Dg[NJ + r] = 0.f; W.invD[NJ + r] = 0.f; W.rhs[NJ + r] = 0.f;
+                W.invD[NJ + r] = 0.f; W.rhs[NJ + r] = 0.f;
             }
         }
 #pragma unroll 1
@@ -463,7 +471,7 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
                 if (pen > 0.f) verr -= pen * P.inv_dt; else perr = -pen * P.erp2 * P.inv_dt;
                 rh = (verr + perr) * iD;
             } else rh = -vrel * iD;
-            W.Dg[NJ + r] = D; W.invD[NJ + r] = iD; W.rhs[NJ + r] = rh;
+            W.invD[NJ + r] = iD; W.rhs[NJ + r] = rh;
         }
     }
     __syncwarp();
@@ -516,15 +524,16 @@ __device__ int tick(WarpMemPgs& W, const DevTables* __restrict__ T, const KParam
     float dv = 0.f;
     float lam_fa[2] = {0.f, 0.f}, lam_fb[2] = {0.f, 0.f}; // friction impulses of contact 16 fb + lane / 2 (both lanes of the pair hold both)
     W.dvs[lane] = 0.f;
-    const float m_rhs = W.rhs[lm], m_iD = W.invD[lm], m_Dg = W.Dg[lm];
-    const float n_rhs = W.rhs[NJ + lane], n_iD = W.invD[NJ + lane], n_Dg = W.Dg[NJ + lane];
+    // the rows' effective masses D (for the residual) are recovered from 1 / D; an all-zero row has D = 0
+    const float m_rhs = W.rhs[lm], m_iD = W.invD[lm], m_Dg = (m_iD != 0.f) ? 1.f / m_iD : 0.f;
+    const float n_rhs = W.rhs[NJ + lane], n_iD = W.invD[NJ + lane], n_Dg = (n_iD != 0.f) ? 1.f / n_iD : 0.f;
     const int pa = lane & ~1; // the lane pair (pa, pa + 1) holds the two friction rows of one contact
     float fa_rhs[2], fa_iD[2], fa_Dg[2], fb_rhs[2], fb_iD[2], fb_Dg[2];
 #pragma unroll
     for (int fb = 0; fb < 2; fb++) {
         const int r = NJ + NC + 32 * fb + pa;
-        fa_rhs[fb] = W.rhs[r]; fa_iD[fb] = W.invD[r]; fa_Dg[fb] = W.Dg[r];
-        fb_rhs[fb] = W.rhs[r + 1]; fb_iD[fb] = W.invD[r + 1]; fb_Dg[fb] = W.Dg[r + 1];
+        fa_rhs[fb] = W.rhs[r]; fa_iD[fb] = W.invD[r]; fa_Dg[fb] = (fa_iD[fb] != 0.f) ? 1.f / fa_iD[fb] : 0.f;
+        fb_rhs[fb] = W.rhs[r + 1]; fb_iD[fb] = W.invD[r + 1]; fb_Dg[fb] = (fb_iD[fb] != 0.f) ? 1.f / fb_iD[fb] : 0.f;
     }
     const float maximp = P.maximp, mu = P.mu;
     const bool cone = P.cone != 0;
