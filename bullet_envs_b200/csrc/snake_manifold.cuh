@@ -44,8 +44,8 @@ struct ManRows {
 // prefetch cannot (the first version of this kernel spent 70 % of its time waiting for exactly these loads).  Ring word v of slot s of
 // thread t: ring[(s * MAN_ROW_V4 + v) * MAN_THREADS + t] -- consecutive threads on consecutive 16 B words, conflict free.
 #define MAN_THREADS 128
-#define MAN_MINB 2
-#define MAN_RING 8
+#define MAN_MINB 3
+#define MAN_RING 6
 #define MAN_RING_BYTES (MAN_RING * MAN_ROW_V4 * MAN_THREADS * 16)
 __device__ __forceinline__ void man_cp16(float4* smem_dst, const float4* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
@@ -312,16 +312,17 @@ __device__ void man_tick(const ExTables& T, const KParams& P, const ManRows& R, 
             if (k < np) { man_cp16(ring + (k * MAN_ROW_V4) * MAN_THREADS, &R.at(k, 0)); man_cp16(ring + (k * MAN_ROW_V4 + 1) * MAN_THREADS, &R.at(k, 1)); }
             man_commit();
         }
+        int sk = 0; // ring slot of row k; row k + MAN_RING - 1 goes into the slot row k - 1 has just left
 #pragma unroll 1
         for (int k = 0; k < np; k++) {
             {
-                const int kn = k + MAN_RING - 1, sn = kn & (MAN_RING - 1);
+                const int kn = k + MAN_RING - 1, sn = (sk == 0) ? MAN_RING - 1 : sk - 1;
                 if (kn < np) { man_cp16(ring + (sn * MAN_ROW_V4) * MAN_THREADS, &R.at(kn, 0)); man_cp16(ring + (sn * MAN_ROW_V4 + 1) * MAN_THREADS, &R.at(kn, 1)); }
                 man_commit();
                 man_wait<MAN_RING - 1>();
             }
-            const int sk = k & (MAN_RING - 1);
             const float4 x0 = ring[(sk * MAN_ROW_V4) * MAN_THREADS], x1 = ring[(sk * MAN_ROW_V4 + 1) * MAN_THREADS];
+            sk = (sk == MAN_RING - 1) ? 0 : sk + 1;
             const float ln = x0.x, rx = x0.y, ry = x0.z, idn = x1.x;
             const float p = ln + x1.y;
             float jd = fmaf(dw.x, ry, dV.z);
@@ -347,10 +348,11 @@ __device__ void man_tick(const ExTables& T, const KParams& P, const ManRows& R, 
             }
             man_commit();
         }
+        sk = 0;
 #pragma unroll 1
         for (int k = 0; k < np; k++) {
             {
-                const int kn = k + MAN_RING - 1, sn = kn & (MAN_RING - 1);
+                const int kn = k + MAN_RING - 1, sn = (sk == 0) ? MAN_RING - 1 : sk - 1;
                 if (kn < np) {
 #pragma unroll
                     for (int v = 0; v < MAN_ROW_V4; v++) if (v != 1) man_cp16(ring + (sn * MAN_ROW_V4 + v) * MAN_THREADS, &R.at(kn, v));
@@ -358,7 +360,8 @@ __device__ void man_tick(const ExTables& T, const KParams& P, const ManRows& R, 
                 man_commit();
                 man_wait<MAN_RING - 1>();
             }
-            const float4* rk = ring + ((k & (MAN_RING - 1)) * MAN_ROW_V4) * MAN_THREADS;
+            const float4* rk = ring + (sk * MAN_ROW_V4) * MAN_THREADS;
+            sk = (sk == MAN_RING - 1) ? 0 : sk + 1;
             const float4 x0 = rk[0], x2 = rk[2 * MAN_THREADS], x3 = rk[3 * MAN_THREADS], x4 = rk[4 * MAN_THREADS];
             const float rx = x0.y, ry = x0.z, rz = x0.w, la = x4.x, lb = x4.y;
             const float pa = la + x4.z, pb = lb + x4.w, lim = mu * x0.x;
