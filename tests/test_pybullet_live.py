@@ -60,3 +60,48 @@ def test_motor_law_and_tick_counts(world):
         assert abs(int(ot[0]) - ticks) <= 1
     pos, _ = p.getBasePositionAndOrientation(snake)
     assert np.abs(np.array(pos) - o.observe()[0, 48:51]).max() < 0.05
+
+
+def test_which_variant_matches_pybullet(world, capsys):
+    """The two open questions of DESIGN.md section 4, answered wherever PyBullet imports: runs the same 10 env-steps in PyBullet and in
+    the three variants of the oracle that have a CUDA twin -- one point per cylinder with the motor rows eliminated (the default), the same
+    with persistent manifolds + warm start 0.1 (snk_set_manifold), and Bullet-order motor rows (motor_solver = 0) -- and prints the base-position and
+    reward-relevant distances -- the combination with the smallest one is the configuration to ship as the default."""
+    p, snake = world
+    model = build_model()
+    motors = model.motor_joint_indices
+    rng = np.random.default_rng(1)
+    acts = rng.uniform(-1, 1, (10, 8))
+    ref = []
+    for a in acts:
+        tgt = np.zeros(16); tgt[1::2] = a * np.pi / 6
+        ticks = 0
+        while True:
+            q = np.array([p.getJointState(snake, j)[0] for j in motors])
+            if not np.linalg.norm(tgt - q) > 0.05 or ticks > 40:
+                break
+            p.setJointMotorControlArray(snake, motors, p.POSITION_CONTROL, targetPositions=list(tgt), forces=[np.inf] * 16)
+            p.stepSimulation()
+            ticks += 1
+        pos, quat = p.getBasePositionAndOrientation(snake)
+        ref.append((ticks, np.array(pos), np.array(quat)))
+    rows = []
+    for solver in (2, 0):
+        for man in (False, True):
+            if man and solver == 0:
+                continue  # the oracle's manifolds live in the exact tick
+            o = Oracle(1, default_params(motor_solver=solver))
+            if man:
+                o.set_manifold(True, 0.1)
+            o.reset()
+            dt, dp = 0, 0.0
+            for a, (ticks, pos, quat) in zip(acts, ref):
+                ob, _, _, ot = o.step(a[None, :])
+                dt += abs(int(ot[0]) - ticks)
+                dp = max(dp, float(np.abs(ob[0, 48:51] - pos).max()))
+            rows.append(("motor rows %s, %s" % ("eliminated" if solver else "Bullet order", "manifolds + warm 0.1" if man else "one point per cylinder"), dt, dp))
+    with capsys.disabled():
+        print("\nvariant                                              sum |tick diff|   max base position diff over 10 env-steps [m]")
+        for name, dt, dp in rows:
+            print("%-55s %6d %12.4f" % (name, dt, dp))
+    assert min(r[2] for r in rows) < 0.1
