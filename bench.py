@@ -429,13 +429,26 @@ def run_ours(args):
             "clocks": clocks,
         }
         line.update(extra)
-        if world == 1:
+        # The legs below are side measurements next to the headline: a failure of one of them is reported in its key and must not take
+        # the line down with it.
+        def side_leg(key, fn):
+            try:
+                line[key] = fn()
+            except Exception as ex:  # noqa: BLE001
+                line[key] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+                try:
+                    torch.cuda.synchronize()
+                except Exception:  # noqa: BLE001
+                    pass
+
+        def leg_hbm():
             # the kernels of the path for which HBM IS the roofline: observation epilogue, state copy, GAE scan
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import bench_hbm_kernels
             hb = bench_hbm_kernels.measure(env, iters=20, with_reset=False, peak=peak)
-            line["hbm_bound_kernels"] = {k["kernel"]: {"GB/s": k["GB/s"], "frac": k["frac_of_measured_hbm_peak"], "ms": k["ms"]} for k in hb["kernels"]}
-        if world == 1 and not args.no_bullet_order:
+            return {k["kernel"]: {"GB/s": k["GB/s"], "frac": k["frac_of_measured_hbm_peak"], "ms": k["ms"]} for k in hb["kernels"]}
+
+        def leg_bullet_order():
             # the cost of deviation D4 being wrong: the same step with the motor rows relaxed inside the PGS in Bullet's order
             # (motor_solver = 0, warp-per-env kernel), 65 536 environments
             nb = 65536
@@ -447,10 +460,13 @@ def run_ours(args):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); eb.step(ab[1]); eb.step(ab[2]); b.record(); torch.cuda.synchronize()
             msb = a.elapsed_time(b) / 2
-            line["bullet_order"] = {"envs": nb, "env_steps_per_s": nb / (msb * 1e-3), "ms_per_step": msb, "ticks_per_s": eb.counters()["ticks"] / (msb * 1e-3),
-                                    "kernel": "snk_env_kernel (warp per environment, 16 motor + 96 contact rows, Bullet's row order, block Gauss-Seidel)",
-                                    "ratio_to_value": nb / (msb * 1e-3) / value}
+            out = {"envs": nb, "env_steps_per_s": nb / (msb * 1e-3), "ms_per_step": msb, "ticks_per_s": eb.counters()["ticks"] / (msb * 1e-3),
+                   "kernel": "snk_env_kernel (warp per environment, 16 motor + 96 contact rows, Bullet's row order, block Gauss-Seidel)",
+                   "ratio_to_value": nb / (msb * 1e-3) / value}
             eb.close()
+            return out
+
+        def leg_manifold():
             # the cost of deviation D1: the same step with Bullet's persistent contact manifolds and warm starting (snk_set_manifold,
             # csrc/snake_manifold.cuh), 262 144 environments from the reset pose
             nm = 262144
@@ -464,12 +480,19 @@ def run_ours(args):
             a.record(); em.step(am[2]); em.step(am[3]); em.step(am[4]); b.record(); torch.cuda.synchronize()
             msm = a.elapsed_time(b) / 3
             pts, tkm = em.manifold_stats()
-            line["manifold"] = {"envs": nm, "env_steps_per_s": nm / (msm * 1e-3), "ms_per_step": msm, "ticks_per_s": tkm / (msm * 1e-3),
-                                "contact_points_per_tick": pts / max(tkm, 1), "warm_start": 0.1,
-                                "kernel": "snk_man_step_kernel (thread per environment, 4-slot manifold per cylinder, rows in global memory streamed "
-                                          "through a cp.async ring)",
-                                "ratio_to_value": nm / (msm * 1e-3) / value}
+            out = {"envs": nm, "env_steps_per_s": nm / (msm * 1e-3), "ms_per_step": msm, "ticks_per_s": tkm / (msm * 1e-3),
+                   "contact_points_per_tick": pts / max(tkm, 1), "warm_start": 0.1,
+                   "kernel": "snk_man_step_kernel (thread per environment, 4-slot manifold per cylinder, rows in global memory streamed through a "
+                             "cp.async ring)",
+                   "ratio_to_value": nm / (msm * 1e-3) / value}
             em.close()
+            return out
+
+        if world == 1:
+            side_leg("hbm_bound_kernels", leg_hbm)
+        if world == 1 and not args.no_bullet_order:
+            side_leg("bullet_order", leg_bullet_order)
+            side_leg("manifold", leg_manifold)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             nb = 2048 * threads  # ~10 s of CPU work per leg

@@ -337,7 +337,7 @@ int snk_set_manifold(snk_handle* h, int on, double warm_start) {
             cudaGetLastError();
             cudaFree(h->man_cache); cudaFree(h->man_scratch);
             h->man_cache = nullptr; h->man_scratch = nullptr; h->manifold = false;
-            return fail(SNK_E_NOMEM, "snk_set_manifold: out of device memory (4 224 B per environment + 582 MB of row tables)%s");
+            return fail(SNK_E_NOMEM, "snk_set_manifold: out of device memory (4 224 B per environment + 388 MB of row tables)%s");
         }
     }
     CU(cudaMemset(h->man_cache, 0, cache_bytes)); // empty caches, like a freshly loaded world

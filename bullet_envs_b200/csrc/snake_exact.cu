@@ -769,6 +769,16 @@ cudaError_t snk_exact_configure(const ExTables* host_tables) {
     if (e == cudaSuccess) e = set_smem(snk_hyb_rollout_kernel<false>, sizeof(StepSmemH));
     if (e == cudaSuccess) e = set_smem(snk_man_step_kernel<true>, MAN_RING_BYTES);
     if (e == cudaSuccess) e = set_smem(snk_man_step_kernel<false>, MAN_RING_BYTES);
+    // MAN_MINB CTAs x MAN_RING_BYTES of ring per SM and the rest of the 256 KB as L1 (state records, contact caches, local arrays): the
+    // carveout is requested explicitly, otherwise it depends on which kernel ran before (a larger one costs L1: 3 CTAs x 60 KB ran 277 ms
+    // against 228 ms for 2 x 60 KB at 262 144 environments)
+    {
+        int pct = (int)((MAN_MINB * (MAN_RING_BYTES + 1024) * 100 + 233471) / 233472);
+        if (getenv("SNK_MAN_CARVEOUT")) pct = atoi(getenv("SNK_MAN_CARVEOUT"));
+        if (pct > 100) pct = 100;
+        if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)snk_man_step_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)snk_man_step_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
     if (e != cudaSuccess) return e;
     int per_sm = 0;
     e = cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev);

@@ -44,8 +44,12 @@ struct ManRows {
 // prefetch cannot (the first version of this kernel spent 70 % of its time waiting for exactly these loads).  Ring word v of slot s of
 // thread t: ring[(s * MAN_ROW_V4 + v) * MAN_THREADS + t] -- consecutive threads on consecutive 16 B words, conflict free.
 #define MAN_THREADS 128
-#define MAN_MINB 3
+#ifndef MAN_MINB
+#define MAN_MINB 2
+#endif
+#ifndef MAN_RING
 #define MAN_RING 6
+#endif
 #define MAN_RING_BYTES (MAN_RING * MAN_ROW_V4 * MAN_THREADS * 16)
 __device__ __forceinline__ void man_cp16(float4* smem_dst, const float4* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");

@@ -201,7 +201,7 @@ int snk_rollout_linear(snk_handle* h, const float* weights_dev, const float* mea
  * handle's snk_step / snk_step_host* to the manifold kernel -- per cylinder the support vertex of the 32-gon hull feeds a
  * 4-slot contact cache with Bullet's add / replace / refresh / breaking rules (up to 128 contact points per environment), and
  * the cached normal impulses x warm_start (Bullet: 0.1; 0 = off) start the solver.  The call (re)allocates and CLEARS the caches
- * (4 224 B per environment + 582 MB of row tables per device); they survive soft resets like Bullet's (Q10).  on == 0 returns to
+ * (4 224 B per environment + 388 MB of row tables per device); they survive soft resets like Bullet's (Q10).  on == 0 returns to
  * the default one-point-per-cylinder tick (deviation D1) and frees the memory.  Only with the exact motor solver; snk_step_trace,
  * snk_tick and snk_rollout_linear are refused while it is on.  Synchronises the device. */
 int snk_set_manifold(snk_handle* h, int on, double warm_start);
