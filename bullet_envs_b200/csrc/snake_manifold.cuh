@@ -59,7 +59,7 @@ template <int N>
 __device__ __forceinline__ void man_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // btPersistentManifold::sortCachedPoints: the slot a new point replaces in a full cache (oracle: man_sort_cached)
-__device__ __forceinline__ int man_sort_cached(const float* mc, V3 lp, float dist) {
+__device__ __forceinline__ int man_sort_cached(const float (&mc)[MAN_CYL_W], V3 lp, float dist) {
     int deepest = -1;
     float maxpen = dist;
 #pragma unroll
@@ -77,14 +77,17 @@ __device__ __forceinline__ int man_sort_cached(const float* mc, V3 lp, float dis
         res[k] = dot(cr, cr);
     }
     int best = 0;
+    float bestr = res[0];
 #pragma unroll
-    for (int k = 1; k < 4; k++) if (res[k] > res[best]) best = k;
+    for (int k = 1; k < 4; k++) if (res[k] > bestr) { bestr = res[k]; best = k; }
     return best;
 }
 
 // One collision-detection pass of cylinder c (oracle: manifold_update).  R / pb: frame of the cylinder's body (pb relative to the base
-// origin), p0: base origin (world).  mc: the cylinder's 4 slots (local copy), n: its point count.
-__device__ __forceinline__ void man_update(const ExTables& T, int c, const M3& R, V3 pb, V3 p0, float* mc, int& n) {
+// origin), p0: base origin (world).  mc: the cylinder's 4 slots, n: its point count.  Every slot index below is a compile-time constant
+// (unrolled loops, selects instead of pointers), so that the 32 words stay in REGISTERS: as a dynamically indexed local array they cost
+// 16 GB of local-memory traffic per launch and 33 KB of the L1 that the state records and caches need.
+__device__ __forceinline__ void man_update(const ExTables& T, int c, const M3& R, V3 pb, V3 p0, float (&mc)[MAN_CYL_W], int& n) {
     const float brk = T.cbrk[c], mar = T.cmar[c], rad = T.crad[c], hl = fabsf(T.ceh[c]);
     const float* F = T.cfr[c];
     // world-z of the body-frame vector ccen + cfr (r sin t, r cos t, +-hl):  z0 + g.x r sin t + g.y r cos t +- g.z hl
@@ -108,31 +111,46 @@ __device__ __forceinline__ void man_update(const ExTables& T, int c, const M3& R
         const V3 lp = mulT(R, rel);
         int idx = -1;
         float shortest = brk * brk;
-        for (int i = 0; i < n; i++) {
-            const V3 d = mk(mc[i * MAN_SLOT_W] - lp.x, mc[i * MAN_SLOT_W + 1] - lp.y, mc[i * MAN_SLOT_W + 2] - lp.z);
-            const float d2 = dot(d, d);
-            if (d2 < shortest) { shortest = d2; idx = i; }
-        }
-        float imp = 0.f;
-        if (idx >= 0) imp = mc[idx * MAN_SLOT_W + 6]; // replaceContactPoint keeps the cached impulse
-        else if (n < MAN_SLOTS) idx = n++;
-        else idx = man_sort_cached(mc, lp, dist);
-        float* s = mc + idx * MAN_SLOT_W;
-        s[0] = lp.x; s[1] = lp.y; s[2] = lp.z; s[3] = dist;
-        s[4] = p0.x + pb.x + rel.x; s[5] = p0.y + pb.y + rel.y; s[6] = imp; s[7] = 0.f;
-    }
-    for (int i = n - 1; i >= 0; i--) { // refreshContactPoints
-        float* s = mc + i * MAN_SLOT_W;
-        const V3 w = mul(R, mk(s[0], s[1], s[2]));
-        const V3 pos = p0 + pb + w;
-        s[3] = pos.z;
-        const float dx = s[4] - pos.x, dy = s[5] - pos.y;
-        if (s[3] > brk || dx * dx + dy * dy > brk * brk) {
 #pragma unroll
-            for (int q = 0; q < MAN_SLOT_W; q++) s[q] = mc[(n - 1) * MAN_SLOT_W + q];
-            n--;
-        }
+        for (int i = 0; i < MAN_SLOTS; i++)
+            if (i < n) {
+                const V3 d = mk(mc[i * MAN_SLOT_W] - lp.x, mc[i * MAN_SLOT_W + 1] - lp.y, mc[i * MAN_SLOT_W + 2] - lp.z);
+                const float d2 = dot(d, d);
+                if (d2 < shortest) { shortest = d2; idx = i; }
+            }
+        float imp = 0.f;
+        if (idx >= 0) { // replaceContactPoint keeps the cached impulse
+#pragma unroll
+            for (int i = 0; i < MAN_SLOTS; i++) if (idx == i) imp = mc[i * MAN_SLOT_W + 6];
+        } else if (n < MAN_SLOTS) idx = n++;
+        else idx = man_sort_cached(mc, lp, dist);
+        const float ax = p0.x + pb.x + rel.x, ay = p0.y + pb.y + rel.y;
+#pragma unroll
+        for (int i = 0; i < MAN_SLOTS; i++)
+            if (idx == i) {
+                mc[i * MAN_SLOT_W] = lp.x; mc[i * MAN_SLOT_W + 1] = lp.y; mc[i * MAN_SLOT_W + 2] = lp.z; mc[i * MAN_SLOT_W + 3] = dist;
+                mc[i * MAN_SLOT_W + 4] = ax; mc[i * MAN_SLOT_W + 5] = ay; mc[i * MAN_SLOT_W + 6] = imp; mc[i * MAN_SLOT_W + 7] = 0.f;
+            }
     }
+#pragma unroll
+    for (int i = MAN_SLOTS - 1; i >= 0; i--) // refreshContactPoints
+        if (i < n) {
+            const V3 w = mul(R, mk(mc[i * MAN_SLOT_W], mc[i * MAN_SLOT_W + 1], mc[i * MAN_SLOT_W + 2]));
+            const V3 pos = p0 + pb + w;
+            mc[i * MAN_SLOT_W + 3] = pos.z;
+            const float dx = mc[i * MAN_SLOT_W + 4] - pos.x, dy = mc[i * MAN_SLOT_W + 5] - pos.y;
+            if (pos.z > brk || dx * dx + dy * dy > brk * brk) { // removeContactPoint: the last point takes the slot
+                const int last = n - 1;
+#pragma unroll
+                for (int q = 0; q < MAN_SLOT_W; q++) {
+                    float v = mc[i * MAN_SLOT_W + q];
+#pragma unroll
+                    for (int l = i + 1; l < MAN_SLOTS; l++) if (last == l) v = mc[l * MAN_SLOT_W + q];
+                    mc[i * MAN_SLOT_W + q] = v;
+                }
+                n--;
+            }
+        }
 }
 
 // -----------------------------------------------------------------------------------------------
@@ -232,7 +250,9 @@ __device__ void man_tick(const ExTables& T, const KParams& P, const ManRows& R, 
             V3 l1 = mk(-Rl.m[3] * P.aniso[0], -Rl.m[4] * P.aniso[1], -Rl.m[5] * P.aniso[2]);
             V3 l2 = mk(Rl.m[0] * P.aniso[0], Rl.m[1] * P.aniso[1], Rl.m[2] * P.aniso[2]);
             V3 d1 = mul(Rl, l1), d2 = mul(Rl, l2);
-            for (int s = 0; s < n; s++) {
+#pragma unroll
+            for (int s = 0; s < MAN_SLOTS; s++) {
+                if (s >= n) break;
                 const V3 rp = mul(c.R, mk(mc[s * MAN_SLOT_W], mc[s * MAN_SLOT_W + 1], mc[s * MAN_SLOT_W + 2])); // point relative to the body origin
                 const V3 pc = c.p + rp;
                 const V3 uJ = vJ + cross(wJ, rp);
