@@ -12,10 +12,12 @@
 //
 // Data placement.  128 points x 20 words do not fit on chip next to 255 other environments, so this variant keeps the row table in
 // GLOBAL memory: every resident thread owns a slice of a scratch array laid out [warp][point][float4 word][lane] (a warp's 32
-// lanes read 512 consecutive bytes; the table of a running environment stays in L1/L2), and the per-environment caches live in HBM
-// as 32 cylinders x 4 slots x 8 floats + 32 counts = 4 224 B.  No tensor memory, so no warp-convergence requirement: a thread
-// runs its own environment's tick loop and leaves its solver loop when ITS residual falls below the threshold.  One environment
-// per thread, persistent grid, grid-stride over the batch.  This is the parity-first kernel of the row, not a tuned one.
+// lanes on 512 consecutive bytes; ~100 MB are live at a time, most of it in L2), streamed through a per-thread cp.async ring in shared
+// memory by the solver sweeps (below), and the per-environment caches live in HBM as 32 cylinders x 4 slots x 8 floats + 32 counts =
+// 4 224 B (only the occupied slots move).  No tensor memory, so no warp-convergence requirement: a thread leaves its solver loop
+// when ITS residual falls below the threshold.  One environment per thread, persistent grid; as in the benchmarked kernel the unit
+// the lanes of a warp share is one physics tick, and a thread whose env-step has ended takes the next environment from a global
+// counter.  Measured and profiled in DESIGN.md section 5 / profiles/README.md (1.1 M env-steps/s at 262 144 environments).
 #pragma once
 #include "snake_exact_core.cuh"
 
