@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU job 21: end-of-round validation: whole GPU suite, smoke, default bench line (with the bullet_order and manifold legs), reference arm, launch list
+# GPU job 21: end-of-round validation (re-run after every later change): whole GPU suite, smoke, default bench line (with the bullet_order and manifold legs), reference arm, launch list
 timeout 1500 python -m pytest tests -m gpu -q --timeout=1200 -p no:cacheprovider 2>&1 | tail -8 > gpurun_out/t21.log
 tail -3 gpurun_out/t21.log
 timeout 200 python __graft_entry__.py smoke 2>&1 | tail -1
