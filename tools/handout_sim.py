@@ -9,9 +9,10 @@ scheduler needs about 0.68 of the time per iteration).  Policies:
   two   the launcher's two pools: with n = k L + r, the first ceil(r / 32) warps draw k + 1 env-steps each from the SHORTEST
         (k + 1) r environments, the others k from the longest ("Balanced last wave")
 
-and the bound no hand-out of whole env-steps can beat: r lanes must run k + 1 env-steps, and giving them the k + 1 shortest jobs
-each still leaves them with `bound` iterations, so the loss against n T / L is a property of the batch size and of the tick
-distribution, not of the policy.  Used for DESIGN.md section 6 (why 131 072 environments per GPU run at 91 % of the 2^20 rate).
+and a reference figure for the integrality of whole env-steps: r lanes must run k + 1 env-steps, and the (k + 1) r SHORTEST jobs spread
+evenly over them already cost `ref` iterations each -- with the narrow tick distribution of this workload (30.1 +- 2.2) the loss against
+n T / L is a property of the batch size, not of the policy (the dynamic pools get slightly below `ref` because warps switch pools and a
+lone warp iterates faster).  Used for DESIGN.md section 6 (why 131 072 environments per GPU run at 91 % of the 2^20 rate).
 
     python tools/handout_sim.py 65536,100000,131072,200000,262144
 """
@@ -70,7 +71,7 @@ def run(long_list, short_list, short_warps, lone=0.68):
 def main():
     L = SM * WPS * 32
     sizes = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "65536,100000,131072,200000,262144").split(",")]
-    print("%8s %7s %5s | %17s | %17s | %s" % ("envs", "ideal", "k+r/L", "longest first", "two pools", "bound for whole env-steps"))
+    print("%8s %7s %5s | %17s | %17s | %s" % ("envs", "ideal", "k+r/L", "longest first", "two pools", "k + 1 shortest jobs on r lanes"))
     for n in sizes:
         rng = np.random.default_rng(0)
         sc = np.sort(np.maximum(ticks_sample(n, rng), 1))[::-1]
