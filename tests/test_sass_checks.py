@@ -54,3 +54,22 @@ def test_bank_conflict_counter_finds_the_solver_loops(sass):
     assert len(found) == 1, found
     n, conflicts, reuse, nfp = found[0]
     assert n <= 150 and conflicts / 2 < 17.7, found
+
+
+def test_manifold_kernel_streams_rows_with_async_copies(sass):
+    """snk_man_step_kernel: the solver sweeps fill their shared-memory ring with cp.async (LDGSTS, 16 bytes, L2 only) and wait per group
+    (LDGDEPBAR / DEPBAR); no tensor-memory instruction (the kernel has no warp-convergence requirement)"""
+    txt = open(sass).read()
+    k = [p for p in txt.split("Function : ") if p.startswith("_Z19snk_man_step_kernelILb1EE")][0]
+    assert k.count("LDGSTS") >= 12, k.count("LDGSTS")          # 2 words per normal row + 4 per friction row, prologue + loop
+    assert "LDGDEPBAR" in k and "DEPBAR" in k
+    assert "LDTM" not in k and "STTM" not in k
+
+
+def test_bullet_order_kernel_is_a_branch_free_block_sweep(sass):
+    """snk_env_kernel (motor_solver = 0): the block Gauss-Seidel broadcasts one impulse change per row with an indexed shuffle (no
+    butterfly in the solver loops: SHFL.BFLY would be the round-1 reduction) and selects instead of branching on the clamps"""
+    txt = open(sass).read()
+    k = [p for p in txt.split("Function : ") if p.startswith("_Z14snk_env_kernelI10WarpMemPgsLb0ELi1ELi9EE")][0]
+    assert k.count("SHFL.IDX") >= 20 and k.count("SHFL.BFLY") <= 8, (k.count("SHFL.IDX"), k.count("SHFL.BFLY"))
+    assert k.count("REDUX") >= 1                                # the residual's warp maximum
