@@ -10,7 +10,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <time.h>
+
+#include <atomic>
 #include <new>
+#include <vector>
 
 #include "snake_host.h"
 
@@ -27,7 +31,8 @@ void snk_exact_release();
 const char* snk_exact_variant();
 cudaError_t snk_exact_launch_step(const KParams& P, float* state, float* tgt_scratch, const float* actions, float* obs, float* rew, uint8_t* done,
                                   int32_t* ticks, unsigned long long* counters, uint8_t* bucket, int32_t* order, int64_t n, cudaStream_t st,
-                                  int* launches);
+                                  int* launches, int flag_rows);
+bool snk_exact_row_flags_supported();
 cudaError_t snk_exact_launch_rollout(const KParams& P, float* state, float* tgt_scratch, const float* weights, const float* mean, const float* inv_std,
                                      const float* noise, int n_steps, float* returns, float* trace, int32_t* queue, int32_t* done_steps,
                                      unsigned long long* counters, int64_t n, cudaStream_t st);
@@ -119,14 +124,14 @@ static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; 
 // One env-step of the environments [off, off + cnt) (default: all).  act / obs / rew / done / ticks point at the rows of environment
 // `off`.  The per-launch scheduler words of `counters` must be zero; the statistics words [0..3] accumulate.
 static cudaError_t launch_step(snk_handle* h, const float* act, float* obs, float* rew, uint8_t* done, int32_t* ticks, cudaStream_t st, int64_t off = 0,
-                               int64_t cnt = -1) {
+                               int64_t cnt = -1, int flag_rows = 0) {
     if (cnt < 0) cnt = h->n;
     int launches = 1;
     cudaError_t e = h->manifold ? snk_man_launch_step(h->P, h->state + off * SNK_STATE_STRIDE, h->tgt + off * NJ,
                                                       h->man_cache + off * (int64_t)snk_man_cache_floats(), h->man_scratch, h->man_warm, act, obs, rew, done,
                                                       ticks, h->counters, cnt, st)
                     : h->exact ? snk_exact_launch_step(h->P, h->state + off * SNK_STATE_STRIDE, h->tgt + off * NJ, act, obs, rew, done, ticks, h->counters,
-                                                     h->bucket + off, h->order + off, cnt, st, &launches)
+                                                     h->bucket + off, h->order + off, cnt, st, &launches, flag_rows)
                              : snk_pgs_launch_step(h->T, h->P, h->state + off * SNK_STATE_STRIDE, act, obs, rew, done, ticks, h->counters, cnt, st);
     h->launches += launches;
     mark_device_work(h, st);
@@ -136,7 +141,7 @@ static cudaError_t launch_step(snk_handle* h, const float* act, float* obs, floa
 #include "snake_hostpool.h"
 
 template <class F>
-static void parallel_chunks(size_t n, F f) { HostPool::get().run(n, std::function<void(size_t, size_t)>(f)); }
+static void parallel_chunks(size_t n, F f, size_t serial_below = (size_t)1 << 16) { HostPool::get().run(n, std::function<void(size_t, size_t)>(f), serial_below); }
 // Touch every page of a caller buffer that is about to be overwritten completely (the fresh arrays numpy hands over are untouched
 // anonymous memory: 470 MB of observations are 115 000 page faults).  Called while the GPU works on the first chunk, so that the faults
 // are not taken inside the widening of the last chunk, which nothing hides.  SNK_HOST_PREFAULT=0 disables it.
@@ -467,15 +472,100 @@ int snk_step_host(snk_handle* h, const float* actions_host, float* obs_host, flo
 // The call the reference's numpy callers make (ppo/train.py:122, ars/train.py:99): float64 arrays in and out, as
 // SubprocVecEnv.step returns them.  Actions are narrowed into the handle's page-locked buffer, the kernel runs on the
 // mapped page-locked buffers (see snk_step_host), and the results are widened into the caller's arrays by a few threads.
+// SNK_HOST_FLAGS=0: snk_step_host_f64 takes the chunk-pipelined path even where the flag-driven one is available (ablation)
+static bool row_flags_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SNK_HOST_FLAGS"); v = !(e && e[0] == '0'); }
+    return v != 0;
+}
+
+// snk_step_host_f64, flag-driven: ONE launch for the whole batch, writing into the handle's mapped page-locked buffers; the kernel
+// posts an environment's ticks word last, behind a system-wide fence (HandOut::flag_rows), and the host threads -- each owning a
+// contiguous range of environments -- widen every row into the caller's float64 arrays as soon as its ticks word turns up, while
+// the launch is still running.  Only the narrowing of the actions (before the launch) and the rows of the last few lanes to finish
+// are not hidden behind the kernel, and the batch is not cut into smaller launches (each of which would pay its own last wave).
+static int step_host_f64_flags(snk_handle* h, const double* actions_host, double* obs_host, double* rew_host, uint8_t* done_host, int32_t* ticks_host) {
+    const size_t n = (size_t)h->n, ad = (size_t)h->P.actdim;
+    cudaStream_t st = h->hstream;
+    float* ha = h->h_act;
+    int32_t* ht = h->h_ticks;
+    const size_t grain = 4096; // environments; below it the calling thread works alone
+    parallel_chunks(n, [=](size_t b, size_t e) {
+        for (size_t i = b * ad; i < e * ad; i++) ha[i] = (float)actions_host[i];
+        for (size_t i = b; i < e; i++) ht[i] = -1; // "row not there yet" (tick counts are 0...41)
+    }, grain);
+    CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
+    CU(launch_step(h, h->h_act, h->h_obs, h->h_rew, h->h_done, h->h_ticks, st, 0, -1, 1));
+    const float* ho = h->h_obs;
+    const float* hr = h->h_rew;
+    const uint8_t* hd = h->h_done;
+    // 0: launch in flight, 1: launch finished (every row is there), 2: the launch failed, 3: finished with a row missing (cannot happen)
+    std::atomic<int> launch_state{0};
+    std::atomic<int> sync_error{(int)cudaSuccess};
+    static int prefault = -1;
+    if (prefault < 0) { const char* e = getenv("SNK_HOST_PREFAULT"); prefault = !(e && e[0] == '0'); }
+    parallel_chunks(n, [&, ho, hr, hd, ht](size_t b, size_t e) {
+        const bool leader = b == 0; // the calling thread: the one with the CUDA context
+        if (prefault && (e - b) >= grain) { // fresh numpy arrays are untouched anonymous memory: take the page faults now, not row by row
+            volatile char* p0 = (volatile char*)(obs_host + b * SNK_OBS_DIM);
+            for (size_t k = 0; k < (e - b) * SNK_OBS_DIM * sizeof(double); k += 4096) p0[k] = 0;
+            volatile char* p1 = (volatile char*)(rew_host + b);
+            for (size_t k = 0; k < (e - b) * sizeof(double); k += 4096) p1[k] = 0;
+        }
+        std::vector<uint32_t> pend(e - b);
+        for (size_t k = 0; k < e - b; k++) pend[k] = (uint32_t)(b + k);
+        size_t np = e - b;
+        while (np) {
+            const int before = launch_state.load(std::memory_order_acquire);
+            size_t w = 0;
+            for (size_t k = 0; k < np; k++) {
+                const size_t i = pend[k];
+                const int32_t t = *(volatile const int32_t*)(ht + i);
+                if (t < 0) { pend[w++] = (uint32_t)i; continue; }
+                std::atomic_thread_fence(std::memory_order_acquire); // the row was posted before its ticks word
+                const float* src = ho + i * SNK_OBS_DIM;
+                double* dst = obs_host + i * SNK_OBS_DIM;
+                for (int c = 0; c < SNK_OBS_DIM; c++) dst[c] = (double)src[c];
+                rew_host[i] = (double)hr[i];
+                done_host[i] = hd[i];
+                if (ticks_host) ticks_host[i] = t;
+            }
+            const size_t converted = np - w;
+            np = w;
+            if (!np) break;
+            if (before == 2) return;
+            if (before == 1) { launch_state.store(3, std::memory_order_release); return; }
+            if (leader) {
+                const cudaError_t q = cudaStreamQuery(st);
+                if (q == cudaSuccess) launch_state.store(1, std::memory_order_release);
+                else if (q != cudaErrorNotReady) { sync_error.store((int)q); launch_state.store(2, std::memory_order_release); }
+            }
+            if (converted == 0) { struct timespec ts = {0, 30000}; nanosleep(&ts, nullptr); } // nothing new: leave the memory bus alone for 30 us
+        }
+        if (leader && launch_state.load(std::memory_order_acquire) == 0) { // the other threads rely on the leader to notice a failed launch
+            const cudaError_t q = cudaStreamSynchronize(st);
+            if (q == cudaSuccess) launch_state.store(1, std::memory_order_release);
+            else { sync_error.store((int)q); launch_state.store(2, std::memory_order_release); }
+        }
+    }, grain);
+    const cudaError_t e_sync = cudaStreamSynchronize(st);
+    if (launch_state.load() == 2 || e_sync != cudaSuccess)
+        return fail(SNK_E_CUDA, "snk_step_host_f64: the env-step launch failed: %s", cudaGetErrorString(e_sync != cudaSuccess ? e_sync : (cudaError_t)sync_error.load()));
+    if (launch_state.load() == 3) return fail(SNK_E_CUDA, "snk_step_host_f64: the launch finished without posting every row%s");
+    return 0;
+}
+
 int snk_step_host_f64(snk_handle* h, const double* actions_host, double* obs_host, double* rew_host, uint8_t* done_host, int32_t* ticks_host) {
     if (!h || !actions_host || !obs_host || !rew_host || !done_host) return fail(SNK_E_ARG, "snk_step_host_f64: null pointer%s");
     CU(cudaSetDevice(h->device));
     int rc = ensure_staging(h);
     if (rc) return rc;
     wait_device_work(h);
+    if (zero_copy_enabled() && row_flags_enabled() && h->exact && !h->manifold && snk_exact_row_flags_supported())
+        return step_host_f64_flags(h, actions_host, obs_host, rew_host, done_host, ticks_host);
     const size_t n = (size_t)h->n, ad = (size_t)h->P.actdim;
     cudaStream_t st = h->hstream;
-    // The batch goes through in a few chunks of environments, pipelined: while the GPU steps chunk c the host threads narrow the
+    // (Kernels without row flags -- Bullet-order rows, persistent manifolds, the ablation layouts.)  The batch goes through in a few chunks of environments, pipelined: while the GPU steps chunk c the host threads narrow the
     // actions of chunk c + 1, and while it steps chunk c + 1 they widen the results of chunk c into the caller's arrays -- only the
     // first narrowing and the last widening are not hidden behind the kernel (SNK_HOST_CHUNKS, default 4 from 2^18 environments).
     static int cfg_chunks = -1;

@@ -83,7 +83,8 @@ __device__ __forceinline__ void run_warp(const KParams& P, Rows R, float* __rest
                                          float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks,
                                          unsigned long long* __restrict__ counters, const int32_t* __restrict__ order, int64_t n,
                                          int64_t first_base, int64_t dyn_base, float* __restrict__ tick_obs = nullptr,
-                                         float* __restrict__ tick_links = nullptr, int pool = 0, int64_t n_long = -1, int64_t dyn_base_short = 0) {
+                                         float* __restrict__ tick_links = nullptr, int pool = 0, int64_t n_long = -1, int64_t dyn_base_short = 0,
+                                         bool flag_rows = false) {
     // Hand-out positions: the warp's first 32 are static, [first_base, first_base + 32), laid out warp-major over the
     // grid by the caller so that a batch smaller than the grid's lanes spreads over all SMs (one warp per scheduler
     // before a second one anywhere); every later position comes from a global counter, which starts at dyn_base.
@@ -151,11 +152,14 @@ __device__ __forceinline__ void run_warp(const KParams& P, Rows R, float* __rest
             ex_step_end(cT, P, e, run, &o);
             rew[env] = o.rew;
             done[env] = (uint8_t)o.done;
-            if (ticks) ticks[env] = o.ticks;
             float* go = obs + env * SNK_OBS_DIM; // 224 B row, 16 B aligned: 14 full-sector vector stores
 #pragma unroll 1
             for (int k = 0; k < SNK_OBS_DIM; k += 4)
                 *reinterpret_cast<float4*>(go + k) = make_float4(ex_obs_of(e, k), ex_obs_of(e, k + 1), ex_obs_of(e, k + 2), ex_obs_of(e, k + 3));
+            // flag_rows (snk_step_host_f64): ticks[env] doubles as the environment's "row ready" flag for host threads that convert
+            // the results while the launch is still running -- it goes out last, behind a system-wide fence
+            if (flag_rows) __threadfence_system();
+            if (ticks) ticks[env] = o.ticks;
             c_ticks += (unsigned long long)o.ticks; c_iters += (unsigned long long)o.iters; c_done += o.done; c_bad += o.bad;
             have = false;
         }
@@ -451,6 +455,7 @@ __device__ __forceinline__ RowsH hyb_rows(StepSmemH& S, uint32_t tbase, int warp
 struct HandOut {       // two-pool hand-out of a launch (see snk_hyb_step_kernel); short_warps = 0: one pool, plain longest-first
     int64_t n_long;    // positions [0, n_long) of the longest-first order are the long pool, [n_long, n) the short pool
     int short_warps;   // warps (in warp-major order over the grid) that draw from the short pool
+    int flag_rows;     // != 0: ticks[env] is written last, behind a system fence (the host reads finished rows during the launch)
 };
 
 // TRACE = true: the same kernel with the mode='test' info stream (snk_step_trace) -- a separate instantiation, so the
@@ -488,7 +493,7 @@ snk_hyb_step_kernel(const KParams P, float* __restrict__ state, float* __restric
     }
     if (warp < active_warps) // SNK_EXACT_WARPS (ablation): the other warps take no environments
         run_warp<CONE, RowsH, TRACE>(P, hyb_rows(S, tbase, warp, lane), state, tgt_scratch, actions, obs, rew, done, ticks, counters, order, n, first_base,
-                                     dyn_base, tick_obs, tick_links, pool, H.short_warps > 0 ? H.n_long : -1, dyn_short);
+                                     dyn_base, tick_obs, tick_links, pool, H.short_warps > 0 ? H.n_long : -1, dyn_short, H.flag_rows != 0);
     hyb_tmem_free(tbase, warp);
 }
 
@@ -700,6 +705,9 @@ static int warps_for(int64_t n, int dev) {
     return (10 * n >= 18LL * g_sms[dev] * (TWARPS + SW_MAX) * 32) ? TWARPS + 3 : TWARPS + 2;
 }
 
+// ticks[] as per-environment ready flags (HandOut::flag_rows) exist in the benchmarked kernel only
+bool snk_exact_row_flags_supported() { return g_rows == ROWS_HYBRID; }
+
 const char* snk_exact_variant() {
     return g_rows == ROWS_HYBRID ? "8 warps/SM, rows in TMEM (8 words) + shared memory (7) + registers (2), 256 envs/SM"
          : g_rows == ROWS_SPLIT  ? "rows in TMEM (4 warps) + shared memory (2 or 3 warps per launch), 192 / 224 envs/SM"
@@ -794,7 +802,7 @@ static int cur_dev() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < MAX_D
 // 2 x 64 words after the 8 counters (zeroed with them)
 cudaError_t snk_exact_launch_step(const KParams& P, float* state, float* tgt_scratch, const float* actions, float* obs, float* rew, uint8_t* done,
                                   int32_t* ticks, unsigned long long* counters, uint8_t* bucket, int32_t* order, int64_t n, cudaStream_t st,
-                                  int* launches) {
+                                  int* launches, int flag_rows) {
     const int dev = cur_dev(), sms = g_sms[dev];
     const int aw = warps_for(n, dev);
     const int lanes = g_rows == ROWS_SMEM ? g_smem_ctas[dev] * EB : sms * aw * 32;
@@ -814,7 +822,7 @@ cudaError_t snk_exact_launch_step(const KParams& P, float* state, float* tgt_scr
         const int64_t want = g_spread ? (n + EB - 1) / EB : (n + aw * 32 - 1) / (aw * 32);
         dim3 grid((unsigned)(want < sms ? want : sms)), block(HWARPS * 32);
         HandOut H;
-        H.n_long = n; H.short_warps = 0;
+        H.n_long = n; H.short_warps = 0; H.flag_rows = flag_rows;
         if (use_order && g_balance && (g_spread == 1 || g_spread == 3)) { // n = k L + r: r lanes (whole warps) run k + 1 env-steps, taken from the shortest
             const int64_t L = (int64_t)grid.x * aw * 32, k = n / L, r = n - k * L;
             // Worth it when plain longest-first would end on a long, thinly populated last wave: L - r idle lanes for one env-step out
@@ -869,7 +877,7 @@ cudaError_t snk_exact_launch_step_trace(const KParams& P, float* state, float* t
     if (g_rows == ROWS_HYBRID) { // the benchmarked kernel's TRACE instantiation: same arithmetic, same bits as snk_step
         dim3 grid((unsigned)(warps < g_sms[dev] ? warps : g_sms[dev])), block(HWARPS * 32);
         HandOut H;
-        H.n_long = n; H.short_warps = 0;
+        H.n_long = n; H.short_warps = 0; H.flag_rows = 0;
         if (P.cone) snk_hyb_step_kernel<true, true><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, nullptr, n, HWARPS, 1, H, tick_obs, tick_links);
         else snk_hyb_step_kernel<false, true><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, nullptr, n, HWARPS, 1, H, tick_obs, tick_links);
         return cudaGetLastError();

@@ -16,9 +16,10 @@ class HostPool {
 public:
     static HostPool& get() { static HostPool p; return p; }
     int size() const { return (int)workers_.size() + 1; }
-    // f(begin, end) over [0, n): the calling thread takes the first chunk, the workers the others
-    void run(size_t n, const std::function<void(size_t, size_t)>& f) {
-        const int nt = (n < ((size_t)1 << 16)) ? 1 : size();
+    // f(begin, end) over [0, n): the calling thread takes the first chunk (begin == 0), the workers the others -- every chunk on
+    // its own thread at the same time (there are never more chunks than threads).  Fewer than `serial_below` items: the caller alone.
+    void run(size_t n, const std::function<void(size_t, size_t)>& f, size_t serial_below = (size_t)1 << 16) {
+        const int nt = (n < serial_below) ? 1 : size();
         if (nt == 1) { f((size_t)0, n); return; }
         const size_t per = (n + nt - 1) / nt;
         {

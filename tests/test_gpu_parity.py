@@ -237,6 +237,25 @@ def test_numpy_path_equals_device_path(torch):
     e1.close(); e2.close(); e3.close()
 
 
+def test_numpy_path_large_batch_rows_widened_during_the_launch(torch):
+    """snk_step_host_f64 with a batch of several waves: one launch, the host threads widen every row when its ticks word arrives in
+    the mapped buffer (HandOut::flag_rows) -- the result must be the device path's, whatever order the rows finish in; twice, so
+    that a stale ticks word of the previous call would be caught."""
+    n = 150001
+    g = torch.Generator().manual_seed(11)
+    a = (torch.rand((3, n, 8), generator=g) * 2.4 - 1.2)
+    e1 = make_env(n); e2 = make_env(n)
+    e1.reset(); e2.reset()
+    for t in range(3):
+        o1, r1, d1, i1 = e1.step(a[t].numpy().astype(np.float64))
+        o2, r2, d2, _ = e2.step(a[t].cuda()); torch.cuda.synchronize()
+        assert o1.dtype == np.float64 and o1.shape == (n, 56)
+        assert np.array_equal(o1.astype(np.float32), o2.cpu().numpy())
+        assert np.array_equal(r1.astype(np.float32), r2.cpu().numpy()) and np.array_equal(d1, d2.cpu().numpy())
+        assert np.array_equal(np.asarray(e1.last_ticks), e2.last_ticks.cpu().numpy())
+    e1.close(); e2.close()
+
+
 def test_host_path_call_waits_for_device_path_work_in_flight(torch):
     """A device-path step is asynchronous on the caller's stream; a numpy step issued right behind it runs on the library's own
     stream and must still see its result (event ordering inside the C ABI).  Large enough that the first kernel is still running."""
