@@ -31,8 +31,9 @@ void snk_exact_release();
 const char* snk_exact_variant();
 cudaError_t snk_exact_launch_step(const KParams& P, float* state, float* tgt_scratch, const float* actions, float* obs, float* rew, uint8_t* done,
                                   int32_t* ticks, unsigned long long* counters, uint8_t* bucket, int32_t* order, int64_t n, cudaStream_t st,
-                                  int* launches, int flag_rows);
+                                  int* launches, int flag_rows, int* split_buf);
 bool snk_exact_row_flags_supported();
+size_t snk_exact_split_buf_bytes();
 cudaError_t snk_exact_launch_rollout(const KParams& P, float* state, float* tgt_scratch, const float* weights, const float* mean, const float* inv_std,
                                      const float* noise, int n_steps, float* returns, float* trace, int32_t* queue, int32_t* done_steps,
                                      unsigned long long* counters, int64_t n, cudaStream_t st);
@@ -77,6 +78,7 @@ struct snk_handle {
     float* tgt;                   // device [n + 1][16]: joint targets of the env-step in flight (exact kernel; row n stays zero)
     uint8_t* bucket;              // device [n]: predicted tick count of the coming env-step (exact kernel)
     int32_t* order;               // device [n]: longest-first hand-out order
+    int* split_buf;               // device: claim counters, flags and run words of the split hand-out (exact kernel)
     int32_t* roll_queue;          // device: ready queue of snk_rollout_linear, n * (steps - 1) entries (grown on demand)
     size_t roll_queue_len;
     unsigned long long* counters; // device [NCOUNTERS]: ticks, sweeps, dones, non-finite, work-queue head
@@ -131,7 +133,7 @@ static cudaError_t launch_step(snk_handle* h, const float* act, float* obs, floa
                                                       h->man_cache + off * (int64_t)snk_man_cache_floats(), h->man_scratch, h->man_warm, act, obs, rew, done,
                                                       ticks, h->counters, cnt, st)
                     : h->exact ? snk_exact_launch_step(h->P, h->state + off * SNK_STATE_STRIDE, h->tgt + off * NJ, act, obs, rew, done, ticks, h->counters,
-                                                     h->bucket + off, h->order + off, cnt, st, &launches, flag_rows)
+                                                     h->bucket + off, h->order + off, cnt, st, &launches, flag_rows, h->split_buf)
                              : snk_pgs_launch_step(h->T, h->P, h->state + off * SNK_STATE_STRIDE, act, obs, rew, done, ticks, h->counters, cnt, st);
     h->launches += launches;
     mark_device_work(h, st);
@@ -211,6 +213,7 @@ int snk_create(const snk_model* model, const snk_params* params, int64_t n_envs,
         h->exact = true;
         if (err == cudaSuccess) err = cudaMalloc(&h->bucket, (size_t)n_envs);
         if (err == cudaSuccess) err = cudaMalloc(&h->order, (size_t)n_envs * sizeof(int32_t));
+        if (err == cudaSuccess) err = cudaMalloc(&h->split_buf, snk_exact_split_buf_bytes());
         if (err == cudaSuccess) err = cudaMalloc(&h->tgt, (size_t)(n_envs + 1) * NJ * sizeof(float));
         if (err == cudaSuccess) err = cudaMemset(h->tgt, 0, (size_t)(n_envs + 1) * NJ * sizeof(float));
     } else {
@@ -230,7 +233,7 @@ int snk_create(const snk_model* model, const snk_params* params, int64_t n_envs,
     if (err != cudaSuccess) {
         if (h->exact) snk_exact_release();
         cudaFree(h->man_cache); cudaFree(h->man_scratch);
-    cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters); cudaFree(h->bucket); cudaFree(h->order); cudaFree(h->tgt);
+    cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters); cudaFree(h->bucket); cudaFree(h->order); cudaFree(h->split_buf); cudaFree(h->tgt);
         delete h;
         return fail(SNK_E_CUDA, "snk_create: %s", cudaGetErrorString(err));
     }
@@ -253,7 +256,7 @@ int snk_destroy(snk_handle* h) {
     if (h->ev_valid) cudaEventDestroy(h->ev_dev);
     for (int c = 0; c < h->n_ev_chunk; c++) cudaEventDestroy(h->ev_chunk[c]);
     if (h->exact) snk_exact_release();
-    cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters); cudaFree(h->bucket); cudaFree(h->order); cudaFree(h->roll_queue); cudaFree(h->tgt);
+    cudaFree(h->T); cudaFree(h->state); cudaFree(h->counters); cudaFree(h->bucket); cudaFree(h->order); cudaFree(h->split_buf); cudaFree(h->roll_queue); cudaFree(h->tgt);
     delete h;
     return 0;
 }

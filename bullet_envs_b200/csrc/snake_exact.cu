@@ -74,6 +74,27 @@ __device__ __forceinline__ void load_targets(const KParams& P, const Rows& R, co
     }
 }
 
+// SPLIT HAND-OUT of one CTA (HandOut::split_total, set up by snk_hyb_step_kernel; n_a = 0: off).  With n = k L + r environments on L
+// lanes, whole env-steps leave r lanes with k + 1 of them and the others with k: the launch ends on a last wave that
+// only r lanes take part in.  Instead the r SHORTEST env-steps are cut in two at a tick boundary: r lanes (n_a of
+// them in this CTA, the same in every warp) START with the first part of one, park it -- the state record is in global memory
+// anyway, the seven words of ExRun go to `run_words` -- and carry on with whole env-steps; when the whole env-steps have run out,
+// the lanes of the same CTA that become free finish the parked ones.  Every lane then carries k env-steps and about r / L of one
+// (r <= L / 2: one part each for 2 r lanes; r > L / 2: the L - r other lanes finish several short second parts each).
+// Parking and resuming never cross a CTA, so the protocol needs no co-residency of CTAs; a lane never blocks its warp on a flag
+// (it retries once per tick), and the arithmetic of a tick does not depend on which lane runs it: results are bit-identical.
+struct SplitCta {
+    int n_a;                // entries (= a-part lanes) of this CTA
+    int a_idx;              // this thread's entry within the CTA, or -1
+    int64_t first;          // global index of the CTA's first entry; entry i sits at position pos0 + i of the hand-out order
+    int64_t pos0;           // n - split_total: the whole env-steps are the positions [0, pos0)
+    int frac_q8;            // an a-part ends after max(1, predicted ticks * frac_q8 / 256) ticks
+    const uint8_t* bucket;  // predicted tick counts (snk_exact_predict_kernel)
+    int* bnext;             // the CTA's claim counter for parked env-steps (zeroed per launch)
+    int* flags;             // per entry (zeroed per launch): 1 parked, 2 finished inside its a-part
+    float* run_words;       // per entry 8 words
+};
+
 // The persistent loop of one warp.  counters: [0] ticks, [1] PGS sweeps, [2] dones, [3] non-finite resets,
 // [4] next environment to hand out.
 // TRACE: the mode='test' info stream (snake.py:275-278,292-293): after every physics tick the observation goes to
@@ -84,13 +105,20 @@ __device__ __forceinline__ void run_warp(const KParams& P, Rows R, float* __rest
                                          unsigned long long* __restrict__ counters, const int32_t* __restrict__ order, int64_t n,
                                          int64_t first_base, int64_t dyn_base, float* __restrict__ tick_obs = nullptr,
                                          float* __restrict__ tick_links = nullptr, int pool = 0, int64_t n_long = -1, int64_t dyn_base_short = 0,
-                                         bool flag_rows = false) {
+                                         bool flag_rows = false, const SplitCta* split = nullptr) {
     // Hand-out positions: the warp's first 32 are static, [first_base, first_base + 32), laid out warp-major over the
     // grid by the caller so that a batch smaller than the grid's lanes spreads over all SMs (one warp per scheduler
     // before a second one anywhere); every later position comes from a global counter, which starts at dyn_base.
     // TWO POOLS (HandOut below): positions [0, n_long) are the long pool, [n_long, n) the short pool; a warp draws from its own pool
     // (counter [4] / [6]) and moves over to the other one when its own is exhausted.  n_long < 0: one pool.
+    const bool split_on = split && split->n_a > 0;
+    const bool one_pool = n_long < 0 || split_on;
     if (n_long < 0) n_long = n;
+    if (split_on) n_long = split->pos0; // one pool: the whole env-steps
+    int64_t a_start = (split_on && split->a_idx >= 0) ? split->pos0 + split->first + split->a_idx : -1; // first of all: the lane's a-part
+    int a_entry = -1, susp_at = 0; // a-part in progress: its entry, and the tick count at which it parks
+    int claim = -1;                // parked env-step this lane has claimed and waits for
+    bool b_done = !split_on;       // nothing (more) to claim
     const int lane = R.lane;
     const unsigned lt_mask = (1u << lane) - 1u;
     ExEnv e; // a lane without an environment computes (masked) on record 0 in the rest pose
@@ -110,31 +138,61 @@ __device__ __forceinline__ void run_warp(const KParams& P, Rows R, float* __rest
 #pragma unroll 1
     for (;;) {
         // ---- lanes without an environment take the next ones (first: the static positions, then the global counter)
-        unsigned need = __ballot_sync(FULL, !have);
+        unsigned need = __ballot_sync(FULL, !have && a_start < 0 && claim < 0);
+        unsigned fixed = __ballot_sync(FULL, a_start >= 0); // lanes that start on their a-part draw nothing from the counters
 #pragma unroll 1
-        for (int attempt = 0; attempt < 2 && need; attempt++) { // second attempt: the other pool, once the warp's own is exhausted
+        for (int attempt = 0; attempt < 2 && (need | fixed); attempt++) { // second attempt: the other pool, once the warp's own is exhausted
             unsigned long long base = (unsigned long long)first_base;
-            if (!first) {
+            if (!first && need) {
                 if (lane == 0) base = (unsigned long long)(pool ? dyn_base_short : dyn_base) + atomicAdd(&counters[pool ? 6 : 4], (unsigned long long)__popc(need));
                 base = __shfl_sync(FULL, base, 0);
             }
             first = false;
-            if (!have) {
-                const int64_t cand = (int64_t)base + __popc(need & lt_mask);
-                if (cand < (pool ? n : n_long)) {
+            if (!have && claim < 0) {
+                const bool apart = a_start >= 0;
+                const int64_t cand = apart ? a_start : (int64_t)base + __popc(need & lt_mask);
+                if (apart || cand < (pool ? n : n_long)) {
                     env = order ? (int64_t)order[cand] : cand; have = true; // longest-first order when the batch exceeds the lanes
                     e.st = state + env * SNK_STATE_STRIDE;
                     R.tg = tgt_scratch + env * NJ;
                     load_targets(P, R, actions + env * P.actdim);
                     ex_load_base(e);
                     ex_step_begin(P, R, e, &run);
+                    if (apart) {
+                        a_entry = (int)(split->first + split->a_idx);
+                        susp_at = max(1, ((int)split->bucket[env] * split->frac_q8) >> 8);
+                        a_start = -1;
+                    }
                 }
             }
-            need = __ballot_sync(FULL, !have);
-            if (n_long == n) break;        // a single pool
+            need = __ballot_sync(FULL, !have && claim < 0);
+            fixed = 0u;
+            if (one_pool) break;
             if (need) pool ^= 1;           // positions beyond the pool's end were drawn: it is empty, go on with the other one
         }
-        if (!__any_sync(FULL, have)) break;
+        if (split_on) { // the whole env-steps have run out for this lane: finish a parked one of the CTA
+            if (!have && claim < 0 && !b_done) {
+                const int j = atomicAdd(split->bnext, 1);
+                if (j < split->n_a) claim = (int)split->first + j; else b_done = true;
+            }
+            if (claim >= 0) {
+                const int f = *reinterpret_cast<volatile int*>(split->flags + claim);
+                if (f == 1) { // parked: its record, target row and run words were written before the flag
+                    __threadfence_block();
+                    env = (int64_t)order[split->pos0 + claim]; have = true;
+                    e.st = state + env * SNK_STATE_STRIDE;
+                    R.tg = tgt_scratch + env * NJ;
+                    ex_load_base(e);
+                    const volatile float* rw = split->run_words + (int64_t)claim * 8;
+                    run.xprev = rw[0]; run.e2 = rw[1]; run.height = rw[2];
+                    run.counter = __float_as_int(rw[3]); run.iters = __float_as_int(rw[4]);
+                    const int bits = __float_as_int(rw[5]);
+                    run.end_height = (bits & 1) != 0; run.have_height = (bits & 2) != 0;
+                    claim = -1;
+                } else if (f == 2) claim = -1; // it ended inside its a-part: claim another one in the next round
+            }
+            if (!__any_sync(FULL, have || claim >= 0 || !b_done)) break;
+        } else if (!__any_sync(FULL, have)) break;
         __syncwarp();
         const int tick0 = run.counter;
         const bool finished = ex_step_advance<CONE>(cT, P, R, e, have, &run); // every lane of the warp ticks together
@@ -162,6 +220,17 @@ __device__ __forceinline__ void run_warp(const KParams& P, Rows R, float* __rest
             if (ticks) ticks[env] = o.ticks;
             c_ticks += (unsigned long long)o.ticks; c_iters += (unsigned long long)o.iters; c_done += o.done; c_bad += o.bad;
             have = false;
+            if (a_entry >= 0) { *reinterpret_cast<volatile int*>(split->flags + a_entry) = 2; a_entry = -1; } // nothing left to park
+        }
+        if (have && a_entry >= 0 && run.counter >= susp_at) { // end of the a-part: park the env-step for another lane of the CTA
+            ex_store_base(e);
+            volatile float* rw = split->run_words + (int64_t)a_entry * 8;
+            rw[0] = run.xprev; rw[1] = run.e2; rw[2] = run.height;
+            rw[3] = __int_as_float(run.counter); rw[4] = __int_as_float(run.iters);
+            rw[5] = __int_as_float((run.end_height ? 1 : 0) | (run.have_height ? 2 : 0));
+            __threadfence_block();
+            *reinterpret_cast<volatile int*>(split->flags + a_entry) = 1;
+            have = false; a_entry = -1;
         }
         __syncwarp();
     }
@@ -456,7 +525,13 @@ struct HandOut {       // two-pool hand-out of a launch (see snk_hyb_step_kernel
     int64_t n_long;    // positions [0, n_long) of the longest-first order are the long pool, [n_long, n) the short pool
     int short_warps;   // warps (in warp-major order over the grid) that draw from the short pool
     int flag_rows;     // != 0: ticks[env] is written last, behind a system fence (the host reads finished rows during the launch)
+    // split hand-out (SplitCta): the split_total shortest env-steps are run in two parts by two lanes of a CTA; 0 = off
+    int split_total, split_frac_q8;
+    const uint8_t* bucket;
+    int* split_buf;    // [SPLIT_CTAS] claim counters, [SPLIT_MAX] flags, [SPLIT_MAX][8] run words (handle owned; counters and flags zeroed per launch)
 };
+#define SPLIT_CTAS 256
+#define SPLIT_MAX (SPLIT_CTAS * HWARPS * 32)
 
 // TRACE = true: the same kernel with the mode='test' info stream (snk_step_trace) -- a separate instantiation, so the
 // benchmarked one carries no trace code, and the traced step returns bit for bit what the plain step returns.
@@ -491,9 +566,24 @@ snk_hyb_step_kernel(const KParams P, float* __restrict__ state, float* __restric
         dyn_short = H.n_long + min((int64_t)H.short_warps * 32, n - H.n_long);
         if (first_base >= (pool ? n : H.n_long)) first_base = n; // nothing static for this warp: it starts with the counters
     }
+    SplitCta sp;
+    sp.n_a = 0;
+    if (!TRACE && H.split_total > 0) { // entries are dealt out CTA by CTA, inside a CTA warp by warp (every warp gets the same number of a-part lanes)
+        const int q = H.split_total / (int)gridDim.x, rm = H.split_total % (int)gridDim.x;
+        sp.n_a = q + ((int)blockIdx.x < rm ? 1 : 0);
+        sp.first = (int64_t)blockIdx.x * q + min((int)blockIdx.x, rm);
+        sp.pos0 = n - H.split_total;
+        sp.a_idx = (lane * HWARPS + warp < sp.n_a) ? lane * HWARPS + warp : -1;
+        sp.frac_q8 = H.split_frac_q8;
+        sp.bucket = H.bucket;
+        sp.bnext = H.split_buf + blockIdx.x;
+        sp.flags = H.split_buf + SPLIT_CTAS;
+        sp.run_words = reinterpret_cast<float*>(H.split_buf + SPLIT_CTAS + SPLIT_MAX);
+        first_base = -1; dyn_base = 0; // no static wave: the lanes without an a-part draw their first env-step from the counter
+    }
     if (warp < active_warps) // SNK_EXACT_WARPS (ablation): the other warps take no environments
         run_warp<CONE, RowsH, TRACE>(P, hyb_rows(S, tbase, warp, lane), state, tgt_scratch, actions, obs, rew, done, ticks, counters, order, n, first_base,
-                                     dyn_base, tick_obs, tick_links, pool, H.short_warps > 0 ? H.n_long : -1, dyn_short, H.flag_rows != 0);
+                                     dyn_base, tick_obs, tick_links, pool, H.short_warps > 0 ? H.n_long : -1, dyn_short, H.flag_rows != 0, &sp);
     hyb_tmem_free(tbase, warp);
 }
 
@@ -696,6 +786,11 @@ static bool g_no_sort = false;   // SNK_EXACT_ORDER=index disables the longest-f
 static int g_spread = 3;         // SNK_EXACT_SPREAD: first-wave hand-out policy (see the step kernels)
 static int g_active_warps = 0;   // SNK_EXACT_WARPS=1..8 forces the number of working warps per SM (0: chosen per launch)
 static bool g_balance = true;    // SNK_EXACT_BALANCE=0 disables the two-pool (balanced) hand-out (ablation)
+static bool g_split = true;      // SNK_EXACT_SPLIT=0 disables the split hand-out (env-steps run in two parts; the two pools take over)
+static int g_split_frac_q8 = 154; // SNK_EXACT_SPLIT_FRAC (percent; default: chosen per launch): share of an env-step's predicted ticks in its first part
+static bool g_split_frac_forced = false;
+static int g_split_kmax = 4;       // SNK_EXACT_SPLIT_KMAX: split only up to this many whole env-steps per lane (beyond, the two pools do as well or better)
+static int g_split_min_pct = 3;    // SNK_EXACT_SPLIT_MINPCT: ... and only if the idle lanes of the last wave are at least this share of the batch
 
 // working warps per SM for a batch of n environments.  Hybrid rows: always 8.  Split rows: 7 (three shared-memory warps) once the
 // batch is about two waves of the 7-warp grid, else 6 -- a single wave finishes sooner with fewer warps per scheduler.
@@ -704,6 +799,8 @@ static int warps_for(int64_t n, int dev) {
     if (g_active_warps >= 1 && g_active_warps <= TWARPS + SW_MAX) return g_active_warps;
     return (10 * n >= 18LL * g_sms[dev] * (TWARPS + SW_MAX) * 32) ? TWARPS + 3 : TWARPS + 2;
 }
+
+size_t snk_exact_split_buf_bytes() { return (size_t)(SPLIT_CTAS + SPLIT_MAX + SPLIT_MAX * 8) * sizeof(int); }
 
 // ticks[] as per-environment ready flags (HandOut::flag_rows) exist in the benchmarked kernel only
 bool snk_exact_row_flags_supported() { return g_rows == ROWS_HYBRID; }
@@ -744,6 +841,15 @@ cudaError_t snk_exact_configure(const ExTables* host_tables) {
     g_spread = (sp && sp[0] >= '0' && sp[0] <= '3') ? sp[0] - '0' : 3;
     const char* bl = getenv("SNK_EXACT_BALANCE");
     g_balance = !(bl && bl[0] == '0');
+    const char* spl = getenv("SNK_EXACT_SPLIT");
+    g_split = !(spl && spl[0] == '0');
+    const char* spf = getenv("SNK_EXACT_SPLIT_FRAC");
+    g_split_frac_forced = spf && atoi(spf) >= 5 && atoi(spf) <= 95;
+    g_split_frac_q8 = g_split_frac_forced ? atoi(spf) * 256 / 100 : 154;
+    const char* skm = getenv("SNK_EXACT_SPLIT_KMAX");
+    g_split_kmax = (skm && atoi(skm) >= 0) ? atoi(skm) : 4;
+    const char* smp = getenv("SNK_EXACT_SPLIT_MINPCT");
+    g_split_min_pct = (smp && atoi(smp) >= 0) ? atoi(smp) : 3;
     const char* w = getenv("SNK_EXACT_WARPS");
     g_active_warps = (w && atoi(w) >= 1 && atoi(w) <= HWARPS) ? atoi(w) : 0;
     e = cudaMemcpyToSymbol(cT, host_tables, sizeof(ExTables));
@@ -802,7 +908,7 @@ static int cur_dev() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < MAX_D
 // 2 x 64 words after the 8 counters (zeroed with them)
 cudaError_t snk_exact_launch_step(const KParams& P, float* state, float* tgt_scratch, const float* actions, float* obs, float* rew, uint8_t* done,
                                   int32_t* ticks, unsigned long long* counters, uint8_t* bucket, int32_t* order, int64_t n, cudaStream_t st,
-                                  int* launches, int flag_rows) {
+                                  int* launches, int flag_rows, int* split_buf) {
     const int dev = cur_dev(), sms = g_sms[dev];
     const int aw = warps_for(n, dev);
     const int lanes = g_rows == ROWS_SMEM ? g_smem_ctas[dev] * EB : sms * aw * 32;
@@ -823,7 +929,27 @@ cudaError_t snk_exact_launch_step(const KParams& P, float* state, float* tgt_scr
         dim3 grid((unsigned)(want < sms ? want : sms)), block(HWARPS * 32);
         HandOut H;
         H.n_long = n; H.short_warps = 0; H.flag_rows = flag_rows;
-        if (use_order && g_balance && (g_spread == 1 || g_spread == 3)) { // n = k L + r: r lanes (whole warps) run k + 1 env-steps, taken from the shortest
+        H.split_total = 0; H.split_frac_q8 = g_split_frac_q8; H.bucket = bucket; H.split_buf = split_buf;
+        if (use_order && g_balance && g_split && split_buf && aw == HWARPS && (int)grid.x == sms && sms <= SPLIT_CTAS) {
+            // n = k L + r: the r shortest env-steps are run in two parts (SplitCta).  Model (tools/handout_sim.py, 131 072 environments =
+            // 3.46 L): 110.2 warp iterations with the two pools below, 107.0 split, 104.3 ideal.  Measured on B200 (ms per step, split /
+            // two pools): 50 000 envs 12.1 / 14.6, 62 000 13.7 / 15.3, 100 000 21.2 / 22.7, 131 072 27.8 / 29.2, 162 918 34.9 / 35.3,
+            // 200 000 42.4 / 42.1 -- from five whole env-steps per lane on the two pools do as well, and without the 3 % gate the large
+            // batches lose a little (2^20: 214.9 / 214.2), so: k <= 4 and (L - r) / n >= 3 %.
+            const int64_t L = (int64_t)grid.x * aw * 32, k = n / L, r = n - k * L;
+            if (k >= 1 && k <= g_split_kmax && 16 * r >= L && 100 * (L - r) >= g_split_min_pct * n) {
+                H.split_total = (int)r;
+                // share of the first part: with r <= L / 2 one part per lane, about half each (the lanes without a first part start on
+                // the LONGEST whole env-steps, so a little more than half balances: 60 %, measured); with r > L / 2 the L - r other
+                // lanes finish several second parts each, and the parts even out at r / L (+ 10 points for the same reason)
+                if (!g_split_frac_forced) H.split_frac_q8 = 2 * r <= L ? 154 : (int)((r * 256) / L) + 26 > 230 ? 230 : (int)((r * 256) / L) + 26;
+            }
+        }
+        if (H.split_total > 0) {
+            cudaError_t me = cudaMemsetAsync(split_buf, 0, (size_t)(SPLIT_CTAS + H.split_total) * sizeof(int), st);
+            if (me != cudaSuccess) return me;
+            *launches += 1;
+        } else if (use_order && g_balance && (g_spread == 1 || g_spread == 3)) { // n = k L + r: r lanes (whole warps) run k + 1 env-steps, taken from the shortest
             const int64_t L = (int64_t)grid.x * aw * 32, k = n / L, r = n - k * L;
             // Worth it when plain longest-first would end on a long, thinly populated last wave: L - r idle lanes for one env-step out
             // of n / L per lane, i.e. a loss of about (L - r) / n.  Measured on B200 (ms per step, balanced / plain): 100 000 envs

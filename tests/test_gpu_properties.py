@@ -135,6 +135,33 @@ def test_warp_count_and_hand_out_policy_do_not_change_results(torch):
     assert len(set(sums)) == 1, sums
 
 
+def test_split_hand_out_does_not_change_results(torch):
+    """Split hand-out (SplitCta in csrc/snake_exact.cu): with n = k L + r environments and r <= L / 2 the r shortest env-steps are run in
+    two parts by two lanes of a CTA (parked at a tick boundary, finished when the whole env-steps have run out).  Not a bit of the
+    results may depend on it: 50 000 and 131 072 environments (1.3 and 3.46 waves of the 37 888-lane grid), three env-steps, the third
+    with repeated actions for a quarter of the batch (zero-tick env-steps, which end inside their first part), split on / off, first
+    parts of 30 % and 90 % of the predicted ticks, and the two pools off as well; checksums of observations, rewards, dones, ticks and
+    the state array, in subprocesses (the switches are read at snk_create)."""
+    import os, subprocess, sys
+    code = ("import sys, torch, hashlib; from bullet_envs_b200 import SnakeVecEnv;"
+            "n=int(sys.argv[1]); g=torch.Generator().manual_seed(21); a=(torch.rand((3,n,8),generator=g)*2.4-1.2); a[2,::4]=a[1,::4]; a=a.cuda();"
+            "e=SnakeVecEnv(num_envs=n,device=0); e.reset(as_torch=True);"
+            "h=hashlib.sha256(); dn=0\n"
+            "for t in range(3):\n"
+            "    o,r,d,_=e.step(a[t]); dn+=int(d.sum())\n"
+            "    for x in (o,r,d,e.last_ticks,e.get_state()): h.update(x.cpu().numpy().tobytes())\n"
+            "print('SUM', h.hexdigest(), dn, e.counters()['ticks'])")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for n in (50000, 131072):
+        sums = []
+        for extra in ({}, {"SNK_EXACT_SPLIT": "0"}, {"SNK_EXACT_SPLIT_FRAC": "30"}, {"SNK_EXACT_SPLIT_FRAC": "90"}, {"SNK_EXACT_SPLIT": "0", "SNK_EXACT_BALANCE": "0"}):
+            env = dict(os.environ, PYTHONPATH=root, **extra)
+            out = subprocess.run([sys.executable, "-c", code, str(n)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+            assert out.returncode == 0, out.stderr[-2000:]
+            sums.append([l for l in out.stdout.splitlines() if l.startswith("SUM")][0])
+        assert len(set(sums)) == 1, sums
+
+
 def test_checkpoint_resume_is_bit_exact(torch):
     from bullet_envs_b200 import SnakeVecEnv
     n = 300
