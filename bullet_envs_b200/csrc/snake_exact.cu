@@ -99,7 +99,7 @@ struct SplitCta {
 // [4] next environment to hand out.
 // TRACE: the mode='test' info stream (snake.py:275-278,292-293): after every physics tick the observation goes to
 // tick_obs[env][tick][56] and the link positions to tick_links[env][tick][51] (max_ticks rows per environment).
-template <bool CONE, class Rows, bool TRACE = false>
+template <bool CONE, class Rows, bool TRACE = false, bool SPLIT = false>
 __device__ __forceinline__ void run_warp(const KParams& P, Rows R, float* __restrict__ state, float* __restrict__ tgt_scratch, const float* __restrict__ actions,
                                          float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks,
                                          unsigned long long* __restrict__ counters, const int32_t* __restrict__ order, int64_t n,
@@ -111,7 +111,7 @@ __device__ __forceinline__ void run_warp(const KParams& P, Rows R, float* __rest
     // before a second one anywhere); every later position comes from a global counter, which starts at dyn_base.
     // TWO POOLS (HandOut below): positions [0, n_long) are the long pool, [n_long, n) the short pool; a warp draws from its own pool
     // (counter [4] / [6]) and moves over to the other one when its own is exhausted.  n_long < 0: one pool.
-    const bool split_on = split && split->n_a > 0;
+    const bool split_on = SPLIT && split && split->n_a > 0; // SPLIT = false: everything below that concerns the split hand-out folds away
     const bool one_pool = n_long < 0 || split_on;
     if (n_long < 0) n_long = n;
     if (split_on) n_long = split->pos0; // one pool: the whole env-steps
@@ -535,7 +535,7 @@ struct HandOut {       // two-pool hand-out of a launch (see snk_hyb_step_kernel
 
 // TRACE = true: the same kernel with the mode='test' info stream (snk_step_trace) -- a separate instantiation, so the
 // benchmarked one carries no trace code, and the traced step returns bit for bit what the plain step returns.
-template <bool CONE, bool TRACE>
+template <bool CONE, bool TRACE, bool SPLIT = false>
 __global__ void __launch_bounds__(HWARPS * 32, 1)
 snk_hyb_step_kernel(const KParams P, float* __restrict__ state, float* __restrict__ tgt_scratch, const float* __restrict__ actions, float* __restrict__ obs,
                     float* __restrict__ rew, uint8_t* __restrict__ done, int32_t* __restrict__ ticks, unsigned long long* __restrict__ counters,
@@ -568,7 +568,7 @@ snk_hyb_step_kernel(const KParams P, float* __restrict__ state, float* __restric
     }
     SplitCta sp;
     sp.n_a = 0;
-    if (!TRACE && H.split_total > 0) { // entries are dealt out CTA by CTA, inside a CTA warp by warp (every warp gets the same number of a-part lanes)
+    if (SPLIT && H.split_total > 0) { // entries are dealt out CTA by CTA, inside a CTA warp by warp (every warp gets the same number of a-part lanes)
         const int q = H.split_total / (int)gridDim.x, rm = H.split_total % (int)gridDim.x;
         sp.n_a = q + ((int)blockIdx.x < rm ? 1 : 0);
         sp.first = (int64_t)blockIdx.x * q + min((int)blockIdx.x, rm);
@@ -582,8 +582,8 @@ snk_hyb_step_kernel(const KParams P, float* __restrict__ state, float* __restric
         first_base = -1; dyn_base = 0; // no static wave: the lanes without an a-part draw their first env-step from the counter
     }
     if (warp < active_warps) // SNK_EXACT_WARPS (ablation): the other warps take no environments
-        run_warp<CONE, RowsH, TRACE>(P, hyb_rows(S, tbase, warp, lane), state, tgt_scratch, actions, obs, rew, done, ticks, counters, order, n, first_base,
-                                     dyn_base, tick_obs, tick_links, pool, H.short_warps > 0 ? H.n_long : -1, dyn_short, H.flag_rows != 0, &sp);
+        run_warp<CONE, RowsH, TRACE, SPLIT>(P, hyb_rows(S, tbase, warp, lane), state, tgt_scratch, actions, obs, rew, done, ticks, counters, order, n, first_base,
+                                            dyn_base, tick_obs, tick_links, pool, H.short_warps > 0 ? H.n_long : -1, dyn_short, H.flag_rows != 0, &sp);
     hyb_tmem_free(tbase, warp);
 }
 
@@ -875,6 +875,8 @@ cudaError_t snk_exact_configure(const ExTables* host_tables) {
     if (e == cudaSuccess) e = set_smem(snk_exact_rollout_kernel<false, 3>, sizeof(StepSmemT<3>));
     if (e == cudaSuccess) e = set_smem(snk_hyb_step_kernel<true, false>, sizeof(StepSmemH));
     if (e == cudaSuccess) e = set_smem(snk_hyb_step_kernel<false, false>, sizeof(StepSmemH));
+    if (e == cudaSuccess) e = set_smem(snk_hyb_step_kernel<true, false, true>, sizeof(StepSmemH));
+    if (e == cudaSuccess) e = set_smem(snk_hyb_step_kernel<false, false, true>, sizeof(StepSmemH));
     if (e == cudaSuccess) e = set_smem(snk_hyb_step_kernel<true, true>, sizeof(StepSmemH));
     if (e == cudaSuccess) e = set_smem(snk_hyb_step_kernel<false, true>, sizeof(StepSmemH));
     if (e == cudaSuccess) e = set_smem(snk_hyb_tick_kernel<true>, sizeof(StepSmemH));
@@ -962,8 +964,11 @@ cudaError_t snk_exact_launch_step(const KParams& P, float* state, float* tgt_scr
                 H.n_long = n_short < n ? n - n_short : 0;
             }
         }
-        if (P.cone) snk_hyb_step_kernel<true, false><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n, aw, g_spread, H, nullptr, nullptr);
-        else snk_hyb_step_kernel<false, false><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n, aw, g_spread, H, nullptr, nullptr);
+        // the split hand-out is an instantiation of its own: the plain one, which runs the large batches, carries none of its code
+#define SNK_LAUNCH_HYB(C, SP) snk_hyb_step_kernel<C, false, SP><<<grid, block, sizeof(StepSmemH), st>>>(P, state, tgt_scratch, actions, obs, rew, done, ticks, counters, use_order, n, aw, g_spread, H, nullptr, nullptr)
+        if (H.split_total > 0) { if (P.cone) SNK_LAUNCH_HYB(true, true); else SNK_LAUNCH_HYB(false, true); }
+        else { if (P.cone) SNK_LAUNCH_HYB(true, false); else SNK_LAUNCH_HYB(false, false); }
+#undef SNK_LAUNCH_HYB
     } else if (g_rows == ROWS_SPLIT) {
         const int sw = aw > TWARPS + 2 ? 3 : 2;
         const int per_cta = (TWARPS + sw) * 32, per_cta_active = aw * 32;

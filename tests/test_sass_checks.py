@@ -27,7 +27,7 @@ def test_hybrid_step_kernel_uses_tensor_memory_shared_memory_and_registers(sass)
     """the benchmarked kernel (RowsH): 8 / 4 / 2 word tensor-memory loads, tensor-memory stores of the solver state, the three
     shared-memory loads of the friction record, and a fully unrolled normal sweep (one 4-word load per contact)"""
     txt = open(sass).read()
-    k = [p for p in txt.split("Function : ") if p.startswith("_Z19snk_hyb_step_kernelILb1ELb0EE")][0]
+    k = [p for p in txt.split("Function : ") if p.startswith("_Z19snk_hyb_step_kernelILb1ELb0ELb0EE")][0]
     assert k.count("LDTM.x8") >= 3 and k.count("LDTM.x4") >= 32 and k.count("LDTM.x2") >= 32
     assert k.count("STTM.x2") >= 3 and k.count("STTM.x8") >= 2
     assert k.count("LDS.128") >= 3 and k.count("LDS.64") >= 3
@@ -46,7 +46,7 @@ def test_bank_conflict_counter_finds_the_solver_loops(sass):
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import sass_bank_conflicts as sbc
     k = sbc.kernels(sass)
-    name = [n for n in k if "snk_hyb_step_kernelILb1ELb0EE" in n][0]
+    name = [n for n in k if "snk_hyb_step_kernelILb1ELb0ELb0EE" in n][0]
     found = []
     for body in sbc.loops(sbc.ins_of(k[name])):
         if 100 <= len(body) <= 200 and any("LDTM.x8" in t for _, t in body) and sum("MUFU.RSQ" in t for _, t in body) == 2:
