@@ -61,7 +61,7 @@ def ncu_constants():
     import glob
     import re
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_*raw_1m.csv")),
-                   key=lambda f: (int(re.search(r"r(\d+)_", os.path.basename(f)).group(1)), os.path.getmtime(f)))
+                   key=lambda f: (int(re.search(r"r(\d+)_", os.path.basename(f)).group(1)), os.path.basename(f)))  # r02_h3 < r02_h4: by name (a checkout does not keep mtimes)
     want = {"dram__bytes_read.sum": "dram_read", "dram__bytes_write.sum": "dram_write", "smsp__inst_executed.sum": "warp_inst",
             "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_pct", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active": "fma_pct",
             "smsp__thread_inst_executed_per_inst_executed.ratio": "lanes_per_inst", "launch__registers_per_thread": "regs"}
