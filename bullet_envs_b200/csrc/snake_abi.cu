@@ -141,6 +141,7 @@ static cudaError_t launch_step(snk_handle* h, const float* act, float* obs, floa
 }
 
 #include "snake_hostpool.h"
+#include "snake_rowflags.h"
 
 template <class F>
 static void parallel_chunks(size_t n, F f, size_t serial_below = (size_t)1 << 16) { HostPool::get().run(n, std::function<void(size_t, size_t)>(f), serial_below); }
@@ -499,62 +500,22 @@ static int step_host_f64_flags(snk_handle* h, const double* actions_host, double
     }, grain);
     CU(cudaMemsetAsync(h->counters, 0, NCOUNTERS * sizeof(unsigned long long), st));
     CU(launch_step(h, h->h_act, h->h_obs, h->h_rew, h->h_done, h->h_ticks, st, 0, -1, 1));
-    const float* ho = h->h_obs;
-    const float* hr = h->h_rew;
-    const uint8_t* hd = h->h_done;
-    // 0: launch in flight, 1: launch finished (every row is there), 2: the launch failed, 3: finished with a row missing (cannot happen)
-    std::atomic<int> launch_state{0};
+    RowSink sink;
+    sink.obs_src = h->h_obs; sink.rew_src = h->h_rew; sink.done_src = h->h_done; sink.ticks_src = h->h_ticks;
+    sink.obs = obs_host; sink.rew = rew_host; sink.done = done_host; sink.ticks = ticks_host; sink.obs_dim = SNK_OBS_DIM;
+    std::atomic<int> launch_state{ROWS_IN_FLIGHT};
     std::atomic<int> sync_error{(int)cudaSuccess};
     static int prefault = -1;
     if (prefault < 0) { const char* e = getenv("SNK_HOST_PREFAULT"); prefault = !(e && e[0] == '0'); }
-    parallel_chunks(n, [&, ho, hr, hd, ht](size_t b, size_t e) {
-        const bool leader = b == 0; // the calling thread: the one with the CUDA context
-        if (prefault && (e - b) >= grain) { // fresh numpy arrays are untouched anonymous memory: take the page faults now, not row by row
-            volatile char* p0 = (volatile char*)(obs_host + b * SNK_OBS_DIM);
-            for (size_t k = 0; k < (e - b) * SNK_OBS_DIM * sizeof(double); k += 4096) p0[k] = 0;
-            volatile char* p1 = (volatile char*)(rew_host + b);
-            for (size_t k = 0; k < (e - b) * sizeof(double); k += 4096) p1[k] = 0;
-        }
-        std::vector<uint32_t> pend(e - b);
-        for (size_t k = 0; k < e - b; k++) pend[k] = (uint32_t)(b + k);
-        size_t np = e - b;
-        while (np) {
-            const int before = launch_state.load(std::memory_order_acquire);
-            size_t w = 0;
-            for (size_t k = 0; k < np; k++) {
-                const size_t i = pend[k];
-                const int32_t t = *(volatile const int32_t*)(ht + i);
-                if (t < 0) { pend[w++] = (uint32_t)i; continue; }
-                std::atomic_thread_fence(std::memory_order_acquire); // the row was posted before its ticks word
-                const float* src = ho + i * SNK_OBS_DIM;
-                double* dst = obs_host + i * SNK_OBS_DIM;
-                for (int c = 0; c < SNK_OBS_DIM; c++) dst[c] = (double)src[c];
-                rew_host[i] = (double)hr[i];
-                done_host[i] = hd[i];
-                if (ticks_host) ticks_host[i] = t;
-            }
-            const size_t converted = np - w;
-            np = w;
-            if (!np) break;
-            if (before == 2) return;
-            if (before == 1) { launch_state.store(3, std::memory_order_release); return; }
-            if (leader) {
-                const cudaError_t q = cudaStreamQuery(st);
-                if (q == cudaSuccess) launch_state.store(1, std::memory_order_release);
-                else if (q != cudaErrorNotReady) { sync_error.store((int)q); launch_state.store(2, std::memory_order_release); }
-            }
-            if (converted == 0) { struct timespec ts = {0, 30000}; nanosleep(&ts, nullptr); } // nothing new: leave the memory bus alone for 30 us
-        }
-        if (leader && launch_state.load(std::memory_order_acquire) == 0) { // the other threads rely on the leader to notice a failed launch
-            const cudaError_t q = cudaStreamSynchronize(st);
-            if (q == cudaSuccess) launch_state.store(1, std::memory_order_release);
-            else { sync_error.store((int)q); launch_state.store(2, std::memory_order_release); }
-        }
+    parallel_chunks(n, [&](size_t b, size_t e) {
+        rows_widen_as_posted(sink, b, e, launch_state, /* leader: the calling thread, which has the CUDA context */ b == 0, prefault && (e - b) >= grain,
+            [&]() { const cudaError_t q = cudaStreamQuery(st); if (q == cudaSuccess) return 1; if (q == cudaErrorNotReady) return 0; sync_error.store((int)q); return -1; },
+            [&]() { const cudaError_t q = cudaStreamSynchronize(st); if (q == cudaSuccess) return 1; sync_error.store((int)q); return -1; });
     }, grain);
     const cudaError_t e_sync = cudaStreamSynchronize(st);
-    if (launch_state.load() == 2 || e_sync != cudaSuccess)
+    if (launch_state.load() == ROWS_LAUNCH_FAILED || e_sync != cudaSuccess)
         return fail(SNK_E_CUDA, "snk_step_host_f64: the env-step launch failed: %s", cudaGetErrorString(e_sync != cudaSuccess ? e_sync : (cudaError_t)sync_error.load()));
-    if (launch_state.load() == 3) return fail(SNK_E_CUDA, "snk_step_host_f64: the launch finished without posting every row%s");
+    if (launch_state.load() == ROWS_MISSING) return fail(SNK_E_CUDA, "snk_step_host_f64: the launch finished without posting every row%s");
     return 0;
 }
 

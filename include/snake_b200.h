@@ -172,7 +172,10 @@ int snk_reset_host(snk_handle* h, const uint8_t* mask_host, float* obs_host);
 
 /* snk_step_host with the reference's own dtypes: float64 actions in, float64 obs / reward out, exactly the arrays
  * SubprocVecEnv.step exchanges with ppo/train.py:122 and ars/train.py:99 (np.stack of the workers' float64 results,
- * ppo/multiprocessing_env.py:126-128).  The narrowing / widening runs on a few host threads (SNK_HOST_THREADS). */
+ * ppo/multiprocessing_env.py:126-128).  The narrowing / widening runs on a few host threads (SNK_HOST_THREADS); with the default
+ * kernel the batch is one launch that posts every environment's row into page-locked memory as the environment finishes, its ticks
+ * word last, and the threads widen the rows into the caller's arrays while the launch is still running.  Synchronous: the arrays are
+ * complete on return. */
 int snk_step_host_f64(snk_handle* h, const double* actions_host, double* obs_host, double* rew_host,
                       uint8_t* done_host, int32_t* ticks_host);
 
