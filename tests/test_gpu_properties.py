@@ -162,6 +162,33 @@ def test_split_hand_out_does_not_change_results(torch):
         assert len(set(sums)) == 1, sums
 
 
+def test_split_hand_out_stress(torch):
+    """No sanitizer on this pool: the park / claim / resume protocol of the split hand-out (CTA-scope fence + flag word, per-CTA claim
+    counter) is exercised instead -- 40 consecutive env-steps (episodes end and restart on the way) at three batch sizes (r / L = 0.19,
+    0.85 and 0.46 of a wave left over), every step a fresh launch with fresh parked env-steps, against the same run without splitting."""
+    import os, subprocess, sys
+    code = ("import sys, torch, hashlib; from bullet_envs_b200 import SnakeVecEnv;"
+            "n=int(sys.argv[1]); g=torch.Generator(device='cuda').manual_seed(33);"
+            "e=SnakeVecEnv(num_envs=n,device=0); e.reset(as_torch=True);"
+            "h=hashlib.sha256(); dn=0\n"
+            "for t in range(40):\n"
+            "    a=torch.rand((n,8),generator=g,device='cuda')*2.6-1.3\n"
+            "    if t % 5 == 4: a[::3]=prev[::3]\n"
+            "    prev=a; o,r,d,_=e.step(a); dn+=int(d.sum())\n"
+            "    for x in (o,r,d,e.last_ticks): h.update(x.cpu().numpy().tobytes())\n"
+            "h.update(e.get_state().cpu().numpy().tobytes()); print('SUM', h.hexdigest(), dn)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for n in (45000, 70000, 131072):
+        sums = []
+        for extra in ({}, {"SNK_EXACT_SPLIT": "0"}):
+            env = dict(os.environ, PYTHONPATH=root, **extra)
+            out = subprocess.run([sys.executable, "-c", code, str(n)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+            assert out.returncode == 0, out.stderr[-2000:]
+            sums.append([l for l in out.stdout.splitlines() if l.startswith("SUM")][0])
+        assert len(set(sums)) == 1, sums
+        assert int(sums[0].split()[2]) > 0      # episodes did end on the way
+
+
 def test_checkpoint_resume_is_bit_exact(torch):
     from bullet_envs_b200 import SnakeVecEnv
     n = 300
