@@ -21,6 +21,7 @@ public:
     void run(size_t n, const std::function<void(size_t, size_t)>& f, size_t serial_below = (size_t)1 << 16) {
         const int nt = (n < serial_below) ? 1 : size();
         if (nt == 1) { f((size_t)0, n); return; }
+        std::lock_guard<std::mutex> one_job(run_mu_); // callers on several threads (one handle each) take turns
         const size_t per = (n + nt - 1) / nt;
         {
             std::unique_lock<std::mutex> lk(mu_);
@@ -70,7 +71,7 @@ private:
         }
     }
     std::vector<std::thread> workers_;
-    std::mutex mu_;
+    std::mutex mu_, run_mu_;
     std::condition_variable cv_, done_;
     const std::function<void(size_t, size_t)>* fn_ = nullptr;
     size_t n_ = 0, per_ = 1, next_ = 0;

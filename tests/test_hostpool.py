@@ -20,6 +20,17 @@ int main() {
             p.run(n, [=](size_t lo, size_t hi) { for (size_t i = lo; i < hi; i++) b[i] = (double)a[i]; });
             for (size_t i = 0; i < n; i++) if (out[i] != (double)in[i]) { printf("mismatch n=%zu i=%zu\n", n, i); return 1; }
         }
+    // two caller threads (one handle each in the library) share the pool: their jobs take turns
+    std::vector<double> o1(300000, -1.0), o2(200000, -1.0);
+    auto job = [&](std::vector<double>* o, double add) {
+        for (int rep = 0; rep < 50; rep++) {
+            double* b = o->data(); const size_t n = o->size();
+            p.run(n, [=](size_t lo, size_t hi) { for (size_t i = lo; i < hi; i++) b[i] = (double)i + add + rep; });
+            for (size_t i = 0; i < n; i++) if (b[i] != (double)i + add + rep) { printf("concurrent mismatch\n"); exit(3); }
+        }
+    };
+    std::thread t1(job, &o1, 0.5), t2(job, &o2, 0.25);
+    t1.join(); t2.join();
     printf("ok\n");
     return 0;
 }
