@@ -19,7 +19,7 @@ whole batch = one launch of the fused env-step kernel.
             tiny by construction; `issue` carries the figure that actually
             bounds it (fp32 issue slots).
 `cpu_baseline`: the oracle port of the reference algorithm on this box's host cores (rank 0, N=1), same tick as the GPU arm.
-`collective` (N>1), `config4_ars_sweep`, `bullet_order` (N=1): see run_ours.
+`collective` (N>1), `config4_ars_sweep`, `config3_ppo_rollout`, `bullet_order`, `manifold` (N=1): see run_ours.
 """
 from __future__ import annotations
 
@@ -488,11 +488,22 @@ def run_ours(args):
             em.close()
             return out
 
+        def leg_config3():
+            # config 3 of BASELINE.json: PPO rollout collection, 65 536 environments, the ppo/train.py policy in torch (fp32), 20-step
+            # rollouts written in place into the rollout buffer + GAE (snk_gae), captured as one CUDA graph (tools/bench_callers.py)
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import argparse as _ap
+            import bench_callers
+            r = bench_callers.ppo(_ap.Namespace(envs=65536, rollouts=2, graph=True, tf32=False, no_validate=True))
+            return {k: r[k] for k in ("workload", "envs", "num_steps", "env_steps_per_s", "ms_per_rollout", "env_steps_per_s_env_only", "ms_policy_and_gae_only")}
+
         if world == 1:
             side_leg("hbm_bound_kernels", leg_hbm)
         if world == 1 and not args.no_bullet_order:
             side_leg("bullet_order", leg_bullet_order)
             side_leg("manifold", leg_manifold)
+        if world == 1 and not args.no_config4:
+            side_leg("config3_ppo_rollout", leg_config3)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             nb = 2048 * threads  # ~10 s of CPU work per leg

@@ -112,11 +112,12 @@ def ppo(args):
             _, nv = net(buf.obs[T]); buf.gae(nv.squeeze(-1))
 
     ms_env = timed(env_only, 2); ms_pol = timed(policy_only, 2)
-    print(json.dumps({"workload": "PPO rollout collection + GAE (snk_gae), ppo/train.py policy in torch, device-resident RolloutBuffer, " + mode + (", no synchronising argument checks in the policy" if fast else "") + (", tf32 matmul" if args.tf32 else ""), "envs": n, "num_steps": T,
+    env.close()
+    return ({"workload": "PPO rollout collection + GAE (snk_gae), ppo/train.py policy in torch, device-resident RolloutBuffer, " + mode + (", no synchronising argument checks in the policy" if fast else "") + (", tf32 matmul" if args.tf32 else ""), "envs": n, "num_steps": T,
                       "rollouts": args.rollouts, "env_steps_per_s": n * T / (ms * 1e-3), "ms_per_rollout": ms,
                       "ms_env_steps_only": ms_env, "env_steps_per_s_env_only": n * T / (ms_env * 1e-3), "ms_policy_and_gae_only": ms_pol,
                       "ratio_to_env_only": ms_env / ms,
-                      "mean_reward": float(rew.mean()), "done_rate": float(done.float().mean()), "n_gpus": 1}))
+                      "mean_reward": float(rew.mean()), "done_rate": float(done.float().mean()), "n_gpus": 1})
 
 
 def ars(args):
@@ -217,4 +218,6 @@ if __name__ == "__main__":
     ap.add_argument("--tf32", action="store_true", help="ppo: TF32 tensor-core matmuls in the policy")
     ap.add_argument("--no-validate", action="store_true", help="ppo: torch.distributions argument validation off (no per-step synchronisation)")
     a = ap.parse_args()
-    {"ppo": ppo, "ars": ars}[a.workload](a)
+    res = {"ppo": ppo, "ars": ars}[a.workload](a)
+    if res is not None:
+        print(json.dumps(res))
