@@ -503,6 +503,9 @@ static int step_host_f64_flags(snk_handle* h, const double* actions_host, double
     RowSink sink;
     sink.obs_src = h->h_obs; sink.rew_src = h->h_rew; sink.done_src = h->h_done; sink.ticks_src = h->h_ticks;
     sink.obs = obs_host; sink.rew = rew_host; sink.done = done_host; sink.ticks = ticks_host; sink.obs_dim = SNK_OBS_DIM;
+    static int nt = -1; // SNK_HOST_NT=0: plain stores for the widened rows (ablation)
+    if (nt < 0) { const char* e = getenv("SNK_HOST_NT"); nt = !(e && e[0] == '0'); }
+    sink.stream = nt != 0;
     std::atomic<int> launch_state{ROWS_IN_FLIGHT};
     std::atomic<int> sync_error{(int)cudaSuccess};
     static int prefault = -1;

@@ -13,6 +13,31 @@
 
 #include <atomic>
 #include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
+// One observation row float32 -> float64.  The caller's array is written once and not read again by these threads: with SSE2 and a
+// 16-byte aligned destination the doubles go out as streaming stores (no read-for-ownership of the destination lines -- the widening
+// is bound by host memory traffic when eight ranks share a box).  `stream` = false or no SSE2: plain stores.
+static inline void row_widen(const float* src, double* dst, int n, bool stream) {
+#if defined(__SSE2__)
+    if (stream && (((uintptr_t)dst & 15u) == 0) && (n % 4) == 0) {
+        for (int c = 0; c < n; c += 4) {
+            const __m128 v = _mm_loadu_ps(src + c);
+            _mm_stream_pd(dst + c, _mm_cvtps_pd(v));
+            _mm_stream_pd(dst + c + 2, _mm_cvtps_pd(_mm_movehl_ps(v, v)));
+        }
+        return;
+    }
+#endif
+    for (int c = 0; c < n; c++) dst[c] = (double)src[c];
+}
+static inline void rows_widen_done() {
+#if defined(__SSE2__)
+    _mm_sfence(); // streaming stores become visible before the thread reports its range as done
+#endif
+}
 
 enum { ROWS_IN_FLIGHT = 0, ROWS_ALL_POSTED = 1, ROWS_LAUNCH_FAILED = 2, ROWS_MISSING = 3 };
 
@@ -20,6 +45,7 @@ struct RowSink {
     const float* obs_src; const float* rew_src; const uint8_t* done_src; const int32_t* ticks_src; // the mapped buffers the producer writes
     double* obs; double* rew; uint8_t* done; int32_t* ticks;                                       // the caller's arrays (ticks may be null)
     int obs_dim;
+    bool stream; // streaming stores for the observation rows (row_widen)
 };
 
 // Widen the rows [b, e).  `state` is shared by all consumer threads of the call (ROWS_IN_FLIGHT at the start).  query(): 0 while the
@@ -43,9 +69,7 @@ static inline void rows_widen_as_posted(const RowSink& s, size_t b, size_t e, st
             const int32_t t = *(volatile const int32_t*)(s.ticks_src + i);
             if (t < 0) { pend[w++] = (uint32_t)i; continue; }
             std::atomic_thread_fence(std::memory_order_acquire); // the row was posted before its ticks word
-            const float* src = s.obs_src + i * s.obs_dim;
-            double* dst = s.obs + i * s.obs_dim;
-            for (int c = 0; c < s.obs_dim; c++) dst[c] = (double)src[c];
+            row_widen(s.obs_src + i * s.obs_dim, s.obs + i * s.obs_dim, s.obs_dim, s.stream);
             s.rew[i] = (double)s.rew_src[i];
             s.done[i] = s.done_src[i];
             if (s.ticks) s.ticks[i] = t;
@@ -53,8 +77,8 @@ static inline void rows_widen_as_posted(const RowSink& s, size_t b, size_t e, st
         const size_t converted = np - w;
         np = w;
         if (!np) break;
-        if (before == ROWS_LAUNCH_FAILED || before == ROWS_MISSING) return;
-        if (before == ROWS_ALL_POSTED) { state.store(ROWS_MISSING, std::memory_order_release); return; } // finished before this pass, and a word is still -1
+        if (before == ROWS_LAUNCH_FAILED || before == ROWS_MISSING) { rows_widen_done(); return; }
+        if (before == ROWS_ALL_POSTED) { rows_widen_done(); state.store(ROWS_MISSING, std::memory_order_release); return; } // finished before this pass, and a word is still -1
         if (leader) {
             const int q = query();
             if (q > 0) state.store(ROWS_ALL_POSTED, std::memory_order_release);
@@ -62,6 +86,7 @@ static inline void rows_widen_as_posted(const RowSink& s, size_t b, size_t e, st
         }
         if (converted == 0) { struct timespec ts = {0, 30000}; nanosleep(&ts, nullptr); } // nothing new: leave the memory bus alone for 30 us
     }
+    rows_widen_done();
     if (leader && state.load(std::memory_order_acquire) == ROWS_IN_FLIGHT) // the other threads rely on the leader to notice a failed launch
         state.store(wait() > 0 ? ROWS_ALL_POSTED : ROWS_LAUNCH_FAILED, std::memory_order_release);
 }

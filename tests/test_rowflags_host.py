@@ -38,7 +38,7 @@ static int run_case(size_t n, int mode, unsigned seed) { // mode 0: all rows pos
     });
     RowSink s;
     s.obs_src = ho.data(); s.rew_src = hr.data(); s.done_src = hd.data(); s.ticks_src = ht.data();
-    s.obs = obs.data(); s.rew = rew.data(); s.done = done.data(); s.ticks = ticks.data(); s.obs_dim = D;
+    s.obs = obs.data(); s.rew = rew.data(); s.done = done.data(); s.ticks = ticks.data(); s.obs_dim = D; s.stream = (seed & 1) != 0;
     std::atomic<int> state{ROWS_IN_FLIGHT};
     HostPool::get().run(n, [&](size_t b, size_t e) {
         rows_widen_as_posted(s, b, e, state, b == 0, true,
